@@ -1,0 +1,105 @@
+/*
+ * leastereo_b200 - C ABI of the B200-native LEAStereo hot path (cost volume -> 3D MatchingNet -> disparity head).
+ *
+ * The reference (devmentality/LEAStereo) is pure Python/PyTorch and has no FFI of its own: its only
+ * boundary is the nn.Module API.  The entry points below are what a binding for that path would call; each cites
+ * the reference lines whose arithmetic it replaces.  INTEGRATION.md shows the ctypes stub a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into memory owned by the caller (PyTorch allocates, keeps alive until the
+ *     stream has passed); nothing is allocated, freed or synchronised inside the library;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are launched on it, on the current device;
+ *   - return value: 0 = ok, non-zero = error (message via lea_last_error(), thread-local);
+ *   - no torch types, no C++ types, no ownership transfer.
+ *
+ * "Planes volume" (lea_vol): the activation layout of the 3D net.  A logical fp32 tensor (B, C, D, H, W) is stored
+ * as P bf16 planes (hi, lo[, lo2]) with value = sum of planes (P=2: 16 significant bits, the bf16x3 split-precision
+ * operand; P=3: exact fp32), channel-blocked by 8 so that one (voxel, 8-channel, plane) group is a 16-byte UMMA
+ * core-matrix row:
+ *        element (b, c, p, d, h, w) lives at  (((((b*(C/8) + c/8)*P + p)*D + d)*H + h)*W + w)*8 + c%8      [bf16]
+ */
+#ifndef LEASTEREO_B200_H_
+#define LEASTEREO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEA_ABI_VERSION 1
+
+typedef struct lea_vol {
+    void*   data;          /* bf16 planes volume, 16-byte aligned                                   */
+    int32_t B, C, P;       /* batch, TOTAL channels of the buffer (multiple of 8), planes (1..3)    */
+    int32_t D, H, W;       /* spatial extent                                                        */
+} lea_vol;
+
+/* One ConvBR (models/operations_3d.py:31-47): Conv3d(k in {1,3}, stride 1, pad (k-1)/2, no bias) -> optional
+ * BatchNorm (eval: y = x*scale + shift, scale/shift precomputed by the host from gamma/beta/running stats, eps 1e-5)
+ * -> optional ReLU -> optional "+ res" (the state sum of retrain/skip_model_3d.py:70) -> written into a channel
+ * slice of a planes volume (the concat of skip_model_3d.py:74 is a slice write) or as plain fp32 NCDHW. */
+typedef struct lea_conv {
+    lea_vol      src;      int32_t src_c0;   /* input volume and first input channel                         */
+    int32_t      c_in, c_out, ksize;         /* c_in % 8 == 0; c_out % 8 == 0 unless dst_f32 != NULL         */
+    const float* bn_scale;                   /* [c_out] or NULL                                               */
+    const float* bn_shift;                   /* [c_out] or NULL                                               */
+    int32_t      relu;
+    int32_t      has_res;  lea_vol res;      int32_t res_c0;   /* summand added after BN/ReLU                 */
+    lea_vol      dst;      int32_t dst_c0;   /* planes output (used when dst_f32 == NULL)                     */
+    float*       dst_f32;                    /* fp32 (B, c_out, D, H, W) output when non-NULL                 */
+} lea_conv;
+
+int         lea_abi_version(void);
+const char* lea_last_error(void);
+/* 1 if this build contains device code (0 for the CPU emulation used by the no-GPU unit tests). */
+int         lea_is_device_build(void);
+
+/* ---- cost volume: retrain/LEAStereo.py:34-48 --------------------------------------------------------------- */
+/* fp32 reference layout, bit-exact: cost (B, 2C, D3, H, W); x, y (B, C, H, W). */
+int lea_cost_volume_f32(const float* x, const float* y, float* cost,
+                        int32_t B, int32_t C, int32_t H, int32_t W, int32_t D3, void* stream);
+/* same volume written straight into the planes layout that stem0 consumes (vol.C == 2C). */
+int lea_cost_volume_planes(const float* x, const float* y, const lea_vol* vol,
+                           int32_t C, void* stream);
+/* feature maps (B, C, H, W) fp32 -> 2-D planes volume (D == 1) used by the fused-cost-volume stem0 loader. */
+int lea_pack_planes(const float* src, const lea_vol* dst, int32_t dst_c0, int32_t c, void* stream);
+int lea_unpack_planes(const lea_vol* src, int32_t src_c0, int32_t c, float* dst, void* stream);
+
+/* ---- trilinear resample, align_corners=True: retrain/skip_model_3d.py:44-51, :162-169 ----------------------- */
+int lea_trilinear_ac(const lea_vol* src, int32_t src_c0, const lea_vol* dst, int32_t dst_c0, int32_t c,
+                     void* stream);
+
+/* ---- ConvBR -------------------------------------------------------------------------------------------------- */
+/* fp32-FMA kernel; weight = PyTorch layout fp32 (c_out, c_in, k, k, k). */
+int lea_conv3d_simt(const lea_conv* p, const float* weight, void* stream);
+
+/* tcgen05/TMEM implicit-GEMM kernel (sm_100a).  wimg = image produced by lea_pack_weights_tc. */
+int64_t lea_tc_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t ksize, int32_t planes);
+int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
+                        int32_t planes, void* stream);
+/* mma_terms: 1 = single-pass bf16 (hi*hi), 0 = full triangular split for the volume's P (P=2: bf16x3, P=3: bf16x6).
+ * fused_cv: when non-zero, src is ignored and the operand loader builds the cost volume on the fly from the two
+ * 2-D planes volumes fx/fy (retrain/LEAStereo.py:34-48 fused into stem0; the volume is never materialised). */
+typedef struct lea_tc_opts {
+    int32_t mma_terms;
+    int32_t fused_cv;  lea_vol fx, fy;  int32_t d3;
+    int32_t num_sms;   /* 0 = query */
+} lea_tc_opts;
+int lea_conv3d_tc(const lea_conv* p, const void* wimg, const lea_tc_opts* opts, void* stream);
+/* self-test of the tcgen05 path on a synthetic GEMM-shaped conv; returns 0 when it matches the SIMT kernel. */
+int lea_tc_selftest(int32_t verbose, void* stream);
+
+/* ---- disparity head: models/build_model_2d.py:27-57 ------------------------------------------------------------ */
+/* mat (B, D3, H3, W3) fp32 -> disp (B, 3*H3, 3*W3) fp32; upsample + softmin + regression in one kernel. */
+int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D3, int32_t H3, int32_t W3,
+                  int32_t maxdisp, void* stream);
+/* DisparityRegression alone (build_model_2d.py:36-41): p (B, maxdisp, H, W) -> (B, H, W). */
+int lea_disparity_regression(const float* p, float* out, int32_t B, int32_t maxdisp, int32_t H, int32_t W,
+                             void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEASTEREO_B200_H_ */

@@ -1,0 +1,153 @@
+// C-ABI entry points of the CUDA-core kernels (argument validation + launch).  Included by leastereo_b200.cu
+// (nvcc, the product) and by tests/emu/emu_lib.cpp (g++, CPU emulation for the no-GPU unit tests).
+
+static int lea_check_vol(const lea_vol* v, const char* what) {
+    LEA_CHECK(v != nullptr && v->data != nullptr, "%s: null volume", what);
+    LEA_CHECK(v->B > 0 && v->D > 0 && v->H > 0 && v->W > 0, "%s: empty volume", what);
+    LEA_CHECK(v->C > 0 && (v->C & 7) == 0, "%s: channel count %d is not a multiple of 8", what, v->C);
+    LEA_CHECK(v->P >= 1 && v->P <= 3, "%s: planes must be 1..3 (got %d)", what, v->P);
+    LEA_CHECK((((uintptr_t)v->data) & 15) == 0, "%s: data pointer is not 16-byte aligned", what);
+    LEA_CHECK((int64_t)v->D * v->H <= 65535, "%s: D*H = %lld exceeds the launch grid limit", what,
+              (long long)v->D * v->H);
+    return 0;
+}
+static int lea_check_slice(const lea_vol* v, int c0, int c, const char* what) {
+    LEA_CHECK((c0 & 7) == 0 && (c & 7) == 0 && c > 0, "%s: channel slice [%d,+%d) must be 8-aligned", what, c0, c);
+    LEA_CHECK(c0 >= 0 && c0 + c <= v->C, "%s: channel slice [%d,+%d) outside %d channels", what, c0, c, v->C);
+    return 0;
+}
+static bool lea_same_space(const lea_vol* a, const lea_vol* b) {
+    return a->B == b->B && a->D == b->D && a->H == b->H && a->W == b->W;
+}
+
+extern "C" int lea_cost_volume_f32(const float* x, const float* y, float* cost,
+                                   int32_t B, int32_t C, int32_t H, int32_t W, int32_t D3, void* stream) {
+    LEA_CHECK(B > 0 && C > 0 && H > 0 && W > 0 && D3 >= 0, "cost_volume_f32: bad shape");
+    if (D3 == 0) return 0;                                   // int(maxdisp/3) == 0 -> empty volume, nothing to write
+    LEA_CHECK(x && y && cost, "cost_volume_f32: null pointer");
+    LEA_CHECK((int64_t)2 * C * D3 <= 65535 && B <= 65535, "cost_volume_f32: grid too large");
+    const bool vec = (W % 4 == 0) && ((((uintptr_t)cost) & 15) == 0);
+    if (vec) {
+        const int hw4 = H * (W / 4);
+        const int chunks = (hw4 + 1023) / 1024;
+        LEA_LAUNCH(lea_cost_volume_f32_kernel, dim3(chunks, 2 * C * D3, B), dim3(256), 0, stream,
+                   x, y, cost, C, H, W, D3, hw4, chunks);
+    } else {
+        LEA_LAUNCH(lea_cost_volume_f32_scalar_kernel, dim3((H * W + 255) / 256, 2 * C * D3, B), dim3(256), 0, stream,
+                   x, y, cost, C, H, W, D3);
+    }
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_cost_volume_planes(const float* x, const float* y, const lea_vol* vol, int32_t C, void* stream) {
+    LEA_CHECK(x && y, "cost_volume_planes: null pointer");
+    if (lea_check_vol(vol, "cost_volume_planes")) return 1;
+    LEA_CHECK(C > 0 && (C & 7) == 0 && vol->C == 2 * C, "cost_volume_planes: volume must have 2C channels, C%%8==0");
+    LEA_CHECK((int64_t)vol->B * (vol->C >> 3) <= 65535, "cost_volume_planes: grid too large");
+    LEA_LAUNCH(lea_cost_volume_planes_kernel, dim3((vol->W + 255) / 256, vol->D * vol->H, vol->B * (vol->C >> 3)),
+               dim3(256), 0, stream, x, y, *vol, C);
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_pack_planes(const float* src, const lea_vol* dst, int32_t dst_c0, int32_t c, void* stream) {
+    LEA_CHECK(src, "pack_planes: null pointer");
+    if (lea_check_vol(dst, "pack_planes") || lea_check_slice(dst, dst_c0, c, "pack_planes")) return 1;
+    LEA_CHECK((int64_t)dst->B * (c >> 3) <= 65535, "pack_planes: grid too large");
+    LEA_LAUNCH(lea_pack_planes_kernel, dim3((dst->W + 255) / 256, dst->D * dst->H, dst->B * (c >> 3)), dim3(256), 0,
+               stream, src, *dst, dst_c0, c);
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_unpack_planes(const lea_vol* src, int32_t src_c0, int32_t c, float* dst, void* stream) {
+    LEA_CHECK(dst, "unpack_planes: null pointer");
+    if (lea_check_vol(src, "unpack_planes") || lea_check_slice(src, src_c0, c, "unpack_planes")) return 1;
+    LEA_CHECK((int64_t)src->B * (c >> 3) <= 65535, "unpack_planes: grid too large");
+    LEA_LAUNCH(lea_unpack_planes_kernel, dim3((src->W + 255) / 256, src->D * src->H, src->B * (c >> 3)), dim3(256), 0,
+               stream, *src, src_c0, c, dst);
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_trilinear_ac(const lea_vol* src, int32_t src_c0, const lea_vol* dst, int32_t dst_c0, int32_t c,
+                                void* stream) {
+    if (lea_check_vol(src, "trilinear_ac src") || lea_check_vol(dst, "trilinear_ac dst")) return 1;
+    if (lea_check_slice(src, src_c0, c, "trilinear_ac src") || lea_check_slice(dst, dst_c0, c, "trilinear_ac dst"))
+        return 1;
+    LEA_CHECK(src->B == dst->B, "trilinear_ac: batch mismatch");
+    LEA_CHECK((int64_t)dst->B * (c >> 3) <= 65535, "trilinear_ac: grid too large");
+    LEA_LAUNCH(lea_trilinear_ac_kernel, dim3((dst->W + 127) / 128, dst->D * dst->H, dst->B * (c >> 3)), dim3(128), 0,
+               stream, *src, src_c0, *dst, dst_c0, c);
+    return LEA_POST_LAUNCH();
+}
+
+static int lea_check_conv(const lea_conv* p, const char* what) {
+    LEA_CHECK(p != nullptr, "%s: null params", what);
+    if (lea_check_vol(&p->src, what) || lea_check_slice(&p->src, p->src_c0, p->c_in, what)) return 1;
+    LEA_CHECK(p->ksize == 1 || p->ksize == 3, "%s: kernel size %d not supported (1 or 3)", what, p->ksize);
+    LEA_CHECK(p->c_out >= 1 && p->c_out <= 64, "%s: c_out %d outside 1..64", what, p->c_out);
+    LEA_CHECK((p->bn_scale == nullptr) == (p->bn_shift == nullptr), "%s: bn_scale/bn_shift must come together", what);
+    if (p->dst_f32 == nullptr) {
+        if (lea_check_vol(&p->dst, what) || lea_check_slice(&p->dst, p->dst_c0, p->c_out, what)) return 1;
+        LEA_CHECK(lea_same_space(&p->src, &p->dst), "%s: src/dst spatial shapes differ", what);
+        if (p->has_res) {
+            if (lea_check_vol(&p->res, what) || lea_check_slice(&p->res, p->res_c0, p->c_out, what)) return 1;
+            LEA_CHECK(lea_same_space(&p->src, &p->res), "%s: src/res spatial shapes differ", what);
+        }
+    } else {
+        LEA_CHECK(!p->has_res, "%s: residual add is not available with fp32 output", what);
+    }
+    return 0;
+}
+
+template <int NPAD>
+static int lea_launch_conv_simt(const lea_conv* p, const float* weight, void* stream) {
+    const int tiles = ((p->src.W + LEA_TW - 1) / LEA_TW) * ((p->src.H + LEA_TH - 1) / LEA_TH);
+    const dim3 grid(tiles, p->src.D, p->src.B);
+    if (p->ksize == 3) {
+        const size_t smem = (size_t)(8 * 3 * (LEA_TH + 2) * (LEA_TW + 2) + 216 * NPAD) * sizeof(float);
+#ifndef LEA_CPU_EMU
+        if (smem > 48 * 1024)   // per device, cheap; DataParallel replicas live on several devices
+            cudaFuncSetAttribute(lea_conv3_simt_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+        LEA_LAUNCH(lea_conv3_simt_kernel<NPAD>, grid, dim3(128), smem, stream, *p, weight);
+    } else {
+        const size_t smem = (size_t)p->c_in * NPAD * sizeof(float);
+        LEA_CHECK(smem <= 48 * 1024, "conv3d_simt: 1x1x1 weights (%d x %d) do not fit shared memory", p->c_in, NPAD);
+        LEA_LAUNCH(lea_conv1_simt_kernel<NPAD>, grid, dim3(128), smem, stream, *p, weight);
+    }
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_conv3d_simt(const lea_conv* p, const float* weight, void* stream) {
+    if (lea_check_conv(p, "conv3d_simt")) return 1;
+    LEA_CHECK(weight != nullptr, "conv3d_simt: null weight");
+    LEA_CHECK(p->src.B <= 65535 && p->src.D <= 65535, "conv3d_simt: grid too large");
+    if (p->c_out <= 8)  return lea_launch_conv_simt<8>(p, weight, stream);
+    if (p->c_out <= 16) return lea_launch_conv_simt<16>(p, weight, stream);
+    if (p->c_out <= 32) return lea_launch_conv_simt<32>(p, weight, stream);
+    return lea_launch_conv_simt<64>(p, weight, stream);
+}
+
+extern "C" int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D3, int32_t H3, int32_t W3,
+                             int32_t maxdisp, void* stream) {
+    LEA_CHECK(mat && disp, "disp_head: null pointer");
+    LEA_CHECK(B > 0 && D3 > 0 && H3 > 0 && W3 > 0 && maxdisp > 0 && B <= 65535, "disp_head: bad shape");
+    const size_t smem = (size_t)D3 * (LEA_DH_TH3 + 2) * (LEA_DH_TW3 + 2) * sizeof(float);
+    LEA_CHECK(smem <= 200 * 1024, "disp_head: D3 = %d needs %zu bytes of shared memory", D3, smem);
+#ifndef LEA_CPU_EMU
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(lea_disp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    const int tiles = ((W3 + LEA_DH_TW3 - 1) / LEA_DH_TW3) * ((H3 + LEA_DH_TH3 - 1) / LEA_DH_TH3);
+    LEA_LAUNCH(lea_disp_head_kernel, dim3(tiles, B), dim3(9 * LEA_DH_TH3 * LEA_DH_TW3), smem, stream,
+               mat, disp, D3, H3, W3, maxdisp);
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_disparity_regression(const float* p, float* out, int32_t B, int32_t maxdisp, int32_t H, int32_t W,
+                                        void* stream) {
+    LEA_CHECK(p && out, "disparity_regression: null pointer");
+    LEA_CHECK(B > 0 && maxdisp > 0 && H > 0 && W > 0 && B <= 65535, "disparity_regression: bad shape");
+    LEA_LAUNCH(lea_disparity_regression_kernel, dim3((H * W + 255) / 256, B), dim3(256), 0, stream,
+               p, out, maxdisp, H * W);
+    return LEA_POST_LAUNCH();
+}

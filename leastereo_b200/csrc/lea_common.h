@@ -1,0 +1,117 @@
+// Shared host/device helpers: build-mode shim, bf16 plane splitting, planes-volume indexing.
+//
+// The SIMT kernels in lea_simt_kernels.cuh are written against this header so that the SAME source compiles
+//   (a) with nvcc for sm_100a (the product), and
+//   (b) with g++ under -DLEA_CPU_EMU (tests/emu: a thread-per-CUDA-thread emulator used ONLY by the no-GPU unit
+//       tests to check index math before GPU time is spent; never loaded by the leastereo_b200 package).
+#pragma once
+
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+
+#include "../../include/leastereo_b200.h"
+
+#ifdef LEA_CPU_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#define LEA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define LEA_HD __host__ __device__ __forceinline__
+#define LEA_D __device__ __forceinline__
+#endif
+
+// ---------------------------------------------------------------------------------------------------------
+// bf16 <-> fp32 by bit manipulation (identical on host, device and emulator; round-to-nearest-even)
+// ---------------------------------------------------------------------------------------------------------
+LEA_HD uint32_t lea_f32_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4); return u;
+#endif
+}
+LEA_HD float lea_bits_f32(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+LEA_HD uint16_t lea_f32_to_bf16(float f) {
+    uint32_t u = lea_f32_bits(f);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN stays NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+LEA_HD float lea_bf16_to_f32(uint16_t h) { return lea_bits_f32(((uint32_t)h) << 16); }
+
+// Split x into up to 3 bf16 planes with x ~= p0 + p1 + p2 (P=3 is exact for normal fp32 values).
+LEA_HD void lea_split_planes(float x, int P, uint16_t* out /*[3]*/) {
+    uint16_t h0 = lea_f32_to_bf16(x);
+    out[0] = h0; out[1] = 0; out[2] = 0;
+    if (P < 2) return;
+    if ((h0 & 0x7f80u) == 0x7f80u) return;                     // inf / NaN: no residual planes
+    float r1 = x - lea_bf16_to_f32(h0);
+    uint16_t h1 = lea_f32_to_bf16(r1);
+    out[1] = h1;
+    if (P < 3) return;
+    float r2 = r1 - lea_bf16_to_f32(h1);
+    out[2] = lea_f32_to_bf16(r2);
+}
+
+// 8 bf16 values = one 16-byte group
+struct __attribute__((aligned(16))) lea_u4 { uint32_t x, y, z, w; };
+
+LEA_HD void lea_unpack8(const lea_u4& v, float* f /*[8]*/, bool accumulate) {
+    const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float lo = lea_bits_f32(q[i] << 16);
+        float hi = lea_bits_f32(q[i] & 0xffff0000u);
+        if (accumulate) { f[2 * i] += lo; f[2 * i + 1] += hi; }
+        else            { f[2 * i] = lo;  f[2 * i + 1] = hi; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// planes-volume indexing (see include/leastereo_b200.h)
+// ---------------------------------------------------------------------------------------------------------
+// index, in 16-byte groups, of (b, channel-block cb, plane p, d, h, w)
+LEA_HD int64_t lea_vol_group(const lea_vol& v, int b, int cb, int p, int d, int h, int w) {
+    return ((((((int64_t)b * (v.C >> 3) + cb) * v.P + p) * v.D + d) * v.H + h) * (int64_t)v.W + w);
+}
+LEA_HD int64_t lea_vol_plane_stride(const lea_vol& v) { return (int64_t)v.D * v.H * v.W; }   // in groups
+
+// read 8 channels of one voxel as fp32 (sum of planes)
+LEA_HD void lea_vol_load8(const lea_vol& v, int b, int cb, int d, int h, int w, float* f) {
+    const lea_u4* base = (const lea_u4*)v.data;
+    int64_t g = lea_vol_group(v, b, cb, 0, d, h, w);
+    const int64_t ps = lea_vol_plane_stride(v);
+    lea_unpack8(base[g], f, false);
+    for (int p = 1; p < v.P; ++p) lea_unpack8(base[g + p * ps], f, true);
+}
+// write 8 channels of one voxel, splitting into the volume's planes
+LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w, const float* f) {
+    lea_u4* base = (lea_u4*)v.data;
+    int64_t g = lea_vol_group(v, b, cb, 0, d, h, w);
+    const int64_t ps = lea_vol_plane_stride(v);
+    uint32_t q[3][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint16_t a[3], c[3];
+        lea_split_planes(f[2 * i], v.P, a);
+        lea_split_planes(f[2 * i + 1], v.P, c);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) q[p][i] = (uint32_t)a[p] | ((uint32_t)c[p] << 16);
+    }
+    for (int p = 0; p < v.P; ++p) {
+        lea_u4 o; o.x = q[p][0]; o.y = q[p][1]; o.z = q[p][2]; o.w = q[p][3];
+        base[g + p * ps] = o;
+    }
+}
+
+// error reporting shared by every API translation unit
+void lea_set_error(const char* fmt, ...);
+#define LEA_CHECK(cond, ...) do { if (!(cond)) { lea_set_error(__VA_ARGS__); return 1; } } while (0)

@@ -1,0 +1,413 @@
+// CUDA-core kernels of the LEAStereo hot path: cost-volume gather, planes pack/unpack, trilinear resample
+// (align_corners=True), fp32-FMA ConvBR (k = 1, 3), fused disparity head, disparity regression.
+// Reference arithmetic being replaced is cited per kernel.  Compiles with nvcc (sm_100a) and, for the no-GPU
+// index-math tests, with g++ -DLEA_CPU_EMU (see lea_common.h).
+#pragma once
+#include "lea_common.h"
+
+#ifndef LEA_CPU_EMU
+#define LEA_DYN_SMEM(type, name) extern __shared__ __align__(16) unsigned char lea_smem_raw_[]; \
+                                 type* name = reinterpret_cast<type*>(lea_smem_raw_)
+#endif
+
+// =========================================================================================================
+// K1  cost volume, reference layout (retrain/LEAStereo.py:34-48), bit-exact copy:
+//       cost[b, c,   d, h, w] = x[b, c, h, w]      if w >= d else 0
+//       cost[b, C+c, d, h, w] = y[b, c, h, w - d]  if w >= d else 0
+//     One thread produces 4 consecutive w of one (b, c2, d) plane and stores them as one 128-bit word.
+//     HBM-bound on the write: 4*(2C*H*W + 2C*D3*H*W) algorithmic bytes per pair.
+// =========================================================================================================
+__global__ void __launch_bounds__(256)
+lea_cost_volume_f32_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ cost,
+                           int C, int H, int W, int D3, int hw4 /* ceil(H*W/4) when W%4==0 */, int chunks) {
+    // grid: (chunks, 2C*D3, B); each block covers 1024 float4 of one plane
+    const int plane = blockIdx.y;               // c2 * D3 + d
+    const int c2 = plane / D3, d = plane - c2 * D3;
+    const int b = blockIdx.z;
+    const bool left = c2 < C;
+    const float* __restrict__ src = (left ? x : y) + ((int64_t)b * C + (left ? c2 : c2 - C)) * H * W;
+    float* __restrict__ dst = cost + (((int64_t)b * 2 * C + c2) * D3 + d) * (int64_t)H * W;
+    const int shift = left ? 0 : d;
+    const int w4n = W >> 2;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+        const int q = (blockIdx.x * 4 + it) * 256 + threadIdx.x;       // float4 index inside the plane
+        if (q >= hw4) break;
+        const int h = q / w4n;
+        const int w = (q - h * w4n) << 2;
+        const float* __restrict__ row = src + (int64_t)h * W;
+        float4 v;
+        v.x = (w + 0 >= d) ? __ldg(row + (w + 0 - shift)) : 0.0f;
+        v.y = (w + 1 >= d) ? __ldg(row + (w + 1 - shift)) : 0.0f;
+        v.z = (w + 2 >= d) ? __ldg(row + (w + 2 - shift)) : 0.0f;
+        v.w = (w + 3 >= d) ? __ldg(row + (w + 3 - shift)) : 0.0f;
+        *reinterpret_cast<float4*>(dst + (int64_t)h * W + w) = v;
+    }
+    (void)chunks;
+}
+
+// scalar variant for W % 4 != 0 (ragged widths); one thread per output element
+__global__ void __launch_bounds__(256)
+lea_cost_volume_f32_scalar_kernel(const float* __restrict__ x, const float* __restrict__ y,
+                                  float* __restrict__ cost, int C, int H, int W, int D3) {
+    const int plane = blockIdx.y;
+    const int c2 = plane / D3, d = plane - c2 * D3;
+    const int b = blockIdx.z;
+    const bool left = c2 < C;
+    const float* __restrict__ src = (left ? x : y) + ((int64_t)b * C + (left ? c2 : c2 - C)) * H * W;
+    float* __restrict__ dst = cost + (((int64_t)b * 2 * C + c2) * D3 + d) * (int64_t)H * W;
+    const int shift = left ? 0 : d;
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= H * W) return;
+    const int h = q / W, w = q - h * W;
+    dst[q] = (w >= d) ? __ldg(src + (int64_t)h * W + (w - shift)) : 0.0f;
+}
+
+// K1b  same volume written in the planes layout stem0 consumes.  One thread = one (b, cb, d, h, w) 8-channel group.
+__global__ void __launch_bounds__(256)
+lea_cost_volume_planes_kernel(const float* __restrict__ x, const float* __restrict__ y, lea_vol vol, int C) {
+    const int W = vol.W, H = vol.H;
+    const int w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= W) return;
+    const int h = blockIdx.y % H;
+    const int d = blockIdx.y / H;
+    const int cbn = vol.C >> 3;
+    const int b = blockIdx.z / cbn, cb = blockIdx.z - b * cbn;
+    const bool left = cb < (C >> 3);
+    const int c0 = (left ? cb : cb - (C >> 3)) * 8;
+    const float* __restrict__ src = (left ? x : y) + (((int64_t)b * C + c0) * H + h) * W;
+    const int sw = left ? w : w - d;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (w >= d) ? __ldg(src + (int64_t)j * H * W + sw) : 0.0f;
+    lea_vol_store8(vol, b, cb, d, h, w, f);
+}
+
+// =========================================================================================================
+// planes pack / unpack: fp32 (B, c, D, H, W) <-> channel slice [c0, c0+c) of a planes volume
+// =========================================================================================================
+__global__ void __launch_bounds__(256)
+lea_pack_planes_kernel(const float* __restrict__ src, lea_vol dst, int dst_c0, int c) {
+    const int w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= dst.W) return;
+    const int h = blockIdx.y % dst.H, d = blockIdx.y / dst.H;
+    const int cbn = c >> 3;
+    const int b = blockIdx.z / cbn, cb = blockIdx.z - b * cbn;
+    const int64_t sp = (int64_t)dst.D * dst.H * dst.W;
+    const float* __restrict__ s = src + ((int64_t)b * c + cb * 8) * sp + ((int64_t)d * dst.H + h) * dst.W + w;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = __ldg(s + j * sp);
+    lea_vol_store8(dst, b, (dst_c0 >> 3) + cb, d, h, w, f);
+}
+
+__global__ void __launch_bounds__(256)
+lea_unpack_planes_kernel(lea_vol src, int src_c0, int c, float* __restrict__ dst) {
+    const int w = blockIdx.x * 256 + threadIdx.x;
+    if (w >= src.W) return;
+    const int h = blockIdx.y % src.H, d = blockIdx.y / src.H;
+    const int cbn = c >> 3;
+    const int b = blockIdx.z / cbn, cb = blockIdx.z - b * cbn;
+    const int64_t sp = (int64_t)src.D * src.H * src.W;
+    float f[8];
+    lea_vol_load8(src, b, (src_c0 >> 3) + cb, d, h, w, f);
+    float* __restrict__ o = dst + ((int64_t)b * c + cb * 8) * sp + ((int64_t)d * src.H + h) * src.W + w;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j * sp] = f[j];
+}
+
+// =========================================================================================================
+// K5  trilinear resample, align_corners=True (retrain/skip_model_3d.py:44-51, :162-169).
+//     PyTorch index rule restated: scale = (in-1)/(out-1) (0 if out == 1); src = scale*dst; i0 = min(floor(src), in-1);
+//     l1 = clamp(src - i0, 0, 1); i1 = i0 + (i0 < in-1); l0 = 1 - l1.  Equal sizes copy.
+// =========================================================================================================
+struct lea_axis_lerp { int i0, i1; float l0, l1; };
+
+LEA_HD lea_axis_lerp lea_axis_ac(int dst, int in_n, int out_n) {
+    lea_axis_lerp r;
+    if (in_n == out_n) { r.i0 = r.i1 = dst; r.l0 = 1.0f; r.l1 = 0.0f; return r; }
+    const float scale = out_n > 1 ? (float)(in_n - 1) / (float)(out_n - 1) : 0.0f;
+    const float src = scale * (float)dst;
+    int i0 = (int)floorf(src);
+    if (i0 > in_n - 1) i0 = in_n - 1;
+    float l1 = src - (float)i0;
+    l1 = l1 < 0.0f ? 0.0f : (l1 > 1.0f ? 1.0f : l1);
+    r.i0 = i0; r.i1 = i0 + (i0 < in_n - 1 ? 1 : 0); r.l0 = 1.0f - l1; r.l1 = l1;
+    return r;
+}
+
+__global__ void __launch_bounds__(128)
+lea_trilinear_ac_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c) {
+    const int w = blockIdx.x * 128 + threadIdx.x;
+    if (w >= dst.W) return;
+    const int h = blockIdx.y % dst.H, d = blockIdx.y / dst.H;
+    const int cbn = c >> 3;
+    const int b = blockIdx.z / cbn, cb = blockIdx.z - b * cbn;
+    const lea_axis_lerp ad = lea_axis_ac(d, src.D, dst.D);
+    const lea_axis_lerp ah = lea_axis_ac(h, src.H, dst.H);
+    const lea_axis_lerp aw = lea_axis_ac(w, src.W, dst.W);
+    const int scb = (src_c0 >> 3) + cb;
+    float out[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = 0.0f;
+#pragma unroll
+    for (int zd = 0; zd < 2; ++zd) {
+        const float wd = zd ? ad.l1 : ad.l0;
+        const int id = zd ? ad.i1 : ad.i0;
+        float accd[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) accd[j] = 0.0f;
+#pragma unroll
+        for (int zh = 0; zh < 2; ++zh) {
+            const float wh = zh ? ah.l1 : ah.l0;
+            const int ih = zh ? ah.i1 : ah.i0;
+            float a[8], bb[8];
+            lea_vol_load8(src, b, scb, id, ih, aw.i0, a);
+            lea_vol_load8(src, b, scb, id, ih, aw.i1, bb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) accd[j] += wh * (aw.l0 * a[j] + aw.l1 * bb[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] += wd * accd[j];
+    }
+    lea_vol_store8(dst, b, (dst_c0 >> 3) + cb, d, h, w, out);
+}
+
+// =========================================================================================================
+// K2s  ConvBR on CUDA cores, fp32 accumulate (models/operations_3d.py:31-47).  The exact-arithmetic conv of the
+//      engine ("simt" mode), the checker the tcgen05 kernel is validated against on the GPU, and the kernel for
+//      shapes tensor cores do not take.  Tile = 8 (w) x 16 (h) output voxels of one depth slice per 128-thread CTA;
+//      each thread owns one voxel and all NPAD output channels.
+// =========================================================================================================
+#define LEA_TW 8
+#define LEA_TH 16
+
+template <int NPAD>
+LEA_D void lea_conv_epilogue(const lea_conv& p, int b, int d, int h, int w, float* acc) {
+    if (h >= p.src.H || w >= p.src.W) return;
+#pragma unroll
+    for (int n = 0; n < NPAD; ++n) {
+        if (n < p.c_out) {
+            float v = acc[n];
+            if (p.bn_scale) v = v * __ldg(p.bn_scale + n) + __ldg(p.bn_shift + n);
+            if (p.relu) v = v > 0.0f ? v : 0.0f;
+            acc[n] = v;
+        }
+    }
+    if (p.dst_f32) {
+        const int64_t sp = (int64_t)p.src.D * p.src.H * p.src.W;
+        float* o = p.dst_f32 + (int64_t)b * p.c_out * sp + ((int64_t)d * p.src.H + h) * p.src.W + w;
+        for (int n = 0; n < p.c_out; ++n) o[n * sp] = acc[n];
+        return;
+    }
+#pragma unroll
+    for (int cb = 0; cb < NPAD / 8; ++cb) {
+        if (cb * 8 < p.c_out) {
+            if (p.has_res) {
+                float r[8];
+                lea_vol_load8(p.res, b, (p.res_c0 >> 3) + cb, d, h, w, r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[cb * 8 + j] += r[j];
+            }
+            lea_vol_store8(p.dst, b, (p.dst_c0 >> 3) + cb, d, h, w, acc + cb * 8);
+        }
+    }
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(128)
+lea_conv3_simt_kernel(lea_conv p, const float* __restrict__ weight) {
+    // smem: in_s[8][3][TH+2][TW+2] floats, then w_s[8][27][NPAD] floats
+    LEA_DYN_SMEM(float, smem);
+    constexpr int HH = LEA_TH + 2, WW = LEA_TW + 2, SLAB = HH * WW, HALO = 3 * SLAB;
+    float* in_s = smem;
+    float* w_s = smem + 8 * HALO;
+    const int tiles_w = (p.src.W + LEA_TW - 1) / LEA_TW;
+    const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
+    const int d = blockIdx.y, b = blockIdx.z;
+    const int w0 = tw * LEA_TW, h0 = th * LEA_TH;
+    const int tid = threadIdx.x;
+    const int lw = tid % LEA_TW, lh = tid / LEA_TW;
+    float acc[NPAD];
+#pragma unroll
+    for (int n = 0; n < NPAD; ++n) acc[n] = 0.0f;
+
+    const int ncb = p.c_in >> 3;
+    for (int cb = 0; cb < ncb; ++cb) {
+        // ---- stage the input halo (8 channels, 3 depth slabs) as fp32 ----
+        for (int v = tid; v < HALO; v += 128) {
+            const int kd = v / SLAB, r = v - kd * SLAB;
+            const int hh = r / WW, ww = r - hh * WW;
+            const int gd = d + kd - 1, gh = h0 + hh - 1, gw = w0 + ww - 1;
+            float f[8];
+            if (gd >= 0 && gd < p.src.D && gh >= 0 && gh < p.src.H && gw >= 0 && gw < p.src.W) {
+                lea_vol_load8(p.src, b, (p.src_c0 >> 3) + cb, gd, gh, gw, f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) in_s[j * HALO + v] = f[j];
+        }
+        // ---- stage the weights of these 8 input channels: w_s[(j*27+tap)*NPAD + n] ----
+        for (int e = tid; e < 216 * NPAD; e += 128) {
+            const int n = e / 216, r = e - n * 216;          // r = j*27 + tap, contiguous in the PyTorch layout
+            float wv = 0.0f;
+            if (n < p.c_out) wv = __ldg(weight + ((int64_t)n * p.c_in + cb * 8) * 27 + r);
+            w_s[r * NPAD + n] = wv;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll 1
+            for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float a = in_s[j * HALO + kd * SLAB + (lh + kh) * WW + (lw + kw)];
+                        const float4* wr = reinterpret_cast<const float4*>(
+                            w_s + (j * 27 + kd * 9 + kh * 3 + kw) * NPAD);
+#pragma unroll
+                        for (int n4 = 0; n4 < NPAD / 4; ++n4) {
+                            const float4 wv = wr[n4];
+                            acc[n4 * 4 + 0] += a * wv.x;
+                            acc[n4 * 4 + 1] += a * wv.y;
+                            acc[n4 * 4 + 2] += a * wv.z;
+                            acc[n4 * 4 + 3] += a * wv.w;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    lea_conv_epilogue<NPAD>(p, b, d, h0 + lh, w0 + lw, acc);
+}
+
+template <int NPAD>
+__global__ void __launch_bounds__(128)
+lea_conv1_simt_kernel(lea_conv p, const float* __restrict__ weight) {
+    // smem: w_s[c_in][NPAD]
+    LEA_DYN_SMEM(float, w_s);
+    const int tid = threadIdx.x;
+    for (int e = tid; e < p.c_in * NPAD; e += 128) {
+        const int n = e / p.c_in, ci = e - n * p.c_in;
+        w_s[ci * NPAD + n] = (n < p.c_out) ? __ldg(weight + (int64_t)n * p.c_in + ci) : 0.0f;
+    }
+    __syncthreads();
+    const int tiles_w = (p.src.W + LEA_TW - 1) / LEA_TW;
+    const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
+    const int d = blockIdx.y, b = blockIdx.z;
+    const int w = tw * LEA_TW + tid % LEA_TW, h = th * LEA_TH + tid / LEA_TW;
+    if (h >= p.src.H || w >= p.src.W) return;
+    float acc[NPAD];
+#pragma unroll
+    for (int n = 0; n < NPAD; ++n) acc[n] = 0.0f;
+    const int ncb = p.c_in >> 3;
+    for (int cb = 0; cb < ncb; ++cb) {
+        float f[8];
+        lea_vol_load8(p.src, b, (p.src_c0 >> 3) + cb, d, h, w, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(w_s + (cb * 8 + j) * NPAD);
+#pragma unroll
+            for (int n4 = 0; n4 < NPAD / 4; ++n4) {
+                const float4 wv = wr[n4];
+                acc[n4 * 4 + 0] += f[j] * wv.x;
+                acc[n4 * 4 + 1] += f[j] * wv.y;
+                acc[n4 * 4 + 2] += f[j] * wv.z;
+                acc[n4 * 4 + 3] += f[j] * wv.w;
+            }
+        }
+    }
+    lea_conv_epilogue<NPAD>(p, b, d, h, w, acc);
+}
+
+// =========================================================================================================
+// K6  fused disparity head (models/build_model_2d.py:45-57 + :27-42):
+//       F.interpolate(x, [maxdisp, 3*H3, 3*W3], 'trilinear', align_corners=False) -> Softmin(dim=1) -> sum_d p*d
+//     in one kernel; the maxdisp x 3H3 x 3W3 probability volume is never written.  align_corners=False index rule:
+//     scale = in/out; src = max(scale*(dst+0.5)-0.5, 0); i0 = floor(src) (<= in-1); l1 = src-i0; i1 = min(i0+1, in-1).
+//     A CTA stages the (TH3+2) x (TW3+2) x D3 low-res neighbourhood in shared memory and produces 3*TH3 x 3*TW3
+//     pixels, one thread per pixel: pass 1 finds m = min_k u[k] of the bilinearly blended column u (a valid softmin
+//     stabiliser because every up-sampled logit is a convex combination of u), pass 2 streams the maxdisp samples.
+// =========================================================================================================
+#define LEA_DH_TH3 4
+#define LEA_DH_TW3 8
+
+LEA_HD lea_axis_lerp lea_axis_half_pixel(int dst, int in_n, int out_n) {
+    lea_axis_lerp r;
+    const float scale = (float)in_n / (float)out_n;
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    if (src < 0.0f) src = 0.0f;
+    int i0 = (int)floorf(src);
+    if (i0 > in_n - 1) i0 = in_n - 1;
+    float l1 = src - (float)i0;
+    l1 = l1 < 0.0f ? 0.0f : (l1 > 1.0f ? 1.0f : l1);
+    r.i0 = i0; r.i1 = i0 + (i0 < in_n - 1 ? 1 : 0); r.l0 = 1.0f - l1; r.l1 = l1;
+    return r;
+}
+
+__global__ void __launch_bounds__(9 * LEA_DH_TH3 * LEA_DH_TW3)
+lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
+                     int D3, int H3, int W3, int maxdisp) {
+    LEA_DYN_SMEM(float, s);            // s[k][TH3+2][TW3+2]
+    constexpr int SH = LEA_DH_TH3 + 2, SW = LEA_DH_TW3 + 2, SP = SH * SW;
+    const int tiles_w = (W3 + LEA_DH_TW3 - 1) / LEA_DH_TW3;
+    const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
+    const int b = blockIdx.y;
+    const int h3_0 = th * LEA_DH_TH3 - 1, w3_0 = tw * LEA_DH_TW3 - 1;     // low-res origin of the staged tile
+    const int tid = threadIdx.x, nthreads = 9 * LEA_DH_TH3 * LEA_DH_TW3;
+    const float* __restrict__ mb = mat + (int64_t)b * D3 * H3 * W3;
+    for (int e = tid; e < D3 * SP; e += nthreads) {
+        const int k = e / SP, r = e - k * SP;
+        const int hh = r / SW, ww = r - hh * SW;
+        int gh = h3_0 + hh, gw = w3_0 + ww;
+        gh = gh < 0 ? 0 : (gh > H3 - 1 ? H3 - 1 : gh);        // clamped reads: edge taps get weight 0 anyway
+        gw = gw < 0 ? 0 : (gw > W3 - 1 ? W3 - 1 : gw);
+        s[e] = __ldg(mb + ((int64_t)k * H3 + gh) * W3 + gw);
+    }
+    __syncthreads();
+    const int ow_l = tid % (3 * LEA_DH_TW3), oh_l = tid / (3 * LEA_DH_TW3);
+    const int oh = th * 3 * LEA_DH_TH3 + oh_l, ow = tw * 3 * LEA_DH_TW3 + ow_l;
+    if (oh >= 3 * H3 || ow >= 3 * W3) return;
+    const lea_axis_lerp ah = lea_axis_half_pixel(oh, H3, 3 * H3);
+    const lea_axis_lerp aw = lea_axis_half_pixel(ow, W3, 3 * W3);
+    const int o00 = (ah.i0 - h3_0) * SW + (aw.i0 - w3_0), o01 = (ah.i0 - h3_0) * SW + (aw.i1 - w3_0);
+    const int o10 = (ah.i1 - h3_0) * SW + (aw.i0 - w3_0), o11 = (ah.i1 - h3_0) * SW + (aw.i1 - w3_0);
+    const float c00 = ah.l0 * aw.l0, c01 = ah.l0 * aw.l1, c10 = ah.l1 * aw.l0, c11 = ah.l1 * aw.l1;
+#define LEA_U(k) (c00 * s[(k) * SP + o00] + c01 * s[(k) * SP + o01] + c10 * s[(k) * SP + o10] + c11 * s[(k) * SP + o11])
+    float m = LEA_U(0);
+    for (int k = 1; k < D3; ++k) { const float u = LEA_U(k); m = u < m ? u : m; }
+    // pass 2: stream the maxdisp samples with a sliding (k0, k1) window along disparity
+    float den = 0.0f, num = 0.0f;
+    int kc = -1; float u0 = 0.0f, u1 = 0.0f; int k1c = -1;
+    for (int i = 0; i < maxdisp; ++i) {
+        const lea_axis_lerp ad = lea_axis_half_pixel(i, D3, maxdisp);
+        if (ad.i0 != kc) {
+            u0 = (ad.i0 == k1c) ? u1 : LEA_U(ad.i0);
+            kc = ad.i0;
+            k1c = -1;
+        }
+        if (ad.i1 != k1c) { u1 = (ad.i1 == kc) ? u0 : LEA_U(ad.i1); k1c = ad.i1; }
+        const float v = ad.l0 * u0 + ad.l1 * u1;
+        const float e = __expf(m - v);                 // softmin: exp(-(v - m)), v >= m up to rounding
+        den += e;
+        num += e * (float)i;
+    }
+#undef LEA_U
+    disp[((int64_t)b * 3 * H3 + oh) * (3 * W3) + ow] = num / den;
+}
+
+// DisparityRegression alone (models/build_model_2d.py:36-41)
+__global__ void __launch_bounds__(256)
+lea_disparity_regression_kernel(const float* __restrict__ p, float* __restrict__ out, int maxdisp, int HW) {
+    const int q = blockIdx.x * 256 + threadIdx.x;
+    if (q >= HW) return;
+    const int b = blockIdx.y;
+    const float* __restrict__ pb = p + (int64_t)b * maxdisp * HW + q;
+    float acc = 0.0f;
+    for (int d = 0; d < maxdisp; ++d) acc += __ldg(pb + (int64_t)d * HW) * (float)d;
+    out[(int64_t)b * HW + q] = acc;
+}

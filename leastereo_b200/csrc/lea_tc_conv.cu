@@ -1,0 +1,561 @@
+// ConvBR as a slab-streaming implicit GEMM on the Blackwell tensor cores (tcgen05.mma, accumulators in TMEM,
+// operands staged by TMA) - models/operations_3d.py:31-47 for k in {1,3}, stride 1.
+//
+// GEMM view:  Out[voxel, co] = sum_{tap, ci} In[voxel + tap, ci] * W[tap, ci, co]
+//   M = 128 output voxels (8 along w x 16 along h of one depth slice) = the 128 TMEM lanes,
+//   N = c_out (padded to 16/32/64) x number of weight planes, K = 16 input channels per tcgen05.mma.
+//
+// Operand layout.  Activations live in HBM as bf16 "planes" (hi, lo[, lo2]) blocked by 8 channels
+// (include/leastereo_b200.h), so a (voxel, 8 channels, plane) group is exactly one 16-byte row of a UMMA
+// no-swizzle K-major core matrix.  One TMA box load per pipeline stage brings a HALO slab
+// (18 h x 10 w voxels x 16 channels x P planes of ONE input depth) into shared memory as [block][h][w][8];
+// every one of the 9 (kh,kw) taps - and all three kd taps, which feed three different output depths - is then
+// just a different START ADDRESS of the same staged slab (rows are 16 B apart, 8-row groups 160 B apart), so a
+// loaded byte is reused 27x from shared memory and each input slab is fetched once per CTA sweep.
+//
+// Split precision ("bf16xN").  With A = a0+a1(+a2), W = w0+w1(+w2) (bf16 planes), the triangular product
+// sum_{i+j<P} a_i*w_j is issued as ONE mma per A plane against the row-concatenated weight tile [w0|w1|..]:
+// plane i uses the first (P-i)*N rows, accumulating into (P-i) column groups of the same TMEM accumulator; the
+// epilogue adds the column groups.  P=2 gives the 3-term bf16x3 product, P=3 the 6-term one (~fp32).
+//
+// Schedule.  Persistent CTAs (one per SM), 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2-5 = epilogue.  A work item is (batch, depth chunk of Dc slices, h tile, w tile).  For every group of 16
+// input channels the producer streams that group's 27-tap weight part (cp.async.bulk) and then the Dc+2 input
+// slabs; the issuer accumulates into Dc resident TMEM accumulators.  Two accumulator sets ping-pong so the
+// epilogue of item i (TMEM -> registers -> BN/ReLU/+res -> plane split -> 16-byte stores) overlaps item i+1.
+#include "lea_common.h"
+#include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#define LEA_TC_TW 8      // output tile: 8 voxels along w ...
+#define LEA_TC_TH 16     // ... x 16 along h = 128 GEMM rows = 128 TMEM lanes
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kMaxTerms = 3;
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kHeaderBytes = 1024;
+constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;    // ~2 s: a stuck pipeline traps instead of hanging
+
+struct TcParams {
+    int B, D, H, W;
+    int g0_stride_b;          // tensor-map dim-4 blocks per batch element = src channel blocks * P
+    int g0_first;             // first dim-4 block of the channel slice = src_cb0 * P
+    int P;
+    int ncg, blocks_per_cg;
+    int ks, taps;
+    int tiles_w, tiles_h, dchunks, Dc, total_items;
+    int NP, c_out, accw, ngroups;
+    int nterm;
+    int term_aoff[kMaxTerms], term_lbo_blocks[kMaxTerms], term_btile[kMaxTerms], term_n[kMaxTerms];
+    int nbt, nb_rows, btile_bytes, wpart_bytes;
+    int slab_vox, pitch_vox, blk_bytes, stage_bytes;
+    int nstages, nwbuf;
+    int swap_lbo_sbo;         // debug switch for the descriptor convention
+    const uint8_t* wimg;
+    const float* bn_scale; const float* bn_shift; int relu;
+    lea_vol dst; int dst_c0; lea_vol res; int res_c0; int has_res; float* dst_f32;
+};
+
+__device__ int g_lea_tc_status;
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kWaitTimeoutCycles) {
+            atomicExch(&g_lea_tc_status, code);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, no swizzle, K-major: rows 16 B apart inside an 8-row core matrix,
+// LBO = byte distance between the two 8-element K halves, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    return d;                                     // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__device__ __host__ __forceinline__ uint32_t make_idesc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+struct ItemGeom { int b, d0, d_hi, h0, w0, dlo, dhi; };
+__device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
+    ItemGeom g;
+    int r = item;
+    const int tw = r % p.tiles_w; r /= p.tiles_w;
+    const int th = r % p.tiles_h; r /= p.tiles_h;
+    const int dc = r % p.dchunks; r /= p.dchunks;
+    g.b = r;
+    g.d0 = dc * p.Dc;
+    g.d_hi = min(g.d0 + p.Dc, p.D);
+    g.h0 = th * LEA_TC_TH; g.w0 = tw * LEA_TC_TW;
+    if (p.ks == 3) { g.dlo = max(g.d0 - 1, 0); g.dhi = min(g.d_hi, p.D - 1); }
+    else           { g.dlo = g.d0;             g.dhi = g.d_hi - 1; }
+    return g;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    // header: barriers
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full = bars;                          // [kMaxStages]
+    uint64_t* empty = bars + kMaxStages;            // [kMaxStages]
+    uint64_t* wfull = bars + 2 * kMaxStages;        // [2]
+    uint64_t* wempty = wfull + 2;                   // [2]
+    uint64_t* accfull = wempty + 2;                 // [2]
+    uint64_t* accempty = accfull + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+    uint8_t* wbuf = smem + kHeaderBytes;
+    const int wbuf_stride = (p.wpart_bytes + 127) & ~127;
+    uint8_t* stages = wbuf + (size_t)p.nwbuf * wbuf_stride;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1);
+            mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0, sphase = 0, wb = 0, wphase = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const ItemGeom g = decode_item(p, item);
+                const int halo = (p.ks == 3) ? 1 : 0;
+                const int gbase = g.b * p.g0_stride_b + p.g0_first;
+                for (int cg = 0; cg < p.ncg; ++cg) {
+                    mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101);
+                    mbar_arrive_expect_tx(smem_u32(wfull + wb), (uint32_t)p.wpart_bytes);
+                    bulk_load(smem_u32(wbuf + (size_t)wb * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
+                              (uint32_t)p.wpart_bytes, smem_u32(wfull + wb));
+                    if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                    for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
+                        mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102);
+                        mbar_arrive_expect_tx(smem_u32(full + stage), (uint32_t)p.stage_bytes);
+                        tma_load_5d(smem_u32(stages + (size_t)stage * p.stage_bytes), &tmap, smem_u32(full + stage),
+                                    0, g.w0 - halo, g.h0 - halo, d_in, gbase + cg * p.blocks_per_cg);
+                        if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            uint32_t idesc[kMaxTerms];
+            for (int t = 0; t < p.nterm; ++t) idesc[t] = make_idesc(p.term_n[t]);
+            const uint32_t a_sbo = (uint32_t)p.pitch_vox * 16u;
+            const uint32_t b_lbo = (uint32_t)p.nb_rows * 16u, b_sbo = 128u;
+            int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+                const ItemGeom g = decode_item(p, item);
+                const int set = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201);
+                tc_fence_after();
+                for (int cg = 0; cg < p.ncg; ++cg) {
+                    mbar_wait(smem_u32(wfull + wb), wphase, 202);
+                    const uint32_t wbase = smem_u32(wbuf + (size_t)wb * wbuf_stride);
+                    for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
+                        mbar_wait(smem_u32(full + stage), sphase, 203);
+                        tc_fence_after();
+                        const uint32_t sbase = smem_u32(stages + (size_t)stage * p.stage_bytes);
+                        for (int kd = 0; kd < p.ks; ++kd) {
+                            const int d_out = (p.ks == 3) ? d_in + 1 - kd : d_in;
+                            if (d_out < g.d0 || d_out >= g.d_hi) continue;
+                            const int first_d_in = (p.ks == 3) ? max(d_out - 1, 0) : d_out;
+                            const bool fresh = (cg == 0) && (d_in == first_d_in);
+                            const uint32_t dcol = tmem_base + (uint32_t)((set * p.Dc + (d_out - g.d0)) * p.accw);
+                            for (int kh = 0; kh < p.ks; ++kh) {
+                                for (int kw = 0; kw < p.ks; ++kw) {
+                                    const int tap = (kd * p.ks + kh) * p.ks + kw;
+                                    const uint32_t a_tap = sbase + (uint32_t)(kh * p.pitch_vox + kw) * 16u;
+                                    const uint32_t b_tap = wbase + (uint32_t)(tap * p.nbt) * (uint32_t)p.btile_bytes;
+                                    for (int t = 0; t < p.nterm; ++t) {
+                                        const uint32_t a_addr = a_tap + (uint32_t)p.term_aoff[t] * (uint32_t)p.blk_bytes;
+                                        const uint32_t a_lbo = (uint32_t)p.term_lbo_blocks[t] * (uint32_t)p.blk_bytes;
+                                        const uint32_t b_addr = b_tap + (uint32_t)p.term_btile[t] * (uint32_t)p.btile_bytes;
+                                        const uint64_t ad = p.swap_lbo_sbo ? make_smem_desc(a_addr, a_sbo, a_lbo)
+                                                                           : make_smem_desc(a_addr, a_lbo, a_sbo);
+                                        const uint64_t bd = p.swap_lbo_sbo ? make_smem_desc(b_addr, b_sbo, b_lbo)
+                                                                           : make_smem_desc(b_addr, b_lbo, b_sbo);
+                                        const uint32_t acc = (fresh && kh == 0 && kw == 0 && t == 0) ? 0u : 1u;
+                                        tc_mma_bf16(dcol, ad, bd, idesc[t], acc);
+                                    }
+                                }
+                            }
+                        }
+                        tc_commit(smem_u32(empty + stage));
+                        if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                    }
+                    tc_commit(smem_u32(wempty + wb));
+                    if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                }
+                tc_commit(smem_u32(accfull + set));
+            }
+        }
+    } else {
+        // ================= epilogue warps 2..5 =================
+        const int q = warp & 3;                      // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;                 // tile row = TMEM lane
+        const int lh = m / LEA_TC_TW, lw = m % LEA_TC_TW;
+        int it = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            const ItemGeom g = decode_item(p, item);
+            const int set = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(smem_u32(accfull + set), aphase, 301);
+            tc_fence_after();
+            const int h = g.h0 + lh, w = g.w0 + lw;
+            const bool valid = (h < p.H) && (w < p.W);
+            for (int j = 0; j < g.d_hi - g.d0; ++j) {
+                const int d = g.d0 + j;
+                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * p.Dc + j) * p.accw);
+                const int ncb = p.dst_f32 ? 1 : (p.c_out >> 3);
+                for (int cb = 0; cb < ncb; ++cb) {
+                    float acc[8];
+                    tc_ld8(trow + (uint32_t)(cb * 8), acc);
+                    for (int gidx = 1; gidx < p.ngroups; ++gidx) {
+                        float t8[8];
+                        tc_ld8(trow + (uint32_t)(gidx * p.NP + cb * 8), t8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] += t8[i];
+                    }
+                    if (!valid) continue;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int n = cb * 8 + i;
+                        if (n < p.c_out) {
+                            float v = acc[i];
+                            if (p.bn_scale) v = v * __ldg(p.bn_scale + n) + __ldg(p.bn_shift + n);
+                            if (p.relu) v = fmaxf(v, 0.0f);
+                            acc[i] = v;
+                        }
+                    }
+                    if (p.dst_f32) {
+                        const int64_t sp = (int64_t)p.D * p.H * p.W;
+                        float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h) * p.W + w;
+                        for (int n = 0; n < p.c_out && n < 8; ++n) o[n * sp] = acc[n];
+                    } else {
+                        if (p.has_res) {
+                            float r8[8];
+                            lea_vol_load8(p.res, g.b, (p.res_c0 >> 3) + cb, d, h, w, r8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) acc[i] += r8[i];
+                        }
+                        lea_vol_store8(p.dst, g.b, (p.dst_c0 >> 3) + cb, d, h, w, acc);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(accempty + set));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// weight image:  [cg][tap][btile][khalf(2)][row(nb_rows)][8] bf16
+//   standard (c_in % 16 == 0): one tile per tap; row = pw*NP + co holds plane pw of W[co][cg*16 + khalf*8 + 0..7][tap]
+//   c_in == 8, P == 2 ("C8"):  A operand is [hi(8) | lo(8)] of the same 8 channels, so
+//       tile 0: khalf0 = Whi, khalf1 = Whi   (hi*Whi + lo*Whi)        tile 1: khalf0 = Wlo, khalf1 = 0   (hi*Wlo)
+// ---------------------------------------------------------------------------------------------------------
+struct TcShape {
+    bool ok; bool c8;
+    int NP, nb_rows, nbt, btile_bytes, taps, ncg, wpart_bytes, accw, ngroups;
+};
+__host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) {
+    TcShape s{};
+    s.ok = false;
+    if (!(ks == 1 || ks == 3) || P < 1 || P > 3) return s;
+    if (!(c_out == 1 || (c_out % 8 == 0 && c_out >= 8 && c_out <= 64))) return s;
+    s.c8 = (c_in == 8);
+    if (s.c8 ? (P != 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
+    s.NP = c_out <= 16 ? 16 : (c_out <= 32 ? 32 : 64);
+    s.taps = ks * ks * ks;
+    if (s.c8) { s.nb_rows = s.NP; s.nbt = 2; s.ncg = 1; s.accw = s.NP; s.ngroups = 1; }
+    else      { s.nb_rows = P * s.NP; s.nbt = 1; s.ncg = c_in / 16; s.accw = P * s.NP; s.ngroups = P; }
+    s.btile_bytes = 2 * s.nb_rows * 16;
+    s.wpart_bytes = s.taps * s.nbt * s.btile_bytes;
+    s.ok = true;
+    return s;
+}
+
+__global__ void lea_pack_weights_tc_kernel(const float* __restrict__ w, lea_u4* __restrict__ img,
+                                           int c_in, int c_out, int ks, int P, int total_groups) {
+    const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gidx >= total_groups) return;
+    const TcShape s = tc_shape(c_in, c_out, ks, P);
+    int r = gidx;
+    const int row = r % s.nb_rows; r /= s.nb_rows;
+    const int khalf = r % 2; r /= 2;
+    const int bt = r % s.nbt; r /= s.nbt;
+    const int tap = r % s.taps; r /= s.taps;
+    const int cg = r;
+    uint32_t q[4] = {0, 0, 0, 0};
+    int co, plane, ci0;
+    bool zero = false;
+    if (s.c8) {
+        co = row; ci0 = 0;
+        if (bt == 0) plane = 0;
+        else { plane = 1; zero = (khalf == 1); }
+    } else {
+        plane = row / s.NP; co = row % s.NP; ci0 = cg * 16 + khalf * 8;
+    }
+    if (!zero && co < c_out) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint16_t a[3], b[3];
+            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i) * s.taps + tap], P, a);
+            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i + 1) * s.taps + tap], P, b);
+            q[i] = (uint32_t)a[plane] | ((uint32_t)b[plane] << 16);
+        }
+    }
+    lea_u4 o; o.x = q[0]; o.y = q[1]; o.z = q[2]; o.w = q[3];
+    img[gidx] = o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+int device_sm_count() {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void* stream, int swap_lbo_sbo) {
+    const int P = c->src.P;
+    const TcShape s = tc_shape(c->c_in, c->c_out, c->ksize, P);
+    LEA_CHECK(s.ok, "conv3d_tc: shape c_in=%d c_out=%d k=%d planes=%d is not taken by the tensor-core kernel",
+              c->c_in, c->c_out, c->ksize, P);
+    LEA_CHECK(c->dst_f32 != nullptr || (c->dst.P == P && (!c->has_res || c->res.P == P)),
+              "conv3d_tc: src/dst/res plane counts differ");
+    LEA_CHECK(c->dst_f32 == nullptr || c->c_out <= 8, "conv3d_tc: fp32 output supports c_out <= 8");
+    const int single = opts && opts->mma_terms == 1;
+
+    TcParams p{};
+    p.B = c->src.B; p.D = c->src.D; p.H = c->src.H; p.W = c->src.W;
+    p.P = P;
+    p.g0_stride_b = (c->src.C >> 3) * P;
+    p.g0_first = (c->src_c0 >> 3) * P;
+    p.ks = c->ksize; p.taps = s.taps;
+    p.NP = s.NP; p.c_out = c->c_out; p.accw = s.accw;
+    p.ncg = s.ncg;
+    p.nbt = s.nbt; p.nb_rows = s.nb_rows; p.btile_bytes = s.btile_bytes; p.wpart_bytes = s.wpart_bytes;
+    if (s.c8) {
+        p.blocks_per_cg = 2;                                   // 1 channel block x 2 planes
+        p.nterm = single ? 1 : 2;
+        p.term_aoff[0] = 0; p.term_lbo_blocks[0] = 1; p.term_btile[0] = 0; p.term_n[0] = s.NP;
+        p.term_aoff[1] = 0; p.term_lbo_blocks[1] = 1; p.term_btile[1] = 1; p.term_n[1] = s.NP;
+        p.ngroups = 1;
+        LEA_CHECK(!single, "conv3d_tc: single-pass mode is not defined for the 8-channel layout");
+    } else {
+        p.blocks_per_cg = 2 * P;                               // 2 channel blocks x P planes, order [cb][plane]
+        p.nterm = single ? 1 : P;
+        for (int t = 0; t < p.nterm; ++t) {
+            p.term_aoff[t] = t;                                // plane t of channel block 0
+            p.term_lbo_blocks[t] = P;                          // same plane of channel block 1
+            p.term_btile[t] = 0;
+            p.term_n[t] = single ? s.NP : (P - t) * s.NP;
+        }
+        p.ngroups = single ? 1 : P;
+    }
+    p.pitch_vox = (p.ks == 3) ? LEA_TC_TW + 2 : LEA_TC_TW;
+    p.slab_vox = p.pitch_vox * ((p.ks == 3) ? LEA_TC_TH + 2 : LEA_TC_TH);
+    p.blk_bytes = p.slab_vox * 16;
+    p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
+    p.tiles_w = (p.W + LEA_TC_TW - 1) / LEA_TC_TW;
+    p.tiles_h = (p.H + LEA_TC_TH - 1) / LEA_TC_TH;
+    int Dc = 512 / (2 * p.accw);
+    if (Dc > 8) Dc = 8;
+    if (Dc > p.D) Dc = p.D;
+    const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
+    // keep at least ~2 work items per SM when the volume is small
+    while (Dc > 1 && (int64_t)p.B * ((p.D + Dc - 1) / Dc) * p.tiles_h * p.tiles_w < 2 * num_sms) Dc = (Dc + 1) / 2;
+    p.Dc = Dc;
+    p.dchunks = (p.D + Dc - 1) / Dc;
+    const int64_t total = (int64_t)p.B * p.dchunks * p.tiles_h * p.tiles_w;
+    LEA_CHECK(total < (1ll << 31), "conv3d_tc: too many work items");
+    p.total_items = (int)total;
+    const int wstride = (p.wpart_bytes + 127) & ~127;
+    p.nwbuf = (2 * wstride + 3 * p.stage_bytes + kHeaderBytes <= kSmemBudget) ? 2 : 1;
+    int nst = (kSmemBudget - kHeaderBytes - p.nwbuf * wstride) / p.stage_bytes;
+    if (nst > kMaxStages) nst = kMaxStages;
+    LEA_CHECK(nst >= 2, "conv3d_tc: shared memory too small for this shape (weights part %d B)", p.wpart_bytes);
+    p.nstages = nst;
+    p.swap_lbo_sbo = swap_lbo_sbo;
+    p.wimg = reinterpret_cast<const uint8_t*>(wimg);
+    p.bn_scale = c->bn_scale; p.bn_shift = c->bn_shift; p.relu = c->relu;
+    p.dst = c->dst; p.dst_c0 = c->dst_c0; p.res = c->res; p.res_c0 = c->res_c0; p.has_res = c->has_res;
+    p.dst_f32 = c->dst_f32;
+    const size_t smem = (size_t)kHeaderBytes + (size_t)p.nwbuf * wstride + (size_t)p.nstages * p.stage_bytes;
+
+    PFN_encodeTiled encode = get_encode_fn();
+    LEA_CHECK(encode != nullptr, "conv3d_tc: cuTensorMapEncodeTiled is not available from the driver");
+    CUtensorMap tmap;
+    const cuuint64_t G = (cuuint64_t)p.B * (c->src.C >> 3) * P;
+    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, G};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)p.D * p.H * p.W * 16};
+    cuuint32_t box[5] = {8, (cuuint32_t)p.pitch_vox, (cuuint32_t)(p.slab_vox / p.pitch_vox), 1,
+                         (cuuint32_t)p.blocks_per_cg};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, c->src.data, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+    cudaError_t e = cudaFuncSetAttribute(lea_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBudget);
+    LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
+    const int grid = p.total_items < num_sms ? p.total_items : num_sms;
+    // always request the full budget so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
+    lea_conv_tc_kernel<<<grid, kThreads, kSmemBudget, (cudaStream_t)stream>>>(tmap, p);
+    (void)smem;
+    e = cudaGetLastError();
+    LEA_CHECK(e == cudaSuccess, "conv3d_tc: launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int64_t lea_tc_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t ksize, int32_t planes) {
+    const TcShape s = tc_shape(c_in, c_out, ksize, planes);
+    if (!s.ok) return 0;
+    return (int64_t)s.ncg * s.wpart_bytes;
+}
+
+extern "C" int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
+                                   int32_t planes, void* stream) {
+    const TcShape s = tc_shape(c_in, c_out, ksize, planes);
+    LEA_CHECK(s.ok, "pack_weights_tc: unsupported shape c_in=%d c_out=%d k=%d planes=%d", c_in, c_out, ksize, planes);
+    LEA_CHECK(weight && wimg && ((((uintptr_t)wimg) & 15) == 0), "pack_weights_tc: bad pointer");
+    const int total = (int)((int64_t)s.ncg * s.wpart_bytes / 16);
+    lea_pack_weights_tc_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        weight, reinterpret_cast<lea_u4*>(wimg), c_in, c_out, ksize, planes, total);
+    cudaError_t e = cudaGetLastError();
+    LEA_CHECK(e == cudaSuccess, "pack_weights_tc: launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+extern "C" int lea_conv3d_tc(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void* stream) {
+    LEA_CHECK(c != nullptr && wimg != nullptr, "conv3d_tc: null argument");
+    LEA_CHECK(!(opts && opts->fused_cv), "conv3d_tc: fused cost-volume loader is not built yet");
+    return tc_launch(c, wimg, opts, stream, 0);
+}
+
+extern "C" int lea_conv3d_tc_debug(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void* stream,
+                                   int swap_lbo_sbo) {
+    return tc_launch(c, wimg, opts, stream, swap_lbo_sbo);
+}
+
+extern "C" int lea_tc_status(void) {
+    int v = 0;
+    cudaMemcpyFromSymbol(&v, g_lea_tc_status, sizeof(int));
+    return v;
+}

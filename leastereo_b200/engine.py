@@ -1,0 +1,430 @@
+"""Execution engine of the hot path: compiles the genotype-driven matching net into a flat list of kernel launches
+over pre-allocated planes volumes, and runs cost volume -> matching net -> disparity head through the C-ABI library.
+
+Dataflow being executed (reference lines): ``retrain/LEAStereo.py:34-51`` (cost volume, matching, disp),
+``retrain/skip_model_3d.py:140-174`` (stems, 12 cells, the two skip concats + conv1/conv2, head),
+``retrain/skip_model_3d.py:41-75`` (cell: resamples, 1x1x1 pre-processing, step sums, concat).
+
+B200-first choices:
+  * activations never leave the planes layout between layers; ``torch.cat`` becomes "write into a channel slice",
+    the state sums become the conv epilogue's residual add, BN(eval)+ReLU live in the conv epilogue;
+  * cells 1, 4 and 8 write their outputs side by side into ONE 3x-wide buffer so that both skip concats
+    (``cat(C1,C4)``, ``cat(C4,C8)``) are plain channel slices of it - no copy;
+  * every buffer, BN scale/shift vector and packed weight image has a fixed address for the life of a plan, so a
+    whole forward can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+import threading
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .kernels import LeaError, Ops, PlanesVol, get_ops, lea_tc_opts
+from .modules import ConvBR3d, Identity3d, newMatching
+from .structure import scale_dimension
+
+_LOCK = threading.Lock()
+
+
+@dataclass
+class Slice:
+    vol: PlanesVol
+    c0: int
+    c: int
+
+    @property
+    def spatial(self):
+        return self.vol.spatial
+
+
+@dataclass
+class Step:
+    kind: str            # "conv_simt" | "conv_tc" | "resample"
+    name: str            # module path, for per-kernel timing reports
+    args: tuple
+    flops: float = 0.0   # 2*M*N*K for convs
+    bytes: float = 0.0   # algorithmic bytes read+written
+
+
+class MatchingPlan:
+    """Launch list + buffers of ``newMatching.forward`` for one (device, B, D, H, W, planes, conv mode)."""
+
+    def __init__(self, matching: newMatching, ops: Ops, B: int, spatial: Tuple[int, int, int], planes: int,
+                 device, conv_mode: str = "simt", mma_terms: int = 0):
+        if conv_mode not in ("simt", "tc"):
+            raise ValueError("conv mode must be 'simt' or 'tc'")
+        self.m = matching
+        self.ops = ops
+        self.B, self.spatial, self.P = B, tuple(int(v) for v in spatial), planes
+        self.device = torch.device(device)
+        self.conv_mode = conv_mode
+        self.mma_terms = mma_terms
+        self.steps: List[Step] = []
+        self.volumes: List[PlanesVol] = []
+        self._convs: List[Tuple[ConvBR3d, int]] = []     # (module, offset into bn buffer)
+        self._bn_channels = 0
+        self._eye: Dict[int, torch.Tensor] = {}
+        self._tc_images: Dict[int, torch.Tensor] = {}
+        self._param_key = None
+        total_bn = sum(mod.conv.out_channels for mod in matching.modules() if isinstance(mod, ConvBR3d))
+        self.bn_scale = torch.ones(total_bn, dtype=torch.float32, device=self.device)
+        self.bn_shift = torch.zeros(total_bn, dtype=torch.float32, device=self.device)
+        self._build()
+
+    # ---- allocation helpers ---------------------------------------------------------------------------
+    def _vol(self, c: int, spatial) -> PlanesVol:
+        v = PlanesVol.empty(self.B, c, self.P, *spatial, self.device)
+        self.volumes.append(v)
+        return v
+
+    def workspace_bytes(self) -> int:
+        return sum(v.nbytes() for v in self.volumes)
+
+    # ---- step emitters --------------------------------------------------------------------------------
+    def _resample(self, name: str, src: Slice, spatial) -> Slice:
+        dst = self._vol(src.c, spatial)
+        nbytes = 2.0 * self.P * 8 * (src.c // 8) * self.B * (_prod(src.spatial) + _prod(spatial))
+        self.steps.append(Step("resample", name, (src.vol, src.c0, src.c, dst, 0), 0.0, nbytes))
+        return Slice(dst, 0, src.c)
+
+    def _emit_conv(self, name: str, mod: Optional[ConvBR3d], src: Slice, dst: Optional[Slice], *, res: bool = False,
+                   dst_f32: Optional[torch.Tensor] = None, identity_c: int = 0):
+        """Append one ConvBR launch (``mod is None``: identity 1x1x1 used for ``skip_connect`` / state copies)."""
+        if mod is None:
+            c_in = c_out = identity_c
+            k, relu, scale, shift = 1, False, None, None
+            weight = self._identity_weight(identity_c)
+        else:
+            w = mod.conv.weight
+            c_out, c_in, k = w.shape[0], w.shape[1], w.shape[2]
+            relu = mod.relu
+            weight = w.detach()
+            scale = shift = None
+            if mod.use_bn:
+                off = self._bn_channels
+                scale = self.bn_scale[off: off + c_out]
+                shift = self.bn_shift[off: off + c_out]
+                self._convs.append((mod, off))
+                self._bn_channels += c_out
+        if src.c != c_in:
+            raise LeaError("%s: input has %d channels, conv expects %d" % (name, src.c, c_in))
+        p = self.ops.make_conv(src.vol, src.c0, c_in, c_out, k, scale, shift, relu,
+                               dst=None if dst is None else dst.vol, dst_c0=0 if dst is None else dst.c0,
+                               res=dst.vol if res else None, res_c0=dst.c0 if res else 0, dst_f32=dst_f32)
+        m_vox = self.B * _prod(src.spatial)
+        flops = 2.0 * m_vox * c_out * c_in * k ** 3
+        if dst_f32 is None:
+            nbytes = 2.0 * self.P * m_vox * (c_in + c_out * (2 if res else 1))
+        else:
+            nbytes = 2.0 * self.P * m_vox * c_in + 4.0 * m_vox * c_out
+        use_tc = self.conv_mode == "tc" and mod is not None and \
+            self.ops.tc_weight_image_bytes(c_in, c_out, k, self.P) > 0
+        if use_tc:
+            opts = lea_tc_opts()
+            opts.mma_terms = self.mma_terms
+            self.steps.append(Step("conv_tc", name, (p, mod, opts, src.vol.t), flops, nbytes))
+        else:
+            self.steps.append(Step("conv_simt", name, (p, weight, mod, src.vol.t), flops, nbytes))
+
+    def _identity_weight(self, c: int) -> torch.Tensor:
+        if c not in self._eye:
+            self._eye[c] = torch.eye(c, dtype=torch.float32, device=self.device).reshape(c, c, 1, 1, 1).contiguous()
+        return self._eye[c]
+
+    # ---- network construction -------------------------------------------------------------------------
+    def _cell(self, i: int, s0: Slice, s1: Slice, out: Optional[Slice] = None) -> Tuple[Slice, Slice]:
+        cell = self.m.cells[i]
+        spec = cell.spec
+        name = "cells.%d" % i
+        prev_input = s1
+        c_out = spec.c_out
+        if spec.downup_sample != 0:
+            sp = tuple(scale_dimension(n, spec.scale) for n in s1.spatial)
+            s1 = self._resample(name + ".resample_s1", s1, sp)
+        if s0.spatial != s1.spatial:
+            s0 = self._resample(name + ".resample_s0", s0, s1.spatial)
+        sp = s1.spatial
+        bm = self.m._block_multiplier
+        n_states = 2 + len(spec.steps)
+        first_in_concat = n_states - bm
+        if first_in_concat < 0:
+            raise LeaError("block_multiplier larger than the number of cell states")
+        if out is None:
+            out = Slice(self._vol(bm * c_out, sp), 0, bm * c_out)
+        elif out.spatial != sp or out.c != bm * c_out:
+            raise LeaError("cell %d output %s x%d does not fit the skip-concat slot %s x%d (the reference's torch.cat "
+                           "would fail too)" % (i, sp, bm * c_out, out.spatial, out.c))
+
+        def state_slot(q: int) -> Slice:
+            pos = q - first_in_concat
+            if pos >= 0:
+                return Slice(out.vol, out.c0 + pos * c_out, c_out)
+            return Slice(self._vol(c_out, sp), 0, c_out)
+
+        if s0.c != c_out:
+            d0 = state_slot(0)
+            self._emit_conv(name + ".pre_preprocess", cell.pre_preprocess, s0, d0)
+            s0 = d0
+        elif first_in_concat <= 0:
+            d0 = state_slot(0)
+            self._emit_conv(name + ".s0_copy", None, s0, d0, identity_c=c_out)
+            s0 = d0
+        d1 = state_slot(1)
+        self._emit_conv(name + ".preprocess", cell.preprocess, s1, d1)
+        states = [s0, d1]
+        for k, step in enumerate(spec.steps):
+            dst = state_slot(2 + k)
+            for n, (j, opi) in enumerate(step):
+                op = cell._ops[opi]
+                if isinstance(op, Identity3d):
+                    self._emit_conv("%s._ops.%d(skip)" % (name, opi), None, states[j], dst, res=n > 0,
+                                    identity_c=c_out)
+                else:
+                    self._emit_conv("%s._ops.%d" % (name, opi), op, states[j], dst, res=n > 0)
+            states.append(dst)
+        return prev_input, out
+
+    def _build(self):
+        m = self.m
+        fm = m.initial_fm
+        L0 = self.spatial
+        self.cost = self._vol(2 * fm, L0)
+        v0, v1 = self._vol(fm, L0), self._vol(fm, L0)
+        self._emit_conv("stem0", m.stem0, Slice(self.cost, 0, 2 * fm), Slice(v0, 0, fm))
+        self._emit_conv("stem1", m.stem1, Slice(v0, 0, fm), Slice(v1, 0, fm))
+        stem0, stem1 = Slice(v0, 0, fm), Slice(v1, 0, fm)
+
+        out0 = self._cell(0, stem0, stem1)
+        # cells 1, 4, 8 share one buffer: [C1 | C4 | C8]  (skip_model_3d.py:150,155 concats become slices)
+        spec1 = m.cells[1].spec
+        sp1 = out0[1].spatial if spec1.downup_sample == 0 else \
+            tuple(scale_dimension(n, spec1.scale) for n in out0[1].spatial)
+        cw = m._block_multiplier * spec1.c_out
+        skip = self._vol(3 * cw, sp1)
+        out1 = self._cell(1, out0[0], out0[1], Slice(skip, 0, cw))
+        out2 = self._cell(2, out1[0], out1[1])
+        out3 = self._cell(3, out2[0], out2[1])
+        out4 = self._cell(4, out3[0], out3[1], Slice(skip, cw, cw))
+        x5 = Slice(self._vol(m.conv1.conv.out_channels, sp1), 0, m.conv1.conv.out_channels)
+        self._emit_conv("conv1", m.conv1, Slice(skip, 0, 2 * cw), x5)
+        out5 = self._cell(5, out4[0], x5)
+        out6 = self._cell(6, out5[0], out5[1])
+        out7 = self._cell(7, out6[0], out6[1])
+        out8 = self._cell(8, out7[0], out7[1], Slice(skip, 2 * cw, cw))
+        x9 = Slice(self._vol(m.conv2.conv.out_channels, sp1), 0, m.conv2.conv.out_channels)
+        self._emit_conv("conv2", m.conv2, Slice(skip, cw, 2 * cw), x9)
+        out9 = self._cell(9, out8[0], x9)
+        out10 = self._cell(10, out9[0], out9[1])
+        out11 = self._cell(11, out10[0], out10[1])
+        last = out11[1]
+
+        # head (skip_model_3d.py:161-173)
+        d, h, w = L0
+        self.mat = torch.empty((self.B, 1, d, h, w), dtype=torch.float32, device=self.device)
+
+        def conv_to(name, mod, src: Slice) -> Slice:
+            dst = Slice(self._vol(mod.conv.out_channels, src.spatial), 0, mod.conv.out_channels)
+            self._emit_conv(name, mod, src, dst)
+            return dst
+
+        if last.spatial[1] == h:
+            feat = last
+        elif last.spatial[1] == h // 2:
+            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, last), L0)
+        elif last.spatial[1] == h // 4:
+            t = self._resample("head.upsample_12", conv_to("last_12", m.last_12, last), (d // 2, h // 2, w // 2))
+            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, t), L0)
+        elif last.spatial[1] == h // 8:
+            t = self._resample("head.upsample_24", conv_to("last_24", m.last_24, last), (d // 4, h // 4, w // 4))
+            t = self._resample("head.upsample_12", conv_to("last_12", m.last_12, t), (d // 2, h // 2, w // 2))
+            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, t), L0)
+        else:
+            raise LeaError("matching net ends on a level the reference head does not handle (H3=%d, last H=%d)"
+                           % (h, last.spatial[1]))
+        if feat.spatial != L0:
+            raise LeaError("head input %s does not match the cost volume %s" % (feat.spatial, L0))
+        self._emit_conv("last_3", m.last_3, feat, None, dst_f32=self.mat)
+
+    # ---- parameters -----------------------------------------------------------------------------------
+    def _current_param_key(self):
+        key = []
+        for mod, _ in self._convs:
+            for t in (mod.bn.weight, mod.bn.bias, mod.bn.running_mean, mod.bn.running_var):
+                key.append((t.data_ptr(), t._version))
+        for s in self.steps:
+            mod = s.args[2] if s.kind == "conv_simt" else (s.args[1] if s.kind == "conv_tc" else None)
+            if mod is not None:
+                t = mod.conv.weight
+                key.append((t.data_ptr(), t._version))
+        return tuple(key)
+
+    def refresh_params(self, force: bool = False):
+        """Recompute BN scale/shift (and packed tensor-core weight images) when parameters changed."""
+        key = self._current_param_key()
+        if not force and key == self._param_key:
+            return
+        with torch.no_grad():
+            if self._convs:
+                g = torch.cat([m.bn.weight.detach().float().reshape(-1) for m, _ in self._convs])
+                b = torch.cat([m.bn.bias.detach().float().reshape(-1) for m, _ in self._convs])
+                mu = torch.cat([m.bn.running_mean.detach().float().reshape(-1) for m, _ in self._convs])
+                var = torch.cat([m.bn.running_var.detach().float().reshape(-1) for m, _ in self._convs])
+                eps = torch.cat([torch.full((m.bn.num_features,), float(m.bn.eps)) for m, _ in self._convs]).to(g.device)
+                scale = g / torch.sqrt(var + eps)
+                self.bn_scale[: scale.numel()].copy_(scale)
+                self.bn_shift[: scale.numel()].copy_(b - mu * scale)
+            for s in self.steps:
+                if s.kind == "conv_simt":
+                    p, weight, mod, ref = s.args
+                    if mod is not None:
+                        w = mod.conv.weight.detach()
+                        if not (w.is_contiguous() and w.dtype == torch.float32 and w.device == self.device):
+                            raise LeaError("%s: weights must be contiguous fp32 on %s" % (s.name, self.device))
+                        s.args = (p, w, mod, ref)
+                elif s.kind == "conv_tc":
+                    p, mod, opts, ref = s.args
+                    img = self._tc_images.get(id(mod))
+                    self._tc_images[id(mod)] = self.ops.pack_weights_tc(mod.conv.weight.detach(), self.P, out=img)
+        self._param_key = key
+
+    # ---- execution ------------------------------------------------------------------------------------
+    def run_step(self, s: Step):
+        if s.kind == "resample":
+            src, c0, c, dst, dst_c0 = s.args
+            self.ops.trilinear_ac(src, c0, c, dst, dst_c0)
+        elif s.kind == "conv_simt":
+            p, weight, _, ref = s.args
+            self.ops.conv3d_simt(p, weight, ref)
+        elif s.kind == "conv_tc":
+            p, mod, opts, ref = s.args
+            self.ops.conv3d_tc(p, self._tc_images[id(mod)], opts, ref)
+        else:
+            raise LeaError("unknown step " + s.kind)
+
+    def run(self, check_params: bool = True) -> torch.Tensor:
+        """Runs the launch list over ``self.cost`` (already filled) and returns ``self.mat``."""
+        if check_params or self._param_key is None:
+            self.refresh_params()
+        for s in self.steps:
+            self.run_step(s)
+        return self.mat
+
+    def conv_flops(self) -> float:
+        return sum(s.flops for s in self.steps)
+
+
+def _prod(t):
+    r = 1
+    for v in t:
+        r *= int(v)
+    return r
+
+
+# --------------------------------------------------------------------------------------------------------
+# module-level entry points used by the nn.Module boundary
+# --------------------------------------------------------------------------------------------------------
+
+DEFAULT_OPTIONS = {"planes": 2, "conv": "simt", "mma_terms": 0, "assume_frozen": False}
+
+
+def _options(model) -> dict:
+    o = dict(DEFAULT_OPTIONS)
+    o.update(getattr(model, "engine_options", None) or {})
+    return o
+
+
+def _plans(owner) -> dict:
+    d = owner.__dict__.get("_lea_plans")
+    if d is None:
+        d = {}
+        owner.__dict__["_lea_plans"] = d
+    return d
+
+
+def invalidate_cached_plans(model):
+    for mod in model.modules():
+        mod.__dict__.pop("_lea_plans", None)
+
+
+def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops: Optional[Ops] = None) -> MatchingPlan:
+    ops = ops or get_ops()
+    key = (str(device), B, tuple(spatial), options["planes"], options["conv"], options["mma_terms"], id(ops))
+    with _LOCK:
+        plans = _plans(matching)
+        plan = plans.get(key)
+        if plan is None:
+            plan = MatchingPlan(matching, ops, B, spatial, options["planes"], device, options["conv"],
+                                options["mma_terms"])
+            plans[key] = plan
+    return plan
+
+
+def _require_inference(module):
+    if module.training:
+        raise NotImplementedError(
+            "leastereo_b200: train-mode BatchNorm and the backward kernels of the hot path are not built yet "
+            "(DESIGN.md, 'what comes next'); call .eval() - there is deliberately no autograd/PyTorch fallback")
+
+
+def hot_path_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optional[Ops] = None) -> torch.Tensor:
+    """cost volume -> matching net -> disparity head on feature maps (B, C, H3, W3) -> (B, 3*H3, 3*W3)."""
+    _require_inference(model)
+    ops = ops or get_ops()
+    opt = _options(model)
+    fx = fx.detach().float().contiguous()
+    fy = fy.detach().float().contiguous()
+    B, Cn, H3, W3 = fx.shape
+    D3 = int(model.maxdisp / 3)
+    if D3 < 1:
+        raise LeaError("maxdisp %r gives an empty cost volume" % (model.maxdisp,))
+    plan = get_plan(model.matching, B, (D3, H3, W3), fx.device, opt, ops)
+    ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"], out=plan.cost)
+    mat = plan.run(check_params=not opt["assume_frozen"])
+    return ops.disp_head(mat, model.maxdisp)
+
+
+def matching_forward(matching: newMatching, x: torch.Tensor, ops: Optional[Ops] = None,
+                     options: Optional[dict] = None) -> torch.Tensor:
+    """``newMatching.forward`` on a materialised fp32 (B, 2C, D3, H3, W3) cost volume."""
+    _require_inference(matching)
+    ops = ops or get_ops()
+    opt = dict(DEFAULT_OPTIONS)
+    opt.update(options or {})
+    x = x.detach().float().contiguous()
+    B, _, D, H, W = x.shape
+    plan = get_plan(matching, B, (D, H, W), x.device, opt, ops)
+    ops.pack(x, opt["planes"], out=plan.cost)
+    return plan.run(check_params=not opt["assume_frozen"]).clone()
+
+
+def conv_br_forward(mod: ConvBR3d, x: torch.Tensor, ops: Optional[Ops] = None, planes: int = 3) -> torch.Tensor:
+    """Stand-alone ``ConvBR.forward`` (operations_3d.py:41-47) on fp32 NCDHW input, eval-mode BN."""
+    _require_inference(mod)
+    ops = ops or get_ops()
+    x = x.detach().float().contiguous()
+    w = mod.conv.weight.detach()
+    c_out, c_in, k = w.shape[0], w.shape[1], w.shape[2]
+    pad_in = (-c_in) % 8
+    if pad_in:
+        x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, 0, 0, pad_in))
+        w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, pad_in))
+    src = ops.pack(x, planes)
+    out = torch.empty((x.shape[0], c_out) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    scale = shift = None
+    if mod.use_bn:
+        bn = mod.bn
+        scale = (bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)).float().contiguous()
+        shift = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
+    p = ops.make_conv(src, 0, c_in + pad_in, c_out, k, scale, shift, mod.relu, dst_f32=out)
+    ops.conv3d_simt(p, w.contiguous(), x)
+    return out
+
+
+def disp_head_forward(x: torch.Tensor, maxdisp: int, ops: Optional[Ops] = None) -> torch.Tensor:
+    return (ops or get_ops()).disp_head(x.detach(), maxdisp)
+
+
+def disparity_regression(x: torch.Tensor, maxdisp: int, ops: Optional[Ops] = None) -> torch.Tensor:
+    return (ops or get_ops()).disparity_regression(x.detach(), maxdisp)

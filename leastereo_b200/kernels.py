@@ -1,0 +1,292 @@
+"""ctypes binding of the C-ABI library (``include/leastereo_b200.h``) and thin tensor-level wrappers.
+
+PyTorch is plumbing here: it allocates device memory and supplies the current CUDA stream; all arithmetic of the
+hot path happens inside ``libleastereo_b200.so``.  There is no fallback: if the library has not been built
+(``python -c 'import __graft_entry__ as g; g.build()'``) or a tensor is not on a CUDA device, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libleastereo_b200.so")
+ABI_VERSION = 1
+
+
+class lea_vol(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("B", C.c_int32), ("C", C.c_int32), ("P", C.c_int32),
+                ("D", C.c_int32), ("H", C.c_int32), ("W", C.c_int32)]
+
+
+class lea_conv(C.Structure):
+    _fields_ = [("src", lea_vol), ("src_c0", C.c_int32),
+                ("c_in", C.c_int32), ("c_out", C.c_int32), ("ksize", C.c_int32),
+                ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p), ("relu", C.c_int32),
+                ("has_res", C.c_int32), ("res", lea_vol), ("res_c0", C.c_int32),
+                ("dst", lea_vol), ("dst_c0", C.c_int32), ("dst_f32", C.c_void_p)]
+
+
+class lea_tc_opts(C.Structure):
+    _fields_ = [("mma_terms", C.c_int32), ("fused_cv", C.c_int32), ("fx", lea_vol), ("fy", lea_vol),
+                ("d3", C.c_int32), ("num_sms", C.c_int32)]
+
+
+# every symbol include/leastereo_b200.h declares: name -> (restype, argtypes)
+_i32, _vp, _i64 = C.c_int32, C.c_void_p, C.c_int64
+_VOLP, _CONVP, _TCP = C.POINTER(lea_vol), C.POINTER(lea_conv), C.POINTER(lea_tc_opts)
+SYMBOLS = {
+    "lea_abi_version": (C.c_int, []),
+    "lea_last_error": (C.c_char_p, []),
+    "lea_is_device_build": (C.c_int, []),
+    "lea_cost_volume_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "lea_cost_volume_planes": (C.c_int, [_vp, _vp, _VOLP, _i32, _vp]),
+    "lea_pack_planes": (C.c_int, [_vp, _VOLP, _i32, _i32, _vp]),
+    "lea_unpack_planes": (C.c_int, [_VOLP, _i32, _i32, _vp, _vp]),
+    "lea_trilinear_ac": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp]),
+    "lea_conv3d_simt": (C.c_int, [_CONVP, _vp, _vp]),
+    "lea_tc_weight_image_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "lea_pack_weights_tc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "lea_conv3d_tc": (C.c_int, [_CONVP, _vp, _TCP, _vp]),
+    "lea_tc_selftest": (C.c_int, [_i32, _vp]),
+    "lea_disp_head": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "lea_disparity_regression": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+}
+
+
+class LeaError(RuntimeError):
+    pass
+
+
+class PlanesVol:
+    """Python handle of a planes volume: bf16 tensor of shape (B, C/8, P, D, H, W, 8)."""
+
+    __slots__ = ("t", "B", "C", "P", "D", "H", "W")
+
+    def __init__(self, t: torch.Tensor):
+        assert t.dtype == torch.bfloat16 and t.dim() == 7 and t.shape[-1] == 8 and t.is_contiguous()
+        self.t = t
+        self.B, cb, self.P, self.D, self.H, self.W, _ = t.shape
+        self.C = cb * 8
+
+    @staticmethod
+    def empty(B, Cn, P, D, H, W, device) -> "PlanesVol":
+        assert Cn % 8 == 0
+        return PlanesVol(torch.empty((B, Cn // 8, P, D, H, W, 8), dtype=torch.bfloat16, device=device))
+
+    @property
+    def spatial(self):
+        return (self.D, self.H, self.W)
+
+    def struct(self) -> lea_vol:
+        return lea_vol(self.t.data_ptr(), self.B, self.C, self.P, self.D, self.H, self.W)
+
+    def nbytes(self) -> int:
+        return self.t.numel() * 2
+
+
+class Ops:
+    """All entry points of one loaded library."""
+
+    def __init__(self, lib_path: str = LIB_PATH, require_device_build: bool = True):
+        if not os.path.exists(lib_path):
+            raise LeaError(
+                "leastereo_b200: native library %s is missing - build it with "
+                "`python -c \"import __graft_entry__ as g; g.build()\"`; there is no PyTorch/CPU fallback for the "
+                "hot path" % lib_path)
+        self.lib = C.CDLL(lib_path)
+        self.lib_path = lib_path
+        missing = []
+        for name, (res, args) in SYMBOLS.items():
+            try:
+                fn = getattr(self.lib, name)
+            except AttributeError:
+                missing.append(name)
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        self.missing = missing
+        if self.lib.lea_abi_version() != ABI_VERSION:
+            raise LeaError("ABI version mismatch: library %d, binding %d" % (self.lib.lea_abi_version(), ABI_VERSION))
+        self.device_build = bool(self.lib.lea_is_device_build())
+        if require_device_build:
+            if not self.device_build:
+                raise LeaError("%s is not a device build" % lib_path)
+            if missing:
+                raise LeaError("%s lacks symbols %r" % (lib_path, missing))
+        self.launches = 0          # kernels launched through this binding (bench.py reports it)
+
+    # ---- helpers ----------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        self.launches += 1
+        if rc != 0:
+            raise LeaError(self.lib.lea_last_error().decode())
+
+    def _dev(self, *tensors):
+        for t in tensors:
+            if self.device_build and not t.is_cuda:
+                raise LeaError("leastereo_b200 kernels need CUDA tensors (got %s); no CPU fallback exists" % t.device)
+            if not self.device_build and t.is_cuda:
+                raise LeaError("emulation library used with CUDA tensors")
+
+    def _stream(self, t: torch.Tensor):
+        if t.is_cuda:
+            return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+        return C.c_void_p(0)
+
+    @staticmethod
+    def _f32(t: torch.Tensor) -> torch.Tensor:
+        if t.dtype != torch.float32:
+            raise LeaError("expected float32, got %s" % t.dtype)
+        return t.contiguous()
+
+    # ---- cost volume ------------------------------------------------------------------------------------
+    def cost_volume_f32(self, x: torch.Tensor, y: torch.Tensor, maxdisp: int) -> torch.Tensor:
+        x, y = self._f32(x), self._f32(y)
+        self._dev(x, y)
+        assert x.shape == y.shape and x.dim() == 4
+        B, Cn, H, W = x.shape
+        D3 = int(maxdisp / 3)
+        cost = torch.empty((B, 2 * Cn, D3, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device) if x.is_cuda else _null():
+            self._check(self.lib.lea_cost_volume_f32(x.data_ptr(), y.data_ptr(), cost.data_ptr(), B, Cn, H, W, D3,
+                                                     self._stream(x)))
+        return cost
+
+    def cost_volume_planes(self, x: torch.Tensor, y: torch.Tensor, maxdisp: int, P: int,
+                           out: Optional[PlanesVol] = None) -> PlanesVol:
+        x, y = self._f32(x), self._f32(y)
+        self._dev(x, y)
+        B, Cn, H, W = x.shape
+        D3 = int(maxdisp / 3)
+        vol = out or PlanesVol.empty(B, 2 * Cn, P, D3, H, W, x.device)
+        vs = vol.struct()
+        with torch.cuda.device(x.device) if x.is_cuda else _null():
+            self._check(self.lib.lea_cost_volume_planes(x.data_ptr(), y.data_ptr(), C.byref(vs), Cn, self._stream(x)))
+        return vol
+
+    # ---- planes pack / unpack ---------------------------------------------------------------------------
+    def pack(self, src: torch.Tensor, P: int, out: Optional[PlanesVol] = None, c0: int = 0) -> PlanesVol:
+        src = self._f32(src)
+        self._dev(src)
+        if src.dim() == 4:
+            src = src.unsqueeze(2)
+        B, Cn, D, H, W = src.shape
+        vol = out or PlanesVol.empty(B, Cn, P, D, H, W, src.device)
+        vs = vol.struct()
+        with torch.cuda.device(src.device) if src.is_cuda else _null():
+            self._check(self.lib.lea_pack_planes(src.data_ptr(), C.byref(vs), c0, Cn, self._stream(src)))
+        return vol
+
+    def unpack(self, vol: PlanesVol, c0: int = 0, c: Optional[int] = None) -> torch.Tensor:
+        c = vol.C - c0 if c is None else c
+        out = torch.empty((vol.B, c, vol.D, vol.H, vol.W), dtype=torch.float32, device=vol.t.device)
+        vs = vol.struct()
+        with torch.cuda.device(out.device) if out.is_cuda else _null():
+            self._check(self.lib.lea_unpack_planes(C.byref(vs), c0, c, out.data_ptr(), self._stream(out)))
+        return out
+
+    # ---- trilinear --------------------------------------------------------------------------------------
+    def trilinear_ac(self, src: PlanesVol, src_c0: int, c: int, dst: PlanesVol, dst_c0: int = 0):
+        self._dev(src.t, dst.t)
+        s, d = src.struct(), dst.struct()
+        with torch.cuda.device(src.t.device) if src.t.is_cuda else _null():
+            self._check(self.lib.lea_trilinear_ac(C.byref(s), src_c0, C.byref(d), dst_c0, c, self._stream(src.t)))
+
+    # ---- conv -------------------------------------------------------------------------------------------
+    def make_conv(self, src: PlanesVol, src_c0: int, c_in: int, c_out: int, ksize: int,
+                  bn_scale: Optional[torch.Tensor], bn_shift: Optional[torch.Tensor], relu: bool,
+                  dst: Optional[PlanesVol] = None, dst_c0: int = 0, res: Optional[PlanesVol] = None, res_c0: int = 0,
+                  dst_f32: Optional[torch.Tensor] = None) -> lea_conv:
+        p = lea_conv()
+        p.src, p.src_c0, p.c_in, p.c_out, p.ksize = src.struct(), src_c0, c_in, c_out, ksize
+        p.bn_scale = bn_scale.data_ptr() if bn_scale is not None else None
+        p.bn_shift = bn_shift.data_ptr() if bn_shift is not None else None
+        p.relu = int(bool(relu))
+        p.has_res = int(res is not None)
+        if res is not None:
+            p.res, p.res_c0 = res.struct(), res_c0
+        if dst_f32 is not None:
+            assert dst_f32.dtype == torch.float32 and dst_f32.is_contiguous()
+            p.dst_f32 = dst_f32.data_ptr()
+        else:
+            p.dst, p.dst_c0 = dst.struct(), dst_c0
+            p.dst_f32 = None
+        return p
+
+    def conv3d_simt(self, p: lea_conv, weight: torch.Tensor, ref: torch.Tensor):
+        self._dev(weight, ref)
+        assert weight.dtype == torch.float32 and weight.is_contiguous()
+        with torch.cuda.device(ref.device) if ref.is_cuda else _null():
+            self._check(self.lib.lea_conv3d_simt(C.byref(p), weight.data_ptr(), self._stream(ref)))
+
+    def tc_weight_image_bytes(self, c_in, c_out, ksize, planes) -> int:
+        return int(self.lib.lea_tc_weight_image_bytes(c_in, c_out, ksize, planes))
+
+    def pack_weights_tc(self, weight: torch.Tensor, planes: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._dev(weight)
+        weight = self._f32(weight)
+        c_out, c_in, k = weight.shape[0], weight.shape[1], weight.shape[2]
+        nbytes = self.tc_weight_image_bytes(c_in, c_out, k, planes)
+        if nbytes <= 0:
+            raise LeaError("tcgen05 conv does not take c_in=%d c_out=%d k=%d" % (c_in, c_out, k))
+        img = out if out is not None else torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+        assert img.numel() == nbytes
+        with torch.cuda.device(weight.device):
+            self._check(self.lib.lea_pack_weights_tc(weight.data_ptr(), img.data_ptr(), c_in, c_out, k, planes,
+                                                     self._stream(weight)))
+        return img
+
+    def conv3d_tc(self, p: lea_conv, wimg: torch.Tensor, opts: lea_tc_opts, ref: torch.Tensor):
+        self._dev(wimg, ref)
+        with torch.cuda.device(ref.device):
+            self._check(self.lib.lea_conv3d_tc(C.byref(p), wimg.data_ptr(), C.byref(opts), self._stream(ref)))
+
+    def tc_selftest(self, verbose: int = 1) -> int:
+        return int(self.lib.lea_tc_selftest(verbose, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    # ---- disparity head ---------------------------------------------------------------------------------
+    def disp_head(self, mat: torch.Tensor, maxdisp: int) -> torch.Tensor:
+        mat = self._f32(mat)
+        self._dev(mat)
+        if mat.dim() == 5:
+            assert mat.shape[1] == 1
+            mat = mat[:, 0]
+        B, D3, H3, W3 = mat.shape
+        out = torch.empty((B, 3 * H3, 3 * W3), dtype=torch.float32, device=mat.device)
+        with torch.cuda.device(mat.device) if mat.is_cuda else _null():
+            self._check(self.lib.lea_disp_head(mat.data_ptr(), out.data_ptr(), B, D3, H3, W3, int(maxdisp),
+                                               self._stream(mat)))
+        return out
+
+    def disparity_regression(self, p: torch.Tensor, maxdisp: int) -> torch.Tensor:
+        p = self._f32(p)
+        self._dev(p)
+        B, D, H, W = p.shape
+        assert D == maxdisp
+        out = torch.empty((B, H, W), dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device) if p.is_cuda else _null():
+            self._check(self.lib.lea_disparity_regression(p.data_ptr(), out.data_ptr(), B, D, H, W, self._stream(p)))
+        return out
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_OPS: Optional[Ops] = None
+
+
+def get_ops() -> Ops:
+    """The product binding: the CUDA build of the library, or an exception - never anything else."""
+    global _OPS
+    if _OPS is None:
+        _OPS = Ops(LIB_PATH, require_device_build=True)
+    return _OPS

@@ -1,0 +1,40 @@
+// Minimal CPU emulation of the CUDA execution model for the SIMT kernels - TEST INFRASTRUCTURE ONLY.
+// One std::thread per CUDA thread of a block, blocks run one after another, __syncthreads() is a std::barrier.
+// It exists so that tests/ can run the unmodified kernel source of leastereo_b200/csrc/lea_simt_kernels.cuh in a
+// container with no GPU and compare it with the oracle.  The leastereo_b200 package never loads this.
+#pragma once
+#include <barrier>
+#include <functional>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include <cstdlib>
+#include <cmath>
+
+struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float a, float b, float c, float d) { float4 r{a, b, c, d}; return r; }
+
+extern thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+extern thread_local std::barrier<>* emu_barrier;
+extern unsigned char* emu_dyn_smem;
+
+#define __global__
+#define __device__
+#define __host__
+#define __shared__ static
+#define __restrict__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define LEA_HD inline
+#define LEA_D inline
+#define __ldg(p) (*(p))
+#define __expf(x) expf(x)
+static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
+using std::min;
+using std::max;
+
+void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+#define LEA_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu_launch(dim3(grid), dim3(block), (smem), [=]() { kernel(__VA_ARGS__); })
+#define LEA_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu_dyn_smem)

@@ -1,0 +1,231 @@
+"""Parity checks of every kernel against the oracle, written once and run twice:
+  * tests/test_gpu_kernels.py   (-m gpu)      through the real C-ABI library on a B200;
+  * tests/test_emu_kernels.py   (-m "not gpu") through the CPU emulation build of the same kernel source, so the index
+    math is verified in the GPU-less build container.
+The checker is always the oracle (oracle/leastereo_oracle.py) or the golden fixtures; tolerances are stated inline.
+"""
+import hashlib
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from conftest import golden_state_dict, load_golden, seeded_model
+from oracle import leastereo_oracle as O
+from leastereo_b200.kernels import PlanesVol
+from leastereo_b200 import engine
+
+
+def _rand(shape, seed, device, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(device)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def check_cost_volume_f32(ops, device):
+    # (B, C, H, W, maxdisp): vector path, scalar path (W % 4 != 0), D3 > W, D3 == 0
+    for (B, Cn, H, W, maxdisp) in [(2, 8, 5, 16, 12), (1, 3, 4, 10, 9), (1, 8, 3, 4, 30), (1, 8, 3, 8, 2)]:
+        x, y = _rand((B, Cn, H, W), 1, device), _rand((B, Cn, H, W), 2, device)
+        got = ops.cost_volume_f32(x, y, maxdisp).cpu().numpy()
+        want = O.cost_volume_numpy(x.cpu().numpy(), y.cpu().numpy(), maxdisp)
+        assert got.shape == want.shape
+        assert got.tobytes() == want.tobytes(), "cost volume must be bit-exact"
+
+
+def check_cost_volume_golden(ops, device, name="cal_48x96_d48"):
+    g = load_golden(name)
+    fx, fy = torch.from_numpy(g["fx"]).to(device), torch.from_numpy(g["fy"]).to(device)
+    cost = ops.cost_volume_f32(fx, fy, int(g["maxdisp"])).cpu().numpy()
+    assert hashlib.sha256(cost.tobytes()).hexdigest() == str(g["cost_sha256"])
+
+
+def check_pack_unpack(ops, device):
+    x = _rand((2, 16, 3, 5, 7), 3, device, scale=100.0)
+    x[0, 0, 0, 0, 0] = 0.0
+    x[0, 1, 0, 0, 0] = 1e-30
+    x[0, 2, 0, 0, 0] = -3e30
+    v3 = ops.pack(x, 3)
+    assert torch.equal(ops.unpack(v3), x), "3 planes must hold fp32 exactly"
+    v2 = ops.pack(x, 2)
+    err = (ops.unpack(v2) - x).abs() / x.abs().clamp_min(1e-30)
+    assert float(err.max()) <= 2.0 ** -16, "2 planes keep 16 significant bits"
+    v1 = ops.pack(x, 1)
+    assert torch.equal(ops.unpack(v1), x.bfloat16().float())
+    # channel-slice addressing
+    big = PlanesVol.empty(2, 32, 3, 3, 5, 7, device)
+    big.t.zero_()
+    ops.pack(x, 3, out=big, c0=8)
+    assert torch.equal(ops.unpack(big, 8, 16), x)
+    assert float(ops.unpack(big, 0, 8).abs().max()) == 0.0 and float(ops.unpack(big, 24, 8).abs().max()) == 0.0
+
+
+def check_cost_volume_planes(ops, device):
+    x, y = _rand((2, 8, 6, 12), 4, device), _rand((2, 8, 6, 12), 5, device)
+    vol = ops.cost_volume_planes(x, y, 15, 3)
+    assert torch.equal(ops.unpack(vol), ops.cost_volume_f32(x, y, 15))
+
+
+def check_trilinear(ops, device):
+    cases = [((8, 6, 12), (4, 3, 6)), ((4, 3, 6), (8, 6, 12)), ((5, 9, 7), (3, 5, 4)), ((3, 5, 4), (5, 9, 7)),
+             ((4, 4, 4), (4, 4, 4)), ((2, 2, 2), (1, 1, 1))]
+    for i, (src_sp, dst_sp) in enumerate(cases):
+        x = _rand((2, 16) + src_sp, 10 + i, device)
+        src = ops.pack(x, 3)
+        dst = PlanesVol.empty(2, 24, 3, *dst_sp, device)
+        dst.t.zero_()
+        ops.trilinear_ac(src, 8, 8, dst, 16)          # channels 8..15 -> slot 16..23
+        got = ops.unpack(dst, 16, 8).cpu()
+        want = F.interpolate(x[:, 8:16].cpu(), dst_sp, mode="trilinear", align_corners=True)
+        assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max())), (src_sp, dst_sp)
+
+
+def _conv_case(ops, device, B, c_in_total, c0, c_in, c_out, k, sp, bn, relu, res, planes, seed, conv_fn):
+    x = _rand((B, c_in_total) + sp, seed, device)
+    w = _rand((c_out, c_in, k, k, k), seed + 1, device, scale=0.2)
+    scale = shift = None
+    if bn:
+        scale = (_rand((c_out,), seed + 2, device).abs() + 0.5).contiguous()
+        shift = _rand((c_out,), seed + 3, device).contiguous()
+    src = ops.pack(x, planes)
+    ref = F.conv3d(x[:, c0:c0 + c_in].cpu(), w.cpu(), None, 1, (k - 1) // 2)
+    if bn:
+        ref = ref * scale.cpu().view(1, -1, 1, 1, 1) + shift.cpu().view(1, -1, 1, 1, 1)
+    if relu:
+        ref = F.relu(ref)
+    if c_out % 8 == 0:
+        dst = PlanesVol.empty(B, c_out + 16, planes, *sp, device)
+        dst.t.zero_()
+        r = None
+        if res:
+            r = _rand((B, c_out) + sp, seed + 4, device)
+            ops.pack(r, planes, out=dst, c0=8)
+            ref = ref + ops.unpack(dst, 8, c_out).cpu()
+        p = ops.make_conv(src, c0, c_in, c_out, k, scale, shift, relu, dst=dst, dst_c0=8,
+                          res=dst if res else None, res_c0=8)
+        conv_fn(p, w, x)
+        got = ops.unpack(dst, 8, c_out).cpu()
+        assert float(ops.unpack(dst, 0, 8).abs().max()) == 0.0, "wrote outside its channel slice"
+    else:
+        out = torch.empty((B, c_out) + sp, dtype=torch.float32, device=device)
+        p = ops.make_conv(src, c0, c_in, c_out, k, scale, shift, relu, dst_f32=out)
+        conv_fn(p, w, x)
+        got = out.cpu()
+    return got, ref
+
+
+def check_conv_simt(ops, device):
+    fn = lambda p, w, x: ops.conv3d_simt(p, w.contiguous(), x)
+    # (B, c_in_total, c0, c_in, c_out, k, spatial, bn, relu, res)
+    cases = [
+        (1, 16, 0, 16, 16, 3, (3, 16, 8), True, True, False),
+        (2, 24, 8, 16, 8, 3, (2, 18, 10), True, True, True),      # partial tiles, channel slice, residual
+        (1, 8, 0, 8, 32, 3, (4, 5, 3), False, False, False),
+        (1, 32, 0, 32, 1, 3, (3, 6, 9), False, False, False),      # last_3-like: c_out = 1, fp32 output
+        (1, 64, 0, 64, 64, 3, (2, 4, 8), True, True, False),
+        (2, 32, 8, 16, 16, 1, (3, 17, 9), True, True, False),      # 1x1x1
+        (1, 128, 0, 128, 32, 1, (2, 4, 8), True, True, True),
+        (1, 8, 0, 8, 8, 1, (1, 1, 1), False, False, False),
+    ]
+    for i, (B, ct, c0, ci, co, k, sp, bn, relu, res) in enumerate(cases):
+        got, ref = _conv_case(ops, device, B, ct, c0, ci, co, k, sp, bn, relu, res, 3, 100 + 10 * i, fn)
+        tol = 2e-5 * max(1.0, float(ref.abs().max()))       # fp32 accumulate, different summation order
+        assert float((got - ref).abs().max()) <= tol, (i, float((got - ref).abs().max()), tol)
+
+
+def check_disp_head(ops, device):
+    for (B, D3, H3, W3, maxdisp, seed) in [(2, 8, 5, 7, 24, 1), (1, 16, 4, 8, 50, 2), (1, 4, 9, 17, 12, 3)]:
+        mat = _rand((B, 1, D3, H3, W3), seed, device, scale=3.0)
+        got = ops.disp_head(mat, maxdisp).cpu()
+        want = O.disp_head(mat.cpu(), maxdisp)
+        assert got.shape == want.shape
+        assert float((got - want).abs().max()) <= 2e-3, float((got - want).abs().max())   # px; __expf vs expf
+    # raw-regime magnitudes (logits ~1e8): must not overflow, hard arg-min behaviour
+    mat = _rand((1, 1, 8, 4, 8), 9, device, scale=1e8)
+    got = ops.disp_head(mat, 24).cpu()
+    want = O.disp_head(mat.cpu(), 24)
+    assert torch.isfinite(got).all()
+    assert float(((got - want).abs() <= 0.1).float().mean()) >= 0.99
+
+
+def check_disparity_regression(ops, device):
+    p = torch.softmax(_rand((2, 24, 5, 7), 5, device), dim=1).contiguous()
+    got = ops.disparity_regression(p, 24).cpu()
+    want = (p.cpu() * torch.arange(24.0).view(1, 24, 1, 1)).sum(1)
+    assert float((got - want).abs().max()) <= 1e-4
+
+
+def run_hot_path(ops, device, g, planes, conv="simt", mma_terms=0):
+    """Product engine on a golden case's feature maps; returns (mat, disp) on CPU."""
+    maxdisp = int(g["maxdisp"])
+    model = seeded_model(maxdisp)
+    model.load_state_dict(golden_state_dict(g, model))
+    model = model.to(device).eval()
+    model.engine_options = {"planes": planes, "conv": conv, "mma_terms": mma_terms}
+    fx, fy = torch.from_numpy(g["fx"]).to(device), torch.from_numpy(g["fy"]).to(device)
+    disp = engine.hot_path_forward(model, fx, fy, ops=ops)
+    B, _, H3, W3 = fx.shape
+    plan = engine.get_plan(model.matching, B, (int(maxdisp / 3), H3, W3), fx.device, engine._options(model), ops)
+    return plan.mat.cpu().clone(), disp.cpu(), model, plan
+
+
+def check_hot_path_golden(ops, device, name, planes, conv="simt", mma_terms=0, mat_rtol=2e-4, require_tolerance=True):
+    g = load_golden(name)
+    mat, disp, _, _ = run_hot_path(ops, device, g, planes, conv, mma_terms)
+    ref_mat, ref_disp = torch.from_numpy(g["mat"]), torch.from_numpy(g["disp"])
+    assert mat.shape == ref_mat.shape and disp.shape == ref_disp.shape
+    rel = float((mat - ref_mat).abs().max()) / float(ref_mat.abs().max())
+    rep = O.tolerance_report(disp, ref_disp)
+    rep["mat_rel_err"] = rel
+    if mat_rtol is not None:
+        assert rel <= mat_rtol, rep
+    if require_tolerance:
+        # north-star tolerance: |dd| <= 0.1 px on >= 99.9 % of pixels, mean |dd| <= 0.01 px
+        assert rep["ok"], rep
+    return rep
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 conv (GPU only)
+# ---------------------------------------------------------------------------------------------------------
+TC_CASES = [
+    # (B, c_in_total, c0, c_in, c_out, k, spatial, bn, relu, res)
+    (1, 16, 0, 16, 16, 3, (4, 16, 8), False, False, False),      # one full tile, smallest K
+    (1, 16, 0, 16, 16, 3, (3, 16, 8), True, True, False),
+    (2, 48, 16, 32, 32, 3, (5, 18, 10), True, True, True),       # partial tiles, slice, residual, 2 channel groups
+    (1, 64, 0, 64, 32, 3, (6, 32, 24), True, True, False),       # stem0-like
+    (1, 128, 0, 128, 64, 3, (4, 16, 16), True, True, False),     # conv1-like (single weight buffer)
+    (1, 8, 0, 8, 8, 3, (4, 16, 16), True, True, True),           # 8-channel layout (cell 10)
+    (1, 32, 0, 32, 1, 3, (5, 16, 8), False, False, False),       # last_3: c_out = 1, fp32 output
+    (2, 32, 0, 32, 16, 1, (3, 17, 9), True, True, False),        # 1x1x1
+    (1, 128, 0, 128, 32, 1, (9, 16, 8), True, True, True),
+    (1, 64, 0, 64, 8, 1, (2, 16, 16), True, True, False),
+    (1, 32, 0, 32, 32, 3, (19, 40, 24), True, True, False),      # several work items per CTA, depth chunks
+]
+
+
+def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False):
+    from leastereo_b200.kernels import lea_tc_opts
+    worst = 0.0
+    for i, (B, ct, c0, ci, co, k, sp, bn, relu, res) in enumerate(cases or TC_CASES):
+        if ops.tc_weight_image_bytes(ci, co, k, planes) <= 0:
+            continue
+        if mma_terms == 1 and ci == 8:
+            continue
+
+        def fn(p, w, x):
+            img = ops.pack_weights_tc(w.contiguous(), planes)
+            opts = lea_tc_opts()
+            opts.mma_terms = mma_terms
+            ops.conv3d_tc(p, img, opts, x)
+
+        got, ref = _conv_case(ops, device, B, ct, c0, ci, co, k, sp, bn, relu, res, planes, 300 + 10 * i, fn)
+        torch.cuda.synchronize()
+        scale = max(1.0, float(ref.abs().max()))
+        err = float((got - ref).abs().max()) / scale
+        # error model: operands carry 8 bits per plane; dropped cross terms ~2^-(8*planes) of |a||w| per product
+        tol = {1: 3e-2, 2: 2e-4, 3: 2e-5}[planes] if mma_terms == 0 else 3e-2
+        if verbose:
+            print("conv_tc case %d planes %d terms %d: rel err %.3g (tol %.1g)" % (i, planes, mma_terms, err, tol))
+        assert err <= tol, (i, planes, mma_terms, err, tol)
+        worst = max(worst, err)
+    return worst

@@ -1,0 +1,82 @@
+"""CPU tests (-m "not gpu"): the SIMT kernel SOURCE of the product, compiled by g++ against tests/emu/cuda_emu.h
+(thread-per-CUDA-thread emulation), checked against the oracle.  This verifies index math, layouts, the engine's
+launch list and buffer wiring in the GPU-less build container; it is not a product path (leastereo_b200 never loads
+the emulation library, see leastereo_b200/kernels.py:get_ops)."""
+import os
+import shutil
+import subprocess
+
+import pytest
+import torch
+
+import kernel_checks as K
+from conftest import ROOT
+from leastereo_b200.kernels import Ops
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+EMU_LIB = os.path.join(EMU_DIR, "libleastereo_emu.so")
+
+
+@pytest.fixture(scope="session")
+def emu_ops():
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    srcs = [os.path.join(EMU_DIR, "emu_lib.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")] + \
+        [os.path.join(ROOT, "leastereo_b200", "csrc", f) for f in
+         ("lea_common.h", "lea_simt_kernels.cuh", "lea_api_simt.inl")]
+    if not os.path.exists(EMU_LIB) or any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-DLEA_CPU_EMU", "-Wno-unknown-pragmas",
+                               "-I" + EMU_DIR, "-o", EMU_LIB, srcs[0], "-lpthread"])
+    torch.set_num_threads(4)
+    return Ops(EMU_LIB, require_device_build=False)
+
+
+DEV = torch.device("cpu")
+
+
+def test_emu_is_not_a_device_build(emu_ops):
+    assert not emu_ops.device_build
+
+
+def test_cost_volume_f32(emu_ops):
+    K.check_cost_volume_f32(emu_ops, DEV)
+
+
+def test_cost_volume_golden(emu_ops):
+    K.check_cost_volume_golden(emu_ops, DEV, "cal_b2_24x48_d24")
+
+
+def test_pack_unpack(emu_ops):
+    K.check_pack_unpack(emu_ops, DEV)
+
+
+def test_cost_volume_planes(emu_ops):
+    K.check_cost_volume_planes(emu_ops, DEV)
+
+
+def test_trilinear(emu_ops):
+    K.check_trilinear(emu_ops, DEV)
+
+
+def test_conv_simt(emu_ops):
+    K.check_conv_simt(emu_ops, DEV)
+
+
+def test_disp_head(emu_ops):
+    K.check_disp_head(emu_ops, DEV)
+
+
+def test_disparity_regression(emu_ops):
+    K.check_disparity_regression(emu_ops, DEV)
+
+
+def test_hot_path_golden_exact_planes(emu_ops):
+    # 3 planes = fp32 storage, fp32 FMA convs: must sit at the fp32 re-ordering noise floor
+    rep = K.check_hot_path_golden(emu_ops, DEV, "cal_b2_24x48_d24", planes=3, mat_rtol=2e-4)
+    assert rep["max_abs"] <= 0.05, rep
+
+
+def test_hot_path_golden_two_planes(emu_ops):
+    # 2 planes (the bf16x3 operand format): activations carry 16 significant bits between layers
+    rep = K.check_hot_path_golden(emu_ops, DEV, "cal_b2_24x48_d24", planes=2, mat_rtol=5e-3)
+    print(rep)
