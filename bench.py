@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the LEAStereo hot path on B200 - BASELINE.json's metric: stereo pairs/sec at KITTI 384x1248, D=192.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+One "step" = one forward of ``LEAStereo(left, right)`` over a batch of B synthetic stereo pairs per GPU (2D feature
+net in stock PyTorch + the CUDA hot path: cost volume -> 3D matching net -> disparity head).  Pairs are independent,
+so N GPUs each run their own batch with no data-path collective (weak scaling); the only collectives are the timing
+barrier and the max-over-ranks of the device time.
+
+Printed JSON line (rank 0): see the task contract; additionally
+  roofline      the 3D-conv kernel family: algorithmic FLOPs (sum 2*M*N*K over the 102 convs) / summed
+                CUDA-event durations of those launches, against the measured bf16 peak;  plus per-kernel entries for
+                the cost-volume and disparity-head kernels against the measured HBM bandwidth (``kernels``);
+  cpu_baseline  the oracle (CPU port of the reference path) timed on the host cores on a bounded sample;
+  e2e           same metric through the public module call with HOST (pinned) inputs and a host copy of the result.
+``--impl reference`` times the reference's own CPU implementation of the path (the oracle port - the Python reference
+cannot travel to the GPU box) on rank 0.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = {"name": "KITTI2015 384x1248 maxdisp=192 inference (BASELINE.json configs[2])", "H": 384, "W": 1248,
+            "maxdisp": 192}
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                    "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"]))}, "measured"
+        except Exception:  # noqa: BLE001
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, reasons, mx = [], set(), None
+        for f in self.samples:
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def build_model(maxdisp, device, options):
+    from leastereo_b200 import LEAStereo, default_args
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = LEAStereo(default_args(maxdisp=maxdisp, cuda=True), device)
+    model = model.to(device).eval()
+    model.engine_options = dict(options)
+    return model
+
+
+def synthetic_pairs(B, H, W, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(B, 3, H, W, generator=g), torch.randn(B, 3, H, W, generator=g)
+
+
+def oracle_state_dict():
+    """Random-init weights of the architecture (seed 0), for the CPU arms."""
+    from leastereo_b200 import LEAStereo, default_args
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = LEAStereo(default_args(maxdisp=WORKLOAD["maxdisp"], cuda=False), "cpu")
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}
+
+
+def time_oracle(rows, steps, warmup):
+    """Times oracle.leastereo_forward on a band of `rows` image rows of the KITTI pair; returns s/step list."""
+    from oracle import leastereo_oracle as O
+    sd = oracle_state_dict()
+    left, right = synthetic_pairs(1, rows, WORKLOAD["W"])
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.leastereo_forward(sd, left, right, WORKLOAD["maxdisp"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            ts.append(dt)
+    return ts
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    H = WORKLOAD["H"]
+    # bounded sample: calibrate on a 96-row band; use the full pair only if the whole run stays within ~4 minutes
+    t_band = time_oracle(96, 1, 0)[0]
+    est_full = t_band * (H / 96.0) * (args.steps + args.warmup)
+    rows = H if est_full <= 240.0 else 96
+    frac = rows / float(H)
+    ts = time_oracle(rows, args.steps, args.warmup)
+    total = sum(ts)
+    value = frac * len(ts) / total
+    sample = "%d-row band of one 384x1248 pair per step (%.2f pair), D=192, fp32 PyTorch-CPU oracle port" % (rows, frac)
+    line = {"impl": "reference", "metric": "stereo pairs/sec, KITTI 384x1248 D=192", "value": value, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+def profile_kernels(model, left, right):
+    """Eager pass with a CUDA-event pair around every launch of the hot path; returns per-kind aggregates."""
+    from leastereo_b200 import engine
+    from leastereo_b200.kernels import get_ops
+    ops = get_ops()
+    opt = engine._options(model)
+    with torch.no_grad():
+        fx, fy = model.extract_features(left, right)
+    fx, fy = fx.float().contiguous(), fy.float().contiguous()
+    B, C, H3, W3 = fx.shape
+    D3 = int(model.maxdisp / 3)
+    plan = engine.get_plan(model.matching, B, (D3, H3, W3), fx.device, opt, ops)
+    plan.refresh_params()
+    stream = torch.cuda.current_stream()
+    records = []
+
+    def timed(name, kind, fn, flops=0.0, nbytes=0.0):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream); fn(); b.record(stream)
+        records.append([name, kind, a, b, flops, nbytes])
+
+    for rep in range(2):       # first repetition warms up, second is reported
+        records.clear()
+        cv_bytes = 4.0 * B * (2 * C * H3 * W3 + 2 * C * D3 * H3 * W3)
+        timed("cost_volume", "cost_volume", lambda: ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"],
+                                                                          out=plan.cost), 0.0, cv_bytes)
+        for s in plan.steps:
+            timed(s.name, s.kind, lambda s=s: plan.run_step(s), s.flops, s.bytes)
+        dh_bytes = 4.0 * B * (D3 * H3 * W3 + 9 * H3 * W3)
+        timed("disp_head", "disp_head", lambda: ops.disp_head(plan.mat, model.maxdisp), 0.0, dh_bytes)
+        torch.cuda.synchronize()
+    agg = {}
+    for name, kind, a, b, flops, nbytes in records:
+        d = agg.setdefault(kind, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        d["launches"] += 1; d["ms"] += a.elapsed_time(b); d["flops"] += flops; d["bytes"] += nbytes
+    per_launch = [(name, kind, a.elapsed_time(b), flops, nbytes) for name, kind, a, b, flops, nbytes in records]
+    return agg, per_launch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--conv", default=os.environ.get("LEA_CONV", "tc"), choices=["tc", "simt"])
+    ap.add_argument("--planes", type=int, default=int(os.environ.get("LEA_PLANES", "2")))
+    ap.add_argument("--mma-terms", type=int, default=0)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-launches", default=None, help="write the per-launch profile to this JSON file")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+
+    import __graft_entry__ as entry
+    if rank == 0:
+        with contextlib.redirect_stdout(sys.stderr):
+            entry.build()
+    if dist is not None:
+        dist.barrier()
+    from leastereo_b200.kernels import get_ops
+    ops = get_ops()
+
+    H, W, maxdisp, B = WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["maxdisp"], args.batch
+    options = {"planes": args.planes, "conv": args.conv, "mma_terms": args.mma_terms, "assume_frozen": True}
+    model = build_model(maxdisp, device, options)
+    left_h, right_h = synthetic_pairs(B, H, W, seed=1 + rank)
+    left_h, right_h = left_h.pin_memory(), right_h.pin_memory()
+    left, right = left_h.to(device), right_h.to(device)
+    out_h = torch.empty((B, H, W), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        model(left, right)                       # builds the plan, packs weights
+        torch.cuda.synchronize()
+        n0 = ops.launches
+        disp = model(left, right)
+        torch.cuda.synchronize()
+        launches_per_step = ops.launches - n0
+
+        graph, static_out = None, None
+        if not args.no_graph:
+            try:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    model(left, right)
+                torch.cuda.current_stream().wait_stream(s)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = model(left, right)
+                graph.replay()
+                torch.cuda.synchronize()
+                if not torch.allclose(static_out, disp, atol=1e-3, rtol=0):
+                    raise RuntimeError("graph replay differs from eager run")
+            except Exception as e:  # noqa: BLE001
+                print("[bench] CUDA graph capture unavailable (%s); running eagerly" % str(e)[:200], file=sys.stderr)
+                graph = None
+
+        def step_device():
+            if graph is not None:
+                graph.replay()
+                return static_out
+            return model(left, right)
+
+        def step_e2e():
+            left.copy_(left_h, non_blocking=True)
+            right.copy_(right_h, non_blocking=True)
+            o = step_device()
+            out_h.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        # ---- device-resident throughput ----
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        with sampler:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(args.steps):
+                step_device()
+            ev1.record()
+            barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        # ---- end to end (host buffers) ----
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        for _ in range(args.steps):
+            step_e2e()
+        ev3.record()
+        barrier()
+        ms_e2e = ev2.elapsed_time(ev3)
+
+        t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=device)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+
+        agg, per_launch = (None, None)
+        if rank == 0:
+            agg, per_launch = profile_kernels(model, left, right)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_src = load_peaks()
+    pairs = B * world * args.steps
+    value = pairs / (ms_total / 1e3)
+    e2e_value = pairs / (ms_e2e / 1e3)
+    conv_kinds = [k for k in agg if k.startswith("conv")]
+    conv_ms = sum(agg[k]["ms"] for k in conv_kinds)
+    conv_flops = sum(agg[k]["flops"] for k in conv_kinds)
+    conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    step_ms_profile = sum(v["ms"] for v in agg.values())
+    kernels = {}
+    for kind, v in agg.items():
+        e = {"launches": v["launches"], "ms": round(v["ms"], 4), "share_of_hot_path": round(v["ms"] / step_ms_profile, 4)}
+        if v["flops"] > 0:
+            e["TFLOPs"] = round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2)
+        if v["bytes"] > 0 and v["ms"] > 0:
+            e["GBps_algorithmic"] = round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1)
+            e["frac_hbm_peak"] = round(e["GBps_algorithmic"] / peaks["hbm_gbs"], 4)
+        kernels[kind] = e
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
+    roofline = {"bound": "tensor", "kernel": "lea_conv_tc_kernel" if args.conv == "tc" else "lea_conv3_simt_kernel",
+                "achieved": round(conv_tflops, 2), "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": round(conv_tflops / peaks["bf16_tflops_sustained"], 4), "traffic": traffic,
+                "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peak_src,
+                "algorithmic_flops_per_step": conv_flops, "conv_launches_per_step": sum(agg[k]["launches"] for k in conv_kinds),
+                "note": "achieved = sum of 2*M*N*K over the 3D convs / summed CUDA-event durations of those launches; "
+                        "split-precision modes issue planes*(planes+1)/2 tensor-core MACs per algorithmic MAC"}
+    line = {"metric": "stereo pairs/sec, KITTI 384x1248 D=192", "value": round(value, 4), "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {1: "bf16", 2: "bf16x3 (2 bf16 planes, fp32 accumulate)", 3: "bf16x6 (3 bf16 planes, fp32 accumulate)"}[
+                args.planes] if args.conv == "tc" else "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"], "pairs_per_gpu_per_step": B, "conv": args.conv, "planes": args.planes,
+                       "mma_terms": args.mma_terms, "cuda_graph": graph is not None, "parallelism": "pairs sharded, no collective",
+                       "l2": "per-step activation working set (>4 GB of planes volumes) exceeds the 126 MB L2; no flush needed",
+                       "weights": "random init seed 0", "feature_net": "stock PyTorch fp32 (TF32 off), inside the timed step"},
+            "e2e": {"value": round(e2e_value, 4), "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * 3 * H * W * 4,
+                    "d2h_bytes_per_step": B * H * W * 4},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": sampler.summary(), "roofline": roofline, "kernels": kernels}
+    if args.dump_launches:
+        json.dump([list(r) for r in per_launch], open(args.dump_launches, "w"), indent=0)
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        t_band = time_oracle(96, 1, 1)[0]
+        rows = 384 if t_band * 4 <= 30.0 else 96
+        ts = time_oracle(rows, 1, 0) if rows != 96 else [t_band]
+        frac = rows / 384.0
+        line["cpu_baseline"] = {"value": round(frac / ts[0], 5), "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": "%d-row band of one 384x1248 pair (%.2f pair), D=192, 1 forward of the fp32 "
+                                          "PyTorch-CPU oracle port" % (rows, frac)}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -110,7 +110,6 @@ extern "C" int lea_tc_selftest(int32_t verbose, void* stream) {
     const Variant variants[] = {
         // a_off a_lbo a_sbo  b_off b_lbo b_sbo swap
         {"dense rows, lbo=K-half stride, sbo=8-row stride", {0, 2048, 128, 0, 256, 128, 0}, true},
-        {"same, LBO/SBO swapped in the descriptor",          {0, 2048, 128, 0, 256, 128, 1}, false},
         {"halo pitch: sbo=160, start +16 B (tap shift kw=1)", {16, 2880, 160, 0, 256, 128, 0}, true},
         {"halo pitch: sbo=160, start +176 B (kh=1,kw=1)",     {176, 2880, 160, 0, 256, 128, 0}, true},
         {"B tile inside a wider image: b_lbo=1024 (64 rows)", {0, 2048, 128, 0, 1024, 128, 0}, true},
