@@ -165,10 +165,53 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
 // ---------------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, %1;\n\t"
+        "selp.u32 %0, 1, 0, px;\n\t}"
+        : "=r"(pred) : "r"(0xffffffffu));
+    return pred;
+}
+// issue one MMA from the elected lane; descriptors are (lo, hi) 32-bit halves
+__device__ __forceinline__ void tc_mma_issue(uint32_t elected, uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi,
+                                             uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %7, 0;\n\t"
+        "setp.ne.b32 q, %0, 0;\n\t"
+        "mov.b64 da, {%2, %3};\n\t"
+        "mov.b64 db, {%4, %5};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, p;\n\t}"
+        ::"r"(elected), "r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_if(uint32_t elected, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
+        ::"r"(elected), "r"(bar) : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane, load + wait in one block so that the results cannot be
+// consumed early
+__device__ __forceinline__ void tc_ld16_wait(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int KS, int NTERM>
 __global__ void __launch_bounds__(kThreads, 1)
 lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    // header: barriers
+    // header: barriers, TMEM base, BN scale/shift
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
     uint64_t* full = bars;                          // [kMaxStages]
     uint64_t* empty = bars + kMaxStages;            // [kMaxStages]
@@ -177,6 +220,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint64_t* accfull = wempty + 2;                 // [2]
     uint64_t* accempty = accfull + 2;               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
+    float* s_scale = reinterpret_cast<float*>(smem + 256);      // [64]
+    float* s_shift = s_scale + 64;                              // [64]
     uint8_t* wbuf = smem + kHeaderBytes;
     const int wbuf_stride = (p.wpart_bytes + 127) & ~127;
     uint8_t* stages = wbuf + (size_t)p.nwbuf * wbuf_stride;
@@ -191,6 +236,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int n = threadIdx.x - 64;
+        s_scale[n] = (p.bn_scale && n < p.c_out) ? __ldg(p.bn_scale + n) : 1.0f;
+        s_shift[n] = (p.bn_shift && n < p.c_out) ? __ldg(p.bn_shift + n) : 0.0f;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -200,6 +250,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    constexpr int kHalo = (KS == 3) ? 1 : 0;
+    constexpr int kPitch = LEA_TC_TW + 2 * kHalo;              // voxels per staged row
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -207,7 +259,6 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             int stage = 0, sphase = 0, wb = 0, wphase = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const ItemGeom g = decode_item(p, item);
-                const int halo = (p.ks == 3) ? 1 : 0;
                 const int gbase = g.b * p.g0_stride_b + p.g0_first;
                 for (int cg = 0; cg < p.ncg; ++cg) {
                     mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101);
@@ -219,115 +270,123 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102);
                         mbar_arrive_expect_tx(smem_u32(full + stage), (uint32_t)p.stage_bytes);
                         tma_load_5d(smem_u32(stages + (size_t)stage * p.stage_bytes), &tmap, smem_u32(full + stage),
-                                    0, g.w0 - halo, g.h0 - halo, d_in, gbase + cg * p.blocks_per_cg);
+                                    0, g.w0 - kHalo, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            uint32_t idesc[kMaxTerms];
-            for (int t = 0; t < p.nterm; ++t) idesc[t] = make_idesc(p.term_n[t]);
-            const uint32_t a_sbo = (uint32_t)p.pitch_vox * 16u;
-            const uint32_t b_lbo = (uint32_t)p.nb_rows * 16u, b_sbo = 128u;
-            int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-                const ItemGeom g = decode_item(p, item);
-                const int set = it & 1, aphase = (it >> 1) & 1;
-                mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201);
-                tc_fence_after();
-                for (int cg = 0; cg < p.ncg; ++cg) {
-                    mbar_wait(smem_u32(wfull + wb), wphase, 202);
-                    const uint32_t wbase = smem_u32(wbuf + (size_t)wb * wbuf_stride);
-                    for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
-                        mbar_wait(smem_u32(full + stage), sphase, 203);
-                        tc_fence_after();
-                        const uint32_t sbase = smem_u32(stages + (size_t)stage * p.stage_bytes);
-                        for (int kd = 0; kd < p.ks; ++kd) {
-                            const int d_out = (p.ks == 3) ? d_in + 1 - kd : d_in;
-                            if (d_out < g.d0 || d_out >= g.d_hi) continue;
-                            const int first_d_in = (p.ks == 3) ? max(d_out - 1, 0) : d_out;
-                            const bool fresh = (cg == 0) && (d_in == first_d_in);
-                            const uint32_t dcol = tmem_base + (uint32_t)((set * p.Dc + (d_out - g.d0)) * p.accw);
-                            for (int kh = 0; kh < p.ks; ++kh) {
-                                for (int kw = 0; kw < p.ks; ++kw) {
-                                    const int tap = (kd * p.ks + kh) * p.ks + kw;
-                                    const uint32_t a_tap = sbase + (uint32_t)(kh * p.pitch_vox + kw) * 16u;
-                                    const uint32_t b_tap = wbase + (uint32_t)(tap * p.nbt) * (uint32_t)p.btile_bytes;
-                                    for (int t = 0; t < p.nterm; ++t) {
-                                        const uint32_t a_addr = a_tap + (uint32_t)p.term_aoff[t] * (uint32_t)p.blk_bytes;
-                                        const uint32_t a_lbo = (uint32_t)p.term_lbo_blocks[t] * (uint32_t)p.blk_bytes;
-                                        const uint32_t b_addr = b_tap + (uint32_t)p.term_btile[t] * (uint32_t)p.btile_bytes;
-                                        const uint64_t ad = p.swap_lbo_sbo ? make_smem_desc(a_addr, a_sbo, a_lbo)
-                                                                           : make_smem_desc(a_addr, a_lbo, a_sbo);
-                                        const uint64_t bd = p.swap_lbo_sbo ? make_smem_desc(b_addr, b_sbo, b_lbo)
-                                                                           : make_smem_desc(b_addr, b_lbo, b_sbo);
-                                        const uint32_t acc = (fresh && kh == 0 && kw == 0 && t == 0) ? 0u : 1u;
-                                        tc_mma_bf16(dcol, ad, bd, idesc[t], acc);
-                                    }
+        // ================= MMA issuer: the whole warp walks the loop (warp-uniform descriptor arithmetic),
+        //                   one elected lane issues tcgen05.mma / tcgen05.commit =================
+        const uint32_t elected = elect_one();
+        uint32_t a_term16[NTERM], a_lbo_field[NTERM], b_term16[NTERM], idesc[NTERM];
+#pragma unroll
+        for (int t = 0; t < NTERM; ++t) {
+            a_term16[t] = (uint32_t)(p.term_aoff[t] * p.blk_bytes) >> 4;
+            a_lbo_field[t] = ((uint32_t)(p.term_lbo_blocks[t] * p.blk_bytes) >> 4) << 16;
+            b_term16[t] = (uint32_t)(p.term_btile[t] * p.btile_bytes) >> 4;
+            idesc[t] = make_idesc(p.term_n[t]);
+        }
+        const uint32_t a_hi = (uint32_t)kPitch | (1u << 14);                      // SBO = kPitch*16 B, version 1
+        const uint32_t b_hi = 8u | (1u << 14);                                    // SBO = 128 B
+        const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;                   // LBO = nb_rows*16 B
+        const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per tap / 16
+        int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            const ItemGeom g = decode_item(p, item);
+            const int set = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201);
+            tc_fence_after();
+            for (int cg = 0; cg < p.ncg; ++cg) {
+                mbar_wait(smem_u32(wfull + wb), wphase, 202);
+                const uint32_t w16 = smem_u32(wbuf + (size_t)wb * wbuf_stride) >> 4;
+                for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
+                    mbar_wait(smem_u32(full + stage), sphase, 203);
+                    tc_fence_after();
+                    const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_bytes) >> 4;
+#pragma unroll 1
+                    for (int kd = 0; kd < KS; ++kd) {
+                        const int d_out = (KS == 3) ? d_in + 1 - kd : d_in;
+                        if (d_out < g.d0 || d_out >= g.d_hi) continue;
+                        const int first_d_in = (KS == 3) ? max(d_out - 1, 0) : d_out;
+                        uint32_t accflag = ((cg == 0) && (d_in == first_d_in)) ? 0u : 1u;
+                        const uint32_t dcol = tmem_base + (uint32_t)((set * p.Dc + (d_out - g.d0)) * p.accw);
+                        const uint32_t b_kd = (w16 + (uint32_t)(kd * KS * KS) * tap16) | b_lbo_field;
+#pragma unroll
+                        for (int kh = 0; kh < KS; ++kh) {
+#pragma unroll
+                            for (int kw = 0; kw < KS; ++kw) {
+                                const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
+                                const uint32_t b_tap = b_kd + (uint32_t)(kh * KS + kw) * tap16;
+#pragma unroll
+                                for (int t = 0; t < NTERM; ++t) {
+                                    tc_mma_issue(elected, dcol, (a_tap + a_term16[t]) | a_lbo_field[t], a_hi,
+                                                 b_tap + b_term16[t], b_hi, idesc[t], accflag);
+                                    accflag = 1u;
                                 }
                             }
                         }
-                        tc_commit(smem_u32(empty + stage));
-                        if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                     }
-                    tc_commit(smem_u32(wempty + wb));
-                    if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                    tc_commit_if(elected, smem_u32(empty + stage));
+                    if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                 }
-                tc_commit(smem_u32(accfull + set));
+                tc_commit_if(elected, smem_u32(wempty + wb));
+                if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
             }
+            tc_commit_if(elected, smem_u32(accfull + set));
         }
     } else {
         // ================= epilogue warps 2..5 =================
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;                 // tile row = TMEM lane
         const int lh = m / LEA_TC_TW, lw = m % LEA_TC_TW;
+        const int64_t sp = (int64_t)p.D * p.H * p.W;
         int it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const ItemGeom g = decode_item(p, item);
             const int set = it & 1, aphase = (it >> 1) & 1;
-            mbar_wait(smem_u32(accfull + set), aphase, 301);
-            tc_fence_after();
             const int h = g.h0 + lh, w = g.w0 + lw;
             const bool valid = (h < p.H) && (w < p.W);
+            mbar_wait(smem_u32(accfull + set), aphase, 301);
+            tc_fence_after();
             for (int j = 0; j < g.d_hi - g.d0; ++j) {
                 const int d = g.d0 + j;
                 const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * p.Dc + j) * p.accw);
-                const int ncb = p.dst_f32 ? 1 : (p.c_out >> 3);
-                for (int cb = 0; cb < ncb; ++cb) {
-                    float acc[8];
-                    tc_ld8(trow + (uint32_t)(cb * 8), acc);
+                for (int c16 = 0; c16 < p.NP; c16 += 16) {
+                    if (c16 >= p.c_out) break;
+                    // residual first: its global-load latency overlaps the TMEM reads
+                    float r16[16];
+                    const bool two = (c16 + 8 < p.c_out);
+                    if (p.has_res && valid) {
+                        lea_vol_load8(p.res, g.b, ((p.res_c0 + c16) >> 3), d, h, w, r16);
+                        if (two) lea_vol_load8(p.res, g.b, ((p.res_c0 + c16) >> 3) + 1, d, h, w, r16 + 8);
+                    }
+                    float acc[16];
+                    tc_ld16_wait(trow + (uint32_t)c16, acc);
                     for (int gidx = 1; gidx < p.ngroups; ++gidx) {
-                        float t8[8];
-                        tc_ld8(trow + (uint32_t)(gidx * p.NP + cb * 8), t8);
+                        float t16[16];
+                        tc_ld16_wait(trow + (uint32_t)(gidx * p.NP + c16), t16);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) acc[i] += t8[i];
+                        for (int i = 0; i < 16; ++i) acc[i] += t16[i];
                     }
                     if (!valid) continue;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int n = cb * 8 + i;
-                        if (n < p.c_out) {
-                            float v = acc[i];
-                            if (p.bn_scale) v = v * __ldg(p.bn_scale + n) + __ldg(p.bn_shift + n);
-                            if (p.relu) v = fmaxf(v, 0.0f);
-                            acc[i] = v;
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
+                        if (p.relu) v = fmaxf(v, 0.0f);
+                        acc[i] = v;
                     }
                     if (p.dst_f32) {
-                        const int64_t sp = (int64_t)p.D * p.H * p.W;
                         float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h) * p.W + w;
-                        for (int n = 0; n < p.c_out && n < 8; ++n) o[n * sp] = acc[n];
+                        for (int n = 0; n < 16 && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
                     } else {
                         if (p.has_res) {
-                            float r8[8];
-                            lea_vol_load8(p.res, g.b, (p.res_c0 >> 3) + cb, d, h, w, r8);
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) acc[i] += r8[i];
+                            for (int i = 0; i < 16; ++i) acc[i] += (i < 8 || two) ? r16[i] : 0.0f;
                         }
-                        lea_vol_store8(p.dst, g.b, (p.dst_c0 >> 3) + cb, d, h, w, acc);
+                        lea_vol_store8(p.dst, g.b, ((p.dst_c0 + c16) >> 3), d, h, w, acc);
+                        if (two) lea_vol_store8(p.dst, g.b, ((p.dst_c0 + c16) >> 3) + 1, d, h, w, acc + 8);
                     }
                 }
             }
@@ -340,6 +399,18 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
+}
+
+typedef void (*TcKernelFn)(const CUtensorMap, const TcParams);
+static TcKernelFn tc_kernel_for(int ks, int nterm) {
+    if (ks == 3) {
+        if (nterm == 1) return lea_conv_tc_kernel<3, 1>;
+        if (nterm == 2) return lea_conv_tc_kernel<3, 2>;
+        return lea_conv_tc_kernel<3, 3>;
+    }
+    if (nterm == 1) return lea_conv_tc_kernel<1, 1>;
+    if (nterm == 2) return lea_conv_tc_kernel<1, 2>;
+    return lea_conv_tc_kernel<1, 3>;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -510,12 +581,12 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    cudaError_t e = cudaFuncSetAttribute(lea_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kSmemBudget);
+    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
     // always request the full budget so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
-    lea_conv_tc_kernel<<<grid, kThreads, kSmemBudget, (cudaStream_t)stream>>>(tmap, p);
+    kernel<<<grid, kThreads, kSmemBudget, (cudaStream_t)stream>>>(tmap, p);
     (void)smem;
     e = cudaGetLastError();
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: launch failed: %s", cudaGetErrorString(e));
