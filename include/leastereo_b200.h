@@ -68,8 +68,11 @@ int lea_pack_planes(const float* src, const lea_vol* dst, int32_t dst_c0, int32_
 int lea_unpack_planes(const lea_vol* src, int32_t src_c0, int32_t c, float* dst, void* stream);
 
 /* ---- trilinear resample, align_corners=True: retrain/skip_model_3d.py:44-51, :162-169 ----------------------- */
+/* Optional epilogue y = relu(x*bn_scale[ch] + bn_shift[ch]) (bn_* may be NULL): a 1x1x1 convolution commutes with
+ * the interpolation, so for UP-sampling cells the engine runs the cell's 1x1x1 conv on the small volume and applies
+ * its BatchNorm+ReLU here, after interpolating (same value in exact arithmetic, ~8x less traffic). */
 int lea_trilinear_ac(const lea_vol* src, int32_t src_c0, const lea_vol* dst, int32_t dst_c0, int32_t c,
-                     void* stream);
+                     const float* bn_scale, const float* bn_shift, int32_t relu, void* stream);
 
 /* ---- ConvBR -------------------------------------------------------------------------------------------------- */
 /* fp32-FMA kernel; weight = PyTorch layout fp32 (c_out, c_in, k, k, k). */

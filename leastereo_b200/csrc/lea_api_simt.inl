@@ -68,14 +68,15 @@ extern "C" int lea_unpack_planes(const lea_vol* src, int32_t src_c0, int32_t c, 
 }
 
 extern "C" int lea_trilinear_ac(const lea_vol* src, int32_t src_c0, const lea_vol* dst, int32_t dst_c0, int32_t c,
-                                void* stream) {
+                                const float* bn_scale, const float* bn_shift, int32_t relu, void* stream) {
+    LEA_CHECK((bn_scale == nullptr) == (bn_shift == nullptr), "trilinear_ac: bn_scale/bn_shift must come together");
     if (lea_check_vol(src, "trilinear_ac src") || lea_check_vol(dst, "trilinear_ac dst")) return 1;
     if (lea_check_slice(src, src_c0, c, "trilinear_ac src") || lea_check_slice(dst, dst_c0, c, "trilinear_ac dst"))
         return 1;
     LEA_CHECK(src->B == dst->B, "trilinear_ac: batch mismatch");
     LEA_CHECK((int64_t)dst->B * (c >> 3) <= 65535, "trilinear_ac: grid too large");
     LEA_LAUNCH(lea_trilinear_ac_kernel, dim3((dst->W + 127) / 128, dst->D * dst->H, dst->B * (c >> 3)), dim3(128), 0,
-               stream, *src, src_c0, *dst, dst_c0, c);
+               stream, *src, src_c0, *dst, dst_c0, c, bn_scale, bn_shift, relu);
     return LEA_POST_LAUNCH();
 }
 

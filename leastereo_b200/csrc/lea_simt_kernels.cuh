@@ -137,7 +137,8 @@ LEA_HD lea_axis_lerp lea_axis_ac(int dst, int in_n, int out_n) {
 }
 
 __global__ void __launch_bounds__(128)
-lea_trilinear_ac_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c) {
+lea_trilinear_ac_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c,
+                        const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int relu) {
     const int w = blockIdx.x * 128 + threadIdx.x;
     if (w >= dst.W) return;
     const int h = blockIdx.y % dst.H, d = blockIdx.y / dst.H;
@@ -169,6 +170,14 @@ lea_trilinear_ac_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c)
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) out[j] += wd * accd[j];
+    }
+    if (bn_scale) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = out[j] * __ldg(bn_scale + cb * 8 + j) + __ldg(bn_shift + cb * 8 + j);
+    }
+    if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = out[j] > 0.0f ? out[j] : 0.0f;
     }
     lea_vol_store8(dst, b, (dst_c0 >> 3) + cb, d, h, w, out);
 }

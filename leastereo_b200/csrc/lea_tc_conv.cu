@@ -430,7 +430,7 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) 
     if (!(c_out == 1 || (c_out % 8 == 0 && c_out >= 8 && c_out <= 64))) return s;
     s.c8 = (c_in == 8);
     if (s.c8 ? (P != 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
-    s.NP = c_out <= 16 ? 16 : (c_out <= 32 ? 32 : 64);
+    s.NP = (c_out + 15) & ~15;                                 // UMMA N granularity at M = 128
     s.taps = ks * ks * ks;
     if (s.c8) { s.nb_rows = s.NP; s.nbt = 2; s.ncg = 1; s.accw = s.NP; s.ngroups = 1; }
     else      { s.nb_rows = P * s.NP; s.nbt = 1; s.ncg = c_in / 16; s.accw = P * s.NP; s.ngroups = P; }

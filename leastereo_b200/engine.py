@@ -41,18 +41,27 @@ class Slice:
 
 @dataclass
 class Step:
-    kind: str            # "conv_simt" | "conv_tc" | "resample"
-    name: str            # module path, for per-kernel timing reports
-    args: tuple
-    flops: float = 0.0   # 2*M*N*K for convs
-    bytes: float = 0.0   # algorithmic bytes read+written
+    kind: str                      # "conv_simt" | "conv_tc" | "resample"
+    name: str                      # module path(s), for per-kernel timing reports
+    flops: float = 0.0             # 2*M*N*K for convs
+    bytes: float = 0.0             # algorithmic bytes read+written
+    # conv
+    p: object = None               # lea_conv
+    mods: tuple = ()               # ConvBR3d modules whose weights are concatenated along c_out (batched conv)
+    weight: Optional[torch.Tensor] = None     # fp32 (c_out, c_in, k, k, k) the launch reads (simt) / packs (tc)
+    wcat: Optional[torch.Tensor] = None       # persistent concat buffer when len(mods) > 1
+    opts: object = None
+    image: Optional[torch.Tensor] = None      # packed tcgen05 weight image
+    ref: Optional[torch.Tensor] = None
+    # resample
+    rs: tuple = ()
 
 
 class MatchingPlan:
     """Launch list + buffers of ``newMatching.forward`` for one (device, B, D, H, W, planes, conv mode)."""
 
     def __init__(self, matching: newMatching, ops: Ops, B: int, spatial: Tuple[int, int, int], planes: int,
-                 device, conv_mode: str = "simt", mma_terms: int = 0):
+                 device, conv_mode: str = "simt", mma_terms: int = 0, fuse: bool = True):
         if conv_mode not in ("simt", "tc"):
             raise ValueError("conv mode must be 'simt' or 'tc'")
         self.m = matching
@@ -61,12 +70,13 @@ class MatchingPlan:
         self.device = torch.device(device)
         self.conv_mode = conv_mode
         self.mma_terms = mma_terms
+        self.fuse = fuse               # graph-level rewrites: batched sibling convs, conv-before-upsample
         self.steps: List[Step] = []
         self.volumes: List[PlanesVol] = []
-        self._convs: List[Tuple[ConvBR3d, int]] = []     # (module, offset into bn buffer)
+        self._bn_users: List[Tuple[ConvBR3d, int]] = []     # (module, offset into the BN buffers)
         self._bn_channels = 0
         self._eye: Dict[int, torch.Tensor] = {}
-        self._tc_images: Dict[int, torch.Tensor] = {}
+        self._resampled: Dict[tuple, Slice] = {}
         self._param_key = None
         total_bn = sum(mod.conv.out_channels for mod in matching.modules() if isinstance(mod, ConvBR3d))
         self.bn_scale = torch.ones(total_bn, dtype=torch.float32, device=self.device)
@@ -82,34 +92,72 @@ class MatchingPlan:
     def workspace_bytes(self) -> int:
         return sum(v.nbytes() for v in self.volumes)
 
-    # ---- step emitters --------------------------------------------------------------------------------
-    def _resample(self, name: str, src: Slice, spatial) -> Slice:
-        dst = self._vol(src.c, spatial)
-        nbytes = 2.0 * self.P * 8 * (src.c // 8) * self.B * (_prod(src.spatial) + _prod(spatial))
-        self.steps.append(Step("resample", name, (src.vol, src.c0, src.c, dst, 0), 0.0, nbytes))
-        return Slice(dst, 0, src.c)
+    def _bn_slices(self, mods) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Contiguous BN scale/shift slices for a list of modules (concatenated in order)."""
+        off0 = self._bn_channels
+        for mod in mods:
+            c = mod.conv.out_channels
+            self._bn_users.append((mod, self._bn_channels))
+            self._bn_channels += c
+        return self.bn_scale[off0: self._bn_channels], self.bn_shift[off0: self._bn_channels]
 
-    def _emit_conv(self, name: str, mod: Optional[ConvBR3d], src: Slice, dst: Optional[Slice], *, res: bool = False,
-                   dst_f32: Optional[torch.Tensor] = None, identity_c: int = 0):
-        """Append one ConvBR launch (``mod is None``: identity 1x1x1 used for ``skip_connect`` / state copies)."""
-        if mod is None:
+    # ---- step emitters --------------------------------------------------------------------------------
+    def _resample(self, name: str, src: Slice, spatial, dst: Optional[Slice] = None,
+                  bn_of: Optional[ConvBR3d] = None, relu: bool = False) -> Slice:
+        cache_key = None
+        if dst is None and bn_of is None and not relu:
+            # the same tensor is often resampled twice (as s1 of cell i and s0 of cell i+1): do it once
+            cache_key = (id(src.vol), src.c0, src.c, tuple(spatial))
+            if cache_key in self._resampled:
+                return self._resampled[cache_key]
+        if dst is None:
+            dst = Slice(self._vol(src.c, spatial), 0, src.c)
+        if cache_key is not None:
+            self._resampled[cache_key] = dst
+        scale = shift = None
+        if bn_of is not None and bn_of.use_bn:
+            scale, shift = self._bn_slices([bn_of])
+        nbytes = 2.0 * self.P * src.c * self.B * (_prod(src.spatial) + _prod(spatial))
+        self.steps.append(Step("resample", name, 0.0, nbytes,
+                               rs=(src.vol, src.c0, src.c, dst.vol, dst.c0, scale, shift, relu)))
+        return dst
+
+    def _emit_conv(self, name: str, mods, src: Slice, dst: Optional[Slice], *, res: bool = False,
+                   dst_f32: Optional[torch.Tensor] = None, identity_c: int = 0, raw: bool = False):
+        """Append one ConvBR launch.
+
+        ``mods``: a ConvBR3d, or a list of ConvBR3d reading the same input whose outputs are adjacent channel
+        slices (their weights / BN vectors are concatenated along c_out: one launch, one pass over the input);
+        ``None`` = identity 1x1x1 (``skip_connect`` / state copy).  ``raw`` drops BN+ReLU (applied later by the
+        up-sampling resample, see ``_resample``)."""
+        wcat = None
+        if mods is None:
+            mods = ()
             c_in = c_out = identity_c
             k, relu, scale, shift = 1, False, None, None
             weight = self._identity_weight(identity_c)
         else:
-            w = mod.conv.weight
-            c_out, c_in, k = w.shape[0], w.shape[1], w.shape[2]
-            relu = mod.relu
-            weight = w.detach()
+            mods = tuple(mods) if isinstance(mods, (list, tuple)) else (mods,)
+            w0 = mods[0].conv.weight
+            c_in, k = w0.shape[1], w0.shape[2]
+            c_out = sum(m.conv.out_channels for m in mods)
+            relu = mods[0].relu and not raw
+            use_bn = mods[0].use_bn and not raw
+            for m in mods[1:]:
+                if (m.conv.weight.shape[1], m.conv.weight.shape[2], m.relu, m.use_bn) != (c_in, k, mods[0].relu, mods[0].use_bn):
+                    raise LeaError("%s: batched convs must agree on c_in, kernel size, bn and relu" % name)
             scale = shift = None
-            if mod.use_bn:
-                off = self._bn_channels
-                scale = self.bn_scale[off: off + c_out]
-                shift = self.bn_shift[off: off + c_out]
-                self._convs.append((mod, off))
-                self._bn_channels += c_out
+            if use_bn:
+                scale, shift = self._bn_slices(mods)
+            if len(mods) == 1:
+                weight = w0.detach()
+            else:
+                wcat = torch.empty((c_out, c_in, k, k, k), dtype=torch.float32, device=self.device)
+                weight = wcat
         if src.c != c_in:
             raise LeaError("%s: input has %d channels, conv expects %d" % (name, src.c, c_in))
+        if dst is not None and dst.c != c_out:
+            raise LeaError("%s: output slice has %d channels, conv produces %d" % (name, dst.c, c_out))
         p = self.ops.make_conv(src.vol, src.c0, c_in, c_out, k, scale, shift, relu,
                                dst=None if dst is None else dst.vol, dst_c0=0 if dst is None else dst.c0,
                                res=dst.vol if res else None, res_c0=dst.c0 if res else 0, dst_f32=dst_f32)
@@ -119,33 +167,47 @@ class MatchingPlan:
             nbytes = 2.0 * self.P * m_vox * (c_in + c_out * (2 if res else 1))
         else:
             nbytes = 2.0 * self.P * m_vox * c_in + 4.0 * m_vox * c_out
-        use_tc = self.conv_mode == "tc" and mod is not None and \
+        use_tc = self.conv_mode == "tc" and len(mods) > 0 and \
             self.ops.tc_weight_image_bytes(c_in, c_out, k, self.P) > 0
+        opts = None
         if use_tc:
             opts = lea_tc_opts()
             opts.mma_terms = self.mma_terms
-            self.steps.append(Step("conv_tc", name, (p, mod, opts, src.vol.t), flops, nbytes))
-        else:
-            self.steps.append(Step("conv_simt", name, (p, weight, mod, src.vol.t), flops, nbytes))
+        self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
+                               weight=weight, wcat=wcat, opts=opts, ref=src.vol.t))
 
     def _identity_weight(self, c: int) -> torch.Tensor:
         if c not in self._eye:
             self._eye[c] = torch.eye(c, dtype=torch.float32, device=self.device).reshape(c, c, 1, 1, 1).contiguous()
         return self._eye[c]
 
+    def _max_batched_c_out(self) -> int:
+        return 64
+
     # ---- network construction -------------------------------------------------------------------------
+    def _pre(self, name: str, mod: ConvBR3d, src: Slice, spatial, dst: Slice):
+        """Cell input path: [resample to ``spatial``] -> 1x1x1 ConvBR -> ``dst``  (skip_model_3d.py:44-53).
+        When the resample ENLARGES the volume the conv runs first on the small volume (it commutes with the
+        interpolation) and BN+ReLU are applied by the resample kernel's epilogue."""
+        if src.spatial == tuple(spatial):
+            self._emit_conv(name, mod, src, dst)
+        elif self.fuse and _prod(src.spatial) < _prod(spatial):
+            small = Slice(self._vol(dst.c, src.spatial), 0, dst.c)
+            self._emit_conv(name + "(raw,low-res)", mod, src, small, raw=True)
+            self._resample(name + ".upsample+bn+relu", small, spatial, dst=dst, bn_of=mod, relu=mod.relu)
+        else:
+            r = self._resample(name + ".resample", src, spatial)
+            self._emit_conv(name, mod, r, dst)
+
     def _cell(self, i: int, s0: Slice, s1: Slice, out: Optional[Slice] = None) -> Tuple[Slice, Slice]:
         cell = self.m.cells[i]
         spec = cell.spec
         name = "cells.%d" % i
         prev_input = s1
         c_out = spec.c_out
+        sp = s1.spatial
         if spec.downup_sample != 0:
             sp = tuple(scale_dimension(n, spec.scale) for n in s1.spatial)
-            s1 = self._resample(name + ".resample_s1", s1, sp)
-        if s0.spatial != s1.spatial:
-            s0 = self._resample(name + ".resample_s0", s0, s1.spatial)
-        sp = s1.spatial
         bm = self.m._block_multiplier
         n_states = 2 + len(spec.steps)
         first_in_concat = n_states - bm
@@ -156,34 +218,76 @@ class MatchingPlan:
         elif out.spatial != sp or out.c != bm * c_out:
             raise LeaError("cell %d output %s x%d does not fit the skip-concat slot %s x%d (the reference's torch.cat "
                            "would fail too)" % (i, sp, bm * c_out, out.spatial, out.c))
+        slots: Dict[int, Slice] = {}
 
         def state_slot(q: int) -> Slice:
-            pos = q - first_in_concat
-            if pos >= 0:
-                return Slice(out.vol, out.c0 + pos * c_out, c_out)
-            return Slice(self._vol(c_out, sp), 0, c_out)
+            if q not in slots:
+                pos = q - first_in_concat
+                slots[q] = Slice(out.vol, out.c0 + pos * c_out, c_out) if pos >= 0 else \
+                    Slice(self._vol(c_out, sp), 0, c_out)
+            return slots[q]
 
+        # ---- the two pre-processed inputs (states 0 and 1)
         if s0.c != c_out:
-            d0 = state_slot(0)
-            self._emit_conv(name + ".pre_preprocess", cell.pre_preprocess, s0, d0)
-            s0 = d0
-        elif first_in_concat <= 0:
-            d0 = state_slot(0)
-            self._emit_conv(name + ".s0_copy", None, s0, d0, identity_c=c_out)
-            s0 = d0
-        d1 = state_slot(1)
-        self._emit_conv(name + ".preprocess", cell.preprocess, s1, d1)
-        states = [s0, d1]
+            self._pre(name + ".pre_preprocess", cell.pre_preprocess, s0, sp, state_slot(0))
+        else:
+            r = s0 if s0.spatial == sp else self._resample(name + ".resample_s0", s0, sp)
+            if first_in_concat <= 0:
+                self._emit_conv(name + ".s0_copy", None, r, state_slot(0), identity_c=c_out)
+            else:
+                slots[0] = r
+        self._pre(name + ".preprocess", cell.preprocess, s1, sp, state_slot(1))
+
+        # ---- step sums: state q = sum of ops over selected earlier states (skip_model_3d.py:57-72)
+        consumers: Dict[int, List[Tuple[int, int]]] = {}        # source state -> [(target state, ops index)]
+        pending: Dict[int, int] = {}                             # target state -> contributions still missing
         for k, step in enumerate(spec.steps):
-            dst = state_slot(2 + k)
-            for n, (j, opi) in enumerate(step):
+            pending[2 + k] = len(step)
+            for (j, opi) in step:
+                consumers.setdefault(j, []).append((2 + k, opi))
+        written: Dict[int, bool] = {}
+        done = {0, 1}
+        emitted = set()
+        while len(emitted) < len(consumers):
+            ready = [j for j in consumers if j in done and j not in emitted]
+            if not ready:
+                raise LeaError("cell %d: genotype wiring has a cycle" % i)
+            # the source with most consumers first: its sibling convs can then all be first writers -> one launch
+            j = max(ready, key=lambda q: (len(consumers[q]), -q))
+            emitted.add(j)
+            todo = sorted(consumers[j])
+            while todo:
+                tgt, opi = todo[0]
                 op = cell._ops[opi]
+                group = [(tgt, opi)]
+                if self.fuse and not isinstance(op, Identity3d):
+                    # extend with siblings: consecutive target slots, same first-writer status, all convs
+                    for (t2, o2) in todo[1:]:
+                        pt, _ = group[-1]
+                        same_buf = (state_slot(t2).vol is state_slot(pt).vol and
+                                    state_slot(t2).c0 == state_slot(pt).c0 + c_out)
+                        if (t2 == pt + 1 and same_buf and written.get(t2, False) == written.get(tgt, False)
+                                and not isinstance(cell._ops[o2], Identity3d)
+                                and (len(group) + 1) * c_out <= self._max_batched_c_out()):
+                            group.append((t2, o2))
+                        else:
+                            break
+                todo = [x for x in todo if x not in group]
+                first = state_slot(group[0][0])
+                dst = Slice(first.vol, first.c0, c_out * len(group))
+                res = written.get(tgt, False)
                 if isinstance(op, Identity3d):
-                    self._emit_conv("%s._ops.%d(skip)" % (name, opi), None, states[j], dst, res=n > 0,
+                    self._emit_conv("%s._ops.%d(skip)" % (name, opi), None, state_slot(j), dst, res=res,
                                     identity_c=c_out)
                 else:
-                    self._emit_conv("%s._ops.%d" % (name, opi), op, states[j], dst, res=n > 0)
-            states.append(dst)
+                    mods = [cell._ops[o] for (_, o) in group]
+                    nm = "%s._ops.%s" % (name, "+".join(str(o) for (_, o) in group))
+                    self._emit_conv(nm, mods, state_slot(j), dst, res=res)
+                for (t2, _) in group:
+                    written[t2] = True
+                    pending[t2] -= 1
+                    if pending[t2] == 0:
+                        done.add(t2)
         return prev_input, out
 
     def _build(self):
@@ -250,56 +354,57 @@ class MatchingPlan:
     # ---- parameters -----------------------------------------------------------------------------------
     def _current_param_key(self):
         key = []
-        for mod, _ in self._convs:
+        for mod, _ in self._bn_users:
             for t in (mod.bn.weight, mod.bn.bias, mod.bn.running_mean, mod.bn.running_var):
                 key.append((t.data_ptr(), t._version))
         for s in self.steps:
-            mod = s.args[2] if s.kind == "conv_simt" else (s.args[1] if s.kind == "conv_tc" else None)
-            if mod is not None:
+            for mod in s.mods:
                 t = mod.conv.weight
                 key.append((t.data_ptr(), t._version))
         return tuple(key)
 
     def refresh_params(self, force: bool = False):
-        """Recompute BN scale/shift (and packed tensor-core weight images) when parameters changed."""
+        """Recompute BN scale/shift, sibling-conv weight concats and packed tensor-core weight images when any
+        parameter changed (checked through tensor versions / storage addresses)."""
         key = self._current_param_key()
         if not force and key == self._param_key:
             return
         with torch.no_grad():
-            if self._convs:
-                g = torch.cat([m.bn.weight.detach().float().reshape(-1) for m, _ in self._convs])
-                b = torch.cat([m.bn.bias.detach().float().reshape(-1) for m, _ in self._convs])
-                mu = torch.cat([m.bn.running_mean.detach().float().reshape(-1) for m, _ in self._convs])
-                var = torch.cat([m.bn.running_var.detach().float().reshape(-1) for m, _ in self._convs])
-                eps = torch.cat([torch.full((m.bn.num_features,), float(m.bn.eps)) for m, _ in self._convs]).to(g.device)
+            if self._bn_users:
+                users = [m for m, _ in self._bn_users]
+                g = torch.cat([m.bn.weight.detach().float().reshape(-1) for m in users])
+                b = torch.cat([m.bn.bias.detach().float().reshape(-1) for m in users])
+                mu = torch.cat([m.bn.running_mean.detach().float().reshape(-1) for m in users])
+                var = torch.cat([m.bn.running_var.detach().float().reshape(-1) for m in users])
+                eps = torch.cat([torch.full((m.bn.num_features,), float(m.bn.eps)) for m in users]).to(g.device)
                 scale = g / torch.sqrt(var + eps)
                 self.bn_scale[: scale.numel()].copy_(scale)
                 self.bn_shift[: scale.numel()].copy_(b - mu * scale)
             for s in self.steps:
-                if s.kind == "conv_simt":
-                    p, weight, mod, ref = s.args
-                    if mod is not None:
-                        w = mod.conv.weight.detach()
+                if not s.kind.startswith("conv"):
+                    continue
+                if s.mods:
+                    for mod in s.mods:
+                        w = mod.conv.weight
                         if not (w.is_contiguous() and w.dtype == torch.float32 and w.device == self.device):
                             raise LeaError("%s: weights must be contiguous fp32 on %s" % (s.name, self.device))
-                        s.args = (p, w, mod, ref)
-                elif s.kind == "conv_tc":
-                    p, mod, opts, ref = s.args
-                    img = self._tc_images.get(id(mod))
-                    self._tc_images[id(mod)] = self.ops.pack_weights_tc(mod.conv.weight.detach(), self.P, out=img)
+                    if s.wcat is not None:
+                        torch.cat([mod.conv.weight.detach() for mod in s.mods], dim=0, out=s.wcat)
+                    else:
+                        s.weight = s.mods[0].conv.weight.detach()
+                if s.kind == "conv_tc":
+                    s.image = self.ops.pack_weights_tc(s.weight, self.P, out=s.image)
         self._param_key = key
 
     # ---- execution ------------------------------------------------------------------------------------
     def run_step(self, s: Step):
         if s.kind == "resample":
-            src, c0, c, dst, dst_c0 = s.args
-            self.ops.trilinear_ac(src, c0, c, dst, dst_c0)
+            src, c0, c, dst, dst_c0, scale, shift, relu = s.rs
+            self.ops.trilinear_ac(src, c0, c, dst, dst_c0, scale, shift, relu)
         elif s.kind == "conv_simt":
-            p, weight, _, ref = s.args
-            self.ops.conv3d_simt(p, weight, ref)
+            self.ops.conv3d_simt(s.p, s.weight, s.ref)
         elif s.kind == "conv_tc":
-            p, mod, opts, ref = s.args
-            self.ops.conv3d_tc(p, self._tc_images[id(mod)], opts, ref)
+            self.ops.conv3d_tc(s.p, s.image, s.opts, s.ref)
         else:
             raise LeaError("unknown step " + s.kind)
 
@@ -326,7 +431,7 @@ def _prod(t):
 # module-level entry points used by the nn.Module boundary
 # --------------------------------------------------------------------------------------------------------
 
-DEFAULT_OPTIONS = {"planes": 2, "conv": "simt", "mma_terms": 0, "assume_frozen": False}
+DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "assume_frozen": False}
 
 
 def _options(model) -> dict:
@@ -350,13 +455,14 @@ def invalidate_cached_plans(model):
 
 def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops: Optional[Ops] = None) -> MatchingPlan:
     ops = ops or get_ops()
-    key = (str(device), B, tuple(spatial), options["planes"], options["conv"], options["mma_terms"], id(ops))
+    key = (str(device), B, tuple(spatial), options["planes"], options["conv"], options["mma_terms"],
+           bool(options.get("fuse", True)), id(ops))
     with _LOCK:
         plans = _plans(matching)
         plan = plans.get(key)
         if plan is None:
             plan = MatchingPlan(matching, ops, B, spatial, options["planes"], device, options["conv"],
-                                options["mma_terms"])
+                                options["mma_terms"], bool(options.get("fuse", True)))
             plans[key] = plan
     return plan
 

@@ -46,7 +46,7 @@ SYMBOLS = {
     "lea_cost_volume_planes": (C.c_int, [_vp, _vp, _VOLP, _i32, _vp]),
     "lea_pack_planes": (C.c_int, [_vp, _VOLP, _i32, _i32, _vp]),
     "lea_unpack_planes": (C.c_int, [_VOLP, _i32, _i32, _vp, _vp]),
-    "lea_trilinear_ac": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp]),
+    "lea_trilinear_ac": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp, _vp, _i32, _vp]),
     "lea_conv3d_simt": (C.c_int, [_CONVP, _vp, _vp]),
     "lea_tc_weight_image_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "lea_pack_weights_tc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
@@ -190,11 +190,16 @@ class Ops:
         return out
 
     # ---- trilinear --------------------------------------------------------------------------------------
-    def trilinear_ac(self, src: PlanesVol, src_c0: int, c: int, dst: PlanesVol, dst_c0: int = 0):
+    def trilinear_ac(self, src: PlanesVol, src_c0: int, c: int, dst: PlanesVol, dst_c0: int = 0,
+                     bn_scale: Optional[torch.Tensor] = None, bn_shift: Optional[torch.Tensor] = None,
+                     relu: bool = False):
         self._dev(src.t, dst.t)
         s, d = src.struct(), dst.struct()
+        sc = bn_scale.data_ptr() if bn_scale is not None else None
+        sh = bn_shift.data_ptr() if bn_shift is not None else None
         with torch.cuda.device(src.t.device) if src.t.is_cuda else _null():
-            self._check(self.lib.lea_trilinear_ac(C.byref(s), src_c0, C.byref(d), dst_c0, c, self._stream(src.t)))
+            self._check(self.lib.lea_trilinear_ac(C.byref(s), src_c0, C.byref(d), dst_c0, c, sc, sh, int(bool(relu)),
+                                                  self._stream(src.t)))
 
     # ---- conv -------------------------------------------------------------------------------------------
     def make_conv(self, src: PlanesVol, src_c0: int, c_in: int, c_out: int, ksize: int,

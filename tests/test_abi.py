@@ -50,7 +50,7 @@ def test_argument_validation_without_gpu(lib_path):
     from leastereo_b200.kernels import Ops, lea_vol
     ops = Ops(lib_path, require_device_build=True)
     v = lea_vol(0, 1, 12, 2, 4, 4, 4)      # null data, channels not a multiple of 8
-    rc = ops.lib.lea_trilinear_ac(ctypes.byref(v), 0, ctypes.byref(v), 0, 8, None)
+    rc = ops.lib.lea_trilinear_ac(ctypes.byref(v), 0, ctypes.byref(v), 0, 8, None, None, 0, None)
     assert rc != 0 and b"null volume" in ops.lib.lea_last_error()
     assert ops.tc_weight_image_bytes(64, 32, 3, 2) == 4 * 27 * 2 * 64 * 16
     assert ops.tc_weight_image_bytes(12, 32, 3, 2) == 0
