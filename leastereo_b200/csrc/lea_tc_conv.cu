@@ -207,7 +207,46 @@ __device__ __forceinline__ void tc_ld16_wait(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-template <int KS, int NTERM>
+// ---- epilogue helpers with the plane count known at compile time -------------------------------------------
+template <int PL>
+__device__ __forceinline__ void ep_load_raw8(const lea_vol& v, int b, int cb, int d, int h, int w, uint4* q) {
+    const uint4* base = reinterpret_cast<const uint4*>(v.data);
+    const int64_t g = lea_vol_group(v, b, cb, 0, d, h, w);
+    const int64_t ps = lea_vol_plane_stride(v);
+#pragma unroll
+    for (int pl = 0; pl < PL; ++pl) q[pl] = __ldg(base + g + pl * ps);
+}
+template <int PL>
+__device__ __forceinline__ void ep_add_raw8(const uint4* q, float* f) {
+#pragma unroll
+    for (int pl = 0; pl < PL; ++pl) {
+        const uint32_t w4[4] = {q[pl].x, q[pl].y, q[pl].z, q[pl].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f[2 * i] += __uint_as_float(w4[i] << 16);
+            f[2 * i + 1] += __uint_as_float(w4[i] & 0xffff0000u);
+        }
+    }
+}
+template <int PL>
+__device__ __forceinline__ void ep_store8(const lea_vol& v, int b, int cb, int d, int h, int w, const float* f) {
+    uint4* base = reinterpret_cast<uint4*>(v.data);
+    const int64_t g = lea_vol_group(v, b, cb, 0, d, h, w);
+    const int64_t ps = lea_vol_plane_stride(v);
+    uint32_t q[PL][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint16_t a[3], c[3];
+        lea_split_planes(f[2 * i], PL, a);
+        lea_split_planes(f[2 * i + 1], PL, c);
+#pragma unroll
+        for (int pl = 0; pl < PL; ++pl) q[pl][i] = (uint32_t)a[pl] | ((uint32_t)c[pl] << 16);
+    }
+#pragma unroll
+    for (int pl = 0; pl < PL; ++pl) base[g + pl * ps] = make_uint4(q[pl][0], q[pl][1], q[pl][2], q[pl][3]);
+}
+
+template <int KS, int NTERM, int PL>
 __global__ void __launch_bounds__(kThreads, 1)
 lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -338,6 +377,9 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
     } else {
         // ================= epilogue warps 2..5 =================
+        // Thread m owns output voxel m of the tile (TMEM lane m).  Depth slices are processed kJB at a time so that
+        // the residual reads of kJB slices are in flight together (the epilogue is otherwise latency-bound).
+        constexpr int kJB = 4;
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;                 // tile row = TMEM lane
         const int lh = m / LEA_TC_TW, lw = m % LEA_TC_TW;
@@ -348,45 +390,60 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const int set = it & 1, aphase = (it >> 1) & 1;
             const int h = g.h0 + lh, w = g.w0 + lw;
             const bool valid = (h < p.H) && (w < p.W);
-            mbar_wait(smem_u32(accfull + set), aphase, 301);
-            tc_fence_after();
-            for (int j = 0; j < g.d_hi - g.d0; ++j) {
-                const int d = g.d0 + j;
-                const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((set * p.Dc + j) * p.accw);
-                for (int c16 = 0; c16 < p.NP; c16 += 16) {
-                    if (c16 >= p.c_out) break;
-                    // residual first: its global-load latency overlaps the TMEM reads
-                    float r16[16];
+            const int nd = g.d_hi - g.d0;
+            bool waited = false;
+            for (int j0 = 0; j0 < nd; j0 += kJB) {
+                for (int c16 = 0; c16 < p.c_out; c16 += 16) {
                     const bool two = (c16 + 8 < p.c_out);
+                    uint4 rq[kJB][2][PL];
                     if (p.has_res && valid) {
-                        lea_vol_load8(p.res, g.b, ((p.res_c0 + c16) >> 3), d, h, w, r16);
-                        if (two) lea_vol_load8(p.res, g.b, ((p.res_c0 + c16) >> 3) + 1, d, h, w, r16 + 8);
-                    }
-                    float acc[16];
-                    tc_ld16_wait(trow + (uint32_t)c16, acc);
-                    for (int gidx = 1; gidx < p.ngroups; ++gidx) {
-                        float t16[16];
-                        tc_ld16_wait(trow + (uint32_t)(gidx * p.NP + c16), t16);
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[i] += t16[i];
-                    }
-                    if (!valid) continue;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
-                        if (p.relu) v = fmaxf(v, 0.0f);
-                        acc[i] = v;
-                    }
-                    if (p.dst_f32) {
-                        float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h) * p.W + w;
-                        for (int n = 0; n < 16 && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
-                    } else {
-                        if (p.has_res) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[i] += (i < 8 || two) ? r16[i] : 0.0f;
+                        for (int jj = 0; jj < kJB; ++jj) {
+                            if (j0 + jj < nd) {
+                                ep_load_raw8<PL>(p.res, g.b, (p.res_c0 + c16) >> 3, g.d0 + j0 + jj, h, w, rq[jj][0]);
+                                if (two)
+                                    ep_load_raw8<PL>(p.res, g.b, ((p.res_c0 + c16) >> 3) + 1, g.d0 + j0 + jj, h, w,
+                                                     rq[jj][1]);
+                            }
                         }
-                        lea_vol_store8(p.dst, g.b, ((p.dst_c0 + c16) >> 3), d, h, w, acc);
-                        if (two) lea_vol_store8(p.dst, g.b, ((p.dst_c0 + c16) >> 3) + 1, d, h, w, acc + 8);
+                    }
+                    if (!waited) {                    // residual loads of the first batch are issued before the wait
+                        mbar_wait(smem_u32(accfull + set), aphase, 301);
+                        tc_fence_after();
+                        waited = true;
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < kJB; ++jj) {
+                        if (j0 + jj >= nd) break;
+                        const int d = g.d0 + j0 + jj;
+                        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                              (uint32_t)((set * p.Dc + j0 + jj) * p.accw);
+                        float acc[16];
+                        tc_ld16_wait(trow + (uint32_t)c16, acc);
+                        for (int gidx = 1; gidx < p.ngroups; ++gidx) {
+                            float t16[16];
+                            tc_ld16_wait(trow + (uint32_t)(gidx * p.NP + c16), t16);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[i] += t16[i];
+                        }
+                        if (!valid) continue;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
+                            if (p.relu) v = fmaxf(v, 0.0f);
+                            acc[i] = v;
+                        }
+                        if (p.dst_f32) {
+                            float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h) * p.W + w;
+                            for (int n = 0; n < 16 && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
+                        } else {
+                            if (p.has_res) {
+                                ep_add_raw8<PL>(rq[jj][0], acc);
+                                if (two) ep_add_raw8<PL>(rq[jj][1], acc + 8);
+                            }
+                            ep_store8<PL>(p.dst, g.b, (p.dst_c0 + c16) >> 3, d, h, w, acc);
+                            if (two) ep_store8<PL>(p.dst, g.b, ((p.dst_c0 + c16) >> 3) + 1, d, h, w, acc + 8);
+                        }
                     }
                 }
             }
@@ -402,15 +459,14 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const TcParams);
-static TcKernelFn tc_kernel_for(int ks, int nterm) {
-    if (ks == 3) {
-        if (nterm == 1) return lea_conv_tc_kernel<3, 1>;
-        if (nterm == 2) return lea_conv_tc_kernel<3, 2>;
-        return lea_conv_tc_kernel<3, 3>;
-    }
-    if (nterm == 1) return lea_conv_tc_kernel<1, 1>;
-    if (nterm == 2) return lea_conv_tc_kernel<1, 2>;
-    return lea_conv_tc_kernel<1, 3>;
+template <int KS>
+static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
+    if (planes == 1) return lea_conv_tc_kernel<KS, 1, 1>;
+    if (planes == 2) return nterm == 1 ? lea_conv_tc_kernel<KS, 1, 2> : lea_conv_tc_kernel<KS, 2, 2>;
+    return nterm == 1 ? lea_conv_tc_kernel<KS, 1, 3> : lea_conv_tc_kernel<KS, 3, 3>;
+}
+static TcKernelFn tc_kernel_for(int ks, int nterm, int planes) {
+    return ks == 3 ? tc_kernel_for_ks<3>(nterm, planes) : tc_kernel_for_ks<1>(nterm, planes);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -581,7 +637,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm);
+    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm, P);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;

@@ -1,0 +1,60 @@
+"""Small, fixed launch sequence for `ncu --set full` captures: one launch each of the headline kernels at KITTI
+shapes (run plain first; see B200_PROFILING.md)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from leastereo_b200.kernels import get_ops, PlanesVol, lea_tc_opts  # noqa: E402
+
+
+def main():
+    which = sys.argv[1:] or ["stem0", "l1res", "l1batched", "conv1", "l0res", "cv", "disp", "resample"]
+    ops = get_ops()
+    dev = torch.device("cuda:0")
+    B, C, H3, W3, D3, maxdisp = 1, 32, 128, 416, 64, 192
+
+    def conv(ci, co, k, sp, res):
+        src = PlanesVol.empty(B, ci, 2, *sp, dev)
+        src.t.copy_(torch.randn(src.t.shape, device=dev).bfloat16() * 0.1)
+        w = torch.randn(co, ci, k, k, k, device=dev) * 0.05
+        scale = torch.ones(co, device=dev); shift = torch.zeros(co, device=dev)
+        dst = PlanesVol.empty(B, co, 2, *sp, dev)
+        dst.t.zero_()
+        p = ops.make_conv(src, 0, ci, co, k, scale, shift, True, dst=dst, res=dst if res else None)
+        img = ops.pack_weights_tc(w, 2)
+        opts = lea_tc_opts()
+        for _ in range(2):
+            ops.conv3d_tc(p, img, opts, w)
+        torch.cuda.synchronize()
+
+    if "stem0" in which:
+        conv(64, 32, 3, (64, 128, 416), False)
+    if "conv1" in which:
+        conv(128, 64, 3, (32, 64, 208), False)
+    if "l1res" in which:
+        conv(16, 16, 3, (32, 64, 208), True)
+    if "l1batched" in which:
+        conv(16, 48, 3, (32, 64, 208), False)
+    if "l0res" in which:
+        conv(8, 8, 3, (64, 128, 416), True)
+    if "cv" in which:
+        x = torch.randn(B, C, H3, W3, device=dev); y = torch.randn(B, C, H3, W3, device=dev)
+        for _ in range(2):
+            ops.cost_volume_f32(x, y, maxdisp)
+    if "disp" in which:
+        mat = torch.randn(B, D3, H3, W3, device=dev) * 3
+        for _ in range(2):
+            ops.disp_head(mat, maxdisp)
+    if "resample" in which:
+        src = PlanesVol.empty(B, 32, 2, 32, 64, 208, dev); src.t.zero_()
+        dst = PlanesVol.empty(B, 32, 2, 64, 128, 416, dev)
+        for _ in range(2):
+            ops.trilinear_ac(src, 0, 32, dst, 0)
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()
