@@ -13,10 +13,15 @@
 // just a different START ADDRESS of the same staged slab (rows are 16 B apart, 8-row groups 160 B apart), so a
 // loaded byte is reused 27x from shared memory and each input slab is fetched once per CTA sweep.
 //
-// Split precision ("bf16xN").  With A = a0+a1(+a2), W = w0+w1(+w2) (bf16 planes), the triangular product
-// sum_{i+j<P} a_i*w_j is issued as ONE mma per A plane against the row-concatenated weight tile [w0|w1|..]:
-// plane i uses the first (P-i)*N rows, accumulating into (P-i) column groups of the same TMEM accumulator; the
-// epilogue adds the column groups.  P=2 gives the 3-term bf16x3 product, P=3 the 6-term one (~fp32).
+// Split precision ("bf16xN").  With A = a0+a1(+a2), W = w0+w1(+w2) (bf16 planes) the triangular product
+// sum_{i+j<P} a_i*w_j is issued term by term; all terms with the same weight plane j accumulate into TMEM
+// "region" j and the epilogue adds the P regions.  P=2 gives the 3-term bf16x3 product, P=3 the 6-term one (~fp32).
+//
+// kd batching.  The three kd taps of one (kh,kw) read the SAME staged window of input slab s and feed the three
+// output depths s+1, s, s-1.  Accumulators of a region are laid out in TMEM in DESCENDING depth order, so those
+// three targets are adjacent columns and ONE tcgen05.mma with N = 3*N_out against the weight tile
+// [W(kd=0); W(kd=1); W(kd=2)] does all three: the 4 KB activation window - the operand that bounds this kernel,
+// shared-memory bandwidth being the limit at small N - is fetched once instead of three times.
 //
 // Schedule.  Persistent CTAs (one per SM), 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
 // warps 2-5 = epilogue.  A work item is (batch, depth chunk of Dc slices, h tile, w tile).  For every group of 16
@@ -35,7 +40,7 @@
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int kMaxTerms = 3;
+constexpr int kMaxTerms = 6;
 constexpr int kMaxStages = 8;
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kHeaderBytes = 1024;
@@ -49,9 +54,10 @@ struct TcParams {
     int ncg, blocks_per_cg;
     int ks, taps;
     int tiles_w, tiles_h, dchunks, Dc, total_items;
-    int NP, c_out, accw, ngroups;
+    int NP, c_out, ngroups;   // padded N, real c_out, TMEM regions (weight planes) summed by the epilogue
     int nterm;
-    int term_aoff[kMaxTerms], term_lbo_blocks[kMaxTerms], term_btile[kMaxTerms], term_n[kMaxTerms];
+    int term_aoff[kMaxTerms], term_lbo_blocks[kMaxTerms], term_btile[kMaxTerms], term_region[kMaxTerms];
+    int term_first[kMaxTerms];   // 1 = first term written into its region (carries the zero-init)
     int nbt, nb_rows, btile_bytes, wpart_bytes;
     int slab_vox, pitch_vox, blk_bytes, stage_bytes;
     int nstages, nwbuf;
@@ -319,50 +325,78 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // ================= MMA issuer: the whole warp walks the loop (warp-uniform descriptor arithmetic),
         //                   one elected lane issues tcgen05.mma / tcgen05.commit =================
         const uint32_t elected = elect_one();
-        uint32_t a_term16[NTERM], a_lbo_field[NTERM], b_term16[NTERM], idesc[NTERM];
+        uint32_t a_term16[NTERM], a_lbo_field[NTERM], b_term16[NTERM], reg_col[NTERM];
+        bool t_first[NTERM];
 #pragma unroll
         for (int t = 0; t < NTERM; ++t) {
             a_term16[t] = (uint32_t)(p.term_aoff[t] * p.blk_bytes) >> 4;
             a_lbo_field[t] = ((uint32_t)(p.term_lbo_blocks[t] * p.blk_bytes) >> 4) << 16;
             b_term16[t] = (uint32_t)(p.term_btile[t] * p.btile_bytes) >> 4;
-            idesc[t] = make_idesc(p.term_n[t]);
+            reg_col[t] = (uint32_t)(p.term_region[t] * p.Dc * p.NP);
+            t_first[t] = p.term_first[t] != 0;
         }
+        const uint32_t idesc1 = make_idesc(p.NP), idesc2 = make_idesc(2 * p.NP), idesc3 = make_idesc(3 * p.NP);
         const uint32_t a_hi = (uint32_t)kPitch | (1u << 14);                      // SBO = kPitch*16 B, version 1
         const uint32_t b_hi = 8u | (1u << 14);                                    // SBO = 128 B
         const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;                   // LBO = nb_rows*16 B
-        const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per tap / 16
+        const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per (kh,kw) / 16
+        const uint32_t set_cols = (uint32_t)(p.ngroups * p.Dc * p.NP);
         int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const ItemGeom g = decode_item(p, item);
             const int set = it & 1, aphase = (it >> 1) & 1;
             mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201);
             tc_fence_after();
+            const uint32_t set_base = tmem_base + (uint32_t)set * set_cols;
             for (int cg = 0; cg < p.ncg; ++cg) {
                 mbar_wait(smem_u32(wfull + wb), wphase, 202);
-                const uint32_t w16 = smem_u32(wbuf + (size_t)wb * wbuf_stride) >> 4;
+                const uint32_t w16 = (smem_u32(wbuf + (size_t)wb * wbuf_stride) >> 4) | b_lbo_field;
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                     mbar_wait(smem_u32(full + stage), sphase, 203);
                     tc_fence_after();
                     const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_bytes) >> 4;
-#pragma unroll 1
-                    for (int kd = 0; kd < KS; ++kd) {
-                        const int d_out = (KS == 3) ? d_in + 1 - kd : d_in;
-                        if (d_out < g.d0 || d_out >= g.d_hi) continue;
-                        const int first_d_in = (KS == 3) ? max(d_out - 1, 0) : d_out;
-                        uint32_t accflag = ((cg == 0) && (d_in == first_d_in)) ? 0u : 1u;
-                        const uint32_t dcol = tmem_base + (uint32_t)((set * p.Dc + (d_out - g.d0)) * p.accw);
-                        const uint32_t b_kd = (w16 + (uint32_t)(kd * KS * KS) * tap16) | b_lbo_field;
+                    // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi)
+                    int kd_a, kd_b;
+                    if (KS == 3) {
+                        kd_a = (d_in + 1 <= g.d_hi - 1) ? 0 : ((d_in <= g.d_hi - 1) ? 1 : 2);
+                        kd_b = (d_in - 1 >= g.d0) ? 2 : ((d_in >= g.d0) ? 1 : 0);
+                    } else { kd_a = 0; kd_b = 0; }
+                    const int nkd = kd_b - kd_a + 1;
+                    // accumulators are stored in descending depth order: depth d sits at column (d_hi-1-d)*NP
+                    const int d_top = (KS == 3) ? d_in + 1 - kd_a : d_in;
+                    const uint32_t col0 = (uint32_t)((g.d_hi - 1 - d_top) * p.NP);
+                    // depths touched for the first time by this slab (only while the first channel group runs):
+                    // kd = 0 always opens depth d_in+1; at d_in == 0 depth 0 (kd = 1) opens too
+                    int nfresh = 0;
+                    if (cg == 0) {
+                        if (KS == 3) {
+                            if (kd_a == 0) nfresh = 1 + ((d_in == 0 && kd_b >= 1) ? 1 : 0);
+                            else if (kd_a == 1 && d_in == 0) nfresh = 1;
+                        } else nfresh = 1;
+                    }
+                    const uint32_t brow16 = (uint32_t)(kd_a * p.NP);              // first weight row used, x16 B
+                    const uint32_t idesc_all = nkd == 3 ? idesc3 : (nkd == 2 ? idesc2 : idesc1);
+                    const uint32_t idesc_fresh = nfresh == 2 ? idesc2 : idesc1;
+                    const int nrest = nkd - nfresh;
+                    const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
 #pragma unroll
-                        for (int kh = 0; kh < KS; ++kh) {
+                    for (int kh = 0; kh < KS; ++kh) {
 #pragma unroll
-                            for (int kw = 0; kw < KS; ++kw) {
-                                const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
-                                const uint32_t b_tap = b_kd + (uint32_t)(kh * KS + kw) * tap16;
+                        for (int kw = 0; kw < KS; ++kw) {
+                            const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
+                            const uint32_t b_tap = w16 + (uint32_t)(kh * KS + kw) * tap16 + brow16;
 #pragma unroll
-                                for (int t = 0; t < NTERM; ++t) {
-                                    tc_mma_issue(elected, dcol, (a_tap + a_term16[t]) | a_lbo_field[t], a_hi,
-                                                 b_tap + b_term16[t], b_hi, idesc[t], accflag);
-                                    accflag = 1u;
+                            for (int t = 0; t < NTERM; ++t) {
+                                const uint32_t a_lo = (a_tap + a_term16[t]) | a_lbo_field[t];
+                                const uint32_t b_lo = b_tap + b_term16[t];
+                                const uint32_t dcol = set_base + reg_col[t] + col0;
+                                if (kh == 0 && kw == 0 && t_first[t] && nfresh > 0) {
+                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
+                                    if (nrest > 0)
+                                        tc_mma_issue(elected, dcol + (uint32_t)(nfresh * p.NP), a_lo, a_hi,
+                                                     b_lo + (uint32_t)(nfresh * p.NP), b_hi, idesc_rest, 1u);
+                                } else {
+                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_all, 1u);
                                 }
                             }
                         }
@@ -416,13 +450,14 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     for (int jj = 0; jj < kJB; ++jj) {
                         if (j0 + jj >= nd) break;
                         const int d = g.d0 + j0 + jj;
+                        // depth d of region r: column set*ngroups*Dc*NP + r*Dc*NP + (d_hi-1-d)*NP
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                              (uint32_t)((set * p.Dc + j0 + jj) * p.accw);
+                                              (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
                         float acc[16];
                         tc_ld16_wait(trow + (uint32_t)c16, acc);
                         for (int gidx = 1; gidx < p.ngroups; ++gidx) {
                             float t16[16];
-                            tc_ld16_wait(trow + (uint32_t)(gidx * p.NP + c16), t16);
+                            tc_ld16_wait(trow + (uint32_t)(gidx * p.Dc * p.NP + c16), t16);
 #pragma unroll
                             for (int i = 0; i < 16; ++i) acc[i] += t16[i];
                         }
@@ -462,22 +497,26 @@ typedef void (*TcKernelFn)(const CUtensorMap, const TcParams);
 template <int KS>
 static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
     if (planes == 1) return lea_conv_tc_kernel<KS, 1, 1>;
-    if (planes == 2) return nterm == 1 ? lea_conv_tc_kernel<KS, 1, 2> : lea_conv_tc_kernel<KS, 2, 2>;
-    return nterm == 1 ? lea_conv_tc_kernel<KS, 1, 3> : lea_conv_tc_kernel<KS, 3, 3>;
+    if (planes == 2) {
+        if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 2>;
+        if (nterm == 2) return lea_conv_tc_kernel<KS, 2, 2>;      // 8-channel layout
+        return lea_conv_tc_kernel<KS, 3, 2>;                       // bf16x3
+    }
+    return nterm == 1 ? lea_conv_tc_kernel<KS, 1, 3> : lea_conv_tc_kernel<KS, 6, 3>;   // bf16x6
 }
 static TcKernelFn tc_kernel_for(int ks, int nterm, int planes) {
     return ks == 3 ? tc_kernel_for_ks<3>(nterm, planes) : tc_kernel_for_ks<1>(nterm, planes);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// weight image:  [cg][tap][btile][khalf(2)][row(nb_rows)][8] bf16
-//   standard (c_in % 16 == 0): one tile per tap; row = pw*NP + co holds plane pw of W[co][cg*16 + khalf*8 + 0..7][tap]
-//   c_in == 8, P == 2 ("C8"):  A operand is [hi(8) | lo(8)] of the same 8 channels, so
+// weight image:  [cg][kh*KS+kw][btile][khalf(2)][row = kd*NP + co][8] bf16        (kd-major rows: one MMA spans 3 kd)
+//   standard (c_in % 16 == 0): tile j = weight plane j; row holds plane j of W[co][cg*16 + khalf*8 + 0..7][kd,kh,kw]
+//   c_in == 8, P == 2 ("C8"):  the A operand is [hi(8) | lo(8)] of the same 8 channels, so
 //       tile 0: khalf0 = Whi, khalf1 = Whi   (hi*Whi + lo*Whi)        tile 1: khalf0 = Wlo, khalf1 = 0   (hi*Wlo)
 // ---------------------------------------------------------------------------------------------------------
 struct TcShape {
     bool ok; bool c8;
-    int NP, nb_rows, nbt, btile_bytes, taps, ncg, wpart_bytes, accw, ngroups;
+    int NP, nb_rows, nbt, btile_bytes, taps2d, ncg, wpart_bytes, ngroups;
 };
 __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) {
     TcShape s{};
@@ -487,11 +526,12 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) 
     s.c8 = (c_in == 8);
     if (s.c8 ? (P != 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
     s.NP = (c_out + 15) & ~15;                                 // UMMA N granularity at M = 128
-    s.taps = ks * ks * ks;
-    if (s.c8) { s.nb_rows = s.NP; s.nbt = 2; s.ncg = 1; s.accw = s.NP; s.ngroups = 1; }
-    else      { s.nb_rows = P * s.NP; s.nbt = 1; s.ncg = c_in / 16; s.accw = P * s.NP; s.ngroups = P; }
+    s.taps2d = ks * ks;
+    s.nb_rows = ks * s.NP;
+    if (s.c8) { s.nbt = 2; s.ncg = 1; s.ngroups = 1; }
+    else      { s.nbt = P; s.ncg = c_in / 16; s.ngroups = P; }
     s.btile_bytes = 2 * s.nb_rows * 16;
-    s.wpart_bytes = s.taps * s.nbt * s.btile_bytes;
+    s.wpart_bytes = s.taps2d * s.nbt * s.btile_bytes;
     s.ok = true;
     return s;
 }
@@ -505,24 +545,27 @@ __global__ void lea_pack_weights_tc_kernel(const float* __restrict__ w, lea_u4* 
     const int row = r % s.nb_rows; r /= s.nb_rows;
     const int khalf = r % 2; r /= 2;
     const int bt = r % s.nbt; r /= s.nbt;
-    const int tap = r % s.taps; r /= s.taps;
+    const int tap2d = r % s.taps2d; r /= s.taps2d;
     const int cg = r;
+    const int kd = row / s.NP, co = row % s.NP;
+    const int tap = kd * s.taps2d + tap2d;                      // PyTorch order (kd, kh, kw)
+    const int ntaps = s.taps2d * ks;
     uint32_t q[4] = {0, 0, 0, 0};
-    int co, plane, ci0;
+    int plane, ci0;
     bool zero = false;
     if (s.c8) {
-        co = row; ci0 = 0;
+        ci0 = 0;
         if (bt == 0) plane = 0;
         else { plane = 1; zero = (khalf == 1); }
     } else {
-        plane = row / s.NP; co = row % s.NP; ci0 = cg * 16 + khalf * 8;
+        plane = bt; ci0 = cg * 16 + khalf * 8;
     }
     if (!zero && co < c_out) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint16_t a[3], b[3];
-            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i) * s.taps + tap], P, a);
-            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i + 1) * s.taps + tap], P, b);
+            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i) * ntaps + tap], P, a);
+            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i + 1) * ntaps + tap], P, b);
             q[i] = (uint32_t)a[plane] | ((uint32_t)b[plane] << 16);
         }
     }
@@ -571,35 +614,39 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.P = P;
     p.g0_stride_b = (c->src.C >> 3) * P;
     p.g0_first = (c->src_c0 >> 3) * P;
-    p.ks = c->ksize; p.taps = s.taps;
-    p.NP = s.NP; p.c_out = c->c_out; p.accw = s.accw;
+    p.ks = c->ksize; p.taps = s.taps2d * c->ksize;
+    p.NP = s.NP; p.c_out = c->c_out;
     p.ncg = s.ncg;
     p.nbt = s.nbt; p.nb_rows = s.nb_rows; p.btile_bytes = s.btile_bytes; p.wpart_bytes = s.wpart_bytes;
+    p.nterm = 0;
+    auto add_term = [&](int aoff, int lbo, int btile, int region, int first) {
+        p.term_aoff[p.nterm] = aoff; p.term_lbo_blocks[p.nterm] = lbo; p.term_btile[p.nterm] = btile;
+        p.term_region[p.nterm] = region; p.term_first[p.nterm] = first; ++p.nterm;
+    };
     if (s.c8) {
-        p.blocks_per_cg = 2;                                   // 1 channel block x 2 planes
-        p.nterm = single ? 1 : 2;
-        p.term_aoff[0] = 0; p.term_lbo_blocks[0] = 1; p.term_btile[0] = 0; p.term_n[0] = s.NP;
-        p.term_aoff[1] = 0; p.term_lbo_blocks[1] = 1; p.term_btile[1] = 1; p.term_n[1] = s.NP;
-        p.ngroups = 1;
         LEA_CHECK(!single, "conv3d_tc: single-pass mode is not defined for the 8-channel layout");
+        p.blocks_per_cg = 2;                                   // 1 channel block x 2 planes
+        add_term(0, 1, 0, 0, 1);                               // [hi|lo] x [Whi;Whi]
+        add_term(0, 1, 1, 0, 0);                               // [hi|lo] x [Wlo;0]
+        p.ngroups = 1;
     } else {
         p.blocks_per_cg = 2 * P;                               // 2 channel blocks x P planes, order [cb][plane]
-        p.nterm = single ? 1 : P;
-        for (int t = 0; t < p.nterm; ++t) {
-            p.term_aoff[t] = t;                                // plane t of channel block 0
-            p.term_lbo_blocks[t] = P;                          // same plane of channel block 1
-            p.term_btile[t] = 0;
-            p.term_n[t] = single ? s.NP : (P - t) * s.NP;
+        if (single) { add_term(0, P, 0, 0, 1); p.ngroups = 1; }
+        else {
+            for (int pw = 0; pw < P; ++pw)                     // region pw = weight plane pw
+                for (int t = 0; t + pw < P; ++t)               // activation plane t (plane t of cb 0; cb 1 is P blocks on)
+                    add_term(t, P, pw, pw, t == 0);
+            p.ngroups = P;
         }
-        p.ngroups = single ? 1 : P;
     }
+    const int accw = p.ngroups * p.NP;                         // TMEM columns per output depth
     p.pitch_vox = (p.ks == 3) ? LEA_TC_TW + 2 : LEA_TC_TW;
     p.slab_vox = p.pitch_vox * ((p.ks == 3) ? LEA_TC_TH + 2 : LEA_TC_TH);
     p.blk_bytes = p.slab_vox * 16;
     p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
     p.tiles_w = (p.W + LEA_TC_TW - 1) / LEA_TC_TW;
     p.tiles_h = (p.H + LEA_TC_TH - 1) / LEA_TC_TH;
-    int Dc = 512 / (2 * p.accw);
+    int Dc = 512 / (2 * accw);
     if (Dc > 8) Dc = 8;
     if (Dc > p.D) Dc = p.D;
     const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
