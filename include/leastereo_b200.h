@@ -89,6 +89,10 @@ typedef struct lea_tc_opts {
     int32_t mma_terms;
     int32_t fused_cv;  lea_vol fx, fy;  int32_t d3;
     int32_t num_sms;   /* 0 = query */
+    int32_t accum_split;   /* 0 = default (1): hi*hi term in its own TMEM accumulator, correction terms in a second one
+                              (the tensor core loses ~1 ulp per fp32 accumulation step; this cuts the steps of the
+                              dominant accumulator 3x); 2 = all terms share one accumulator (more depth per work item) */
+    int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
 } lea_tc_opts;
 int lea_conv3d_tc(const lea_conv* p, const void* wimg, const lea_tc_opts* opts, void* stream);
 /* self-test of the tcgen05 path on a synthetic GEMM-shaped conv; returns 0 when it matches the SIMT kernel. */

@@ -14,8 +14,8 @@
 // loaded byte is reused 27x from shared memory and each input slab is fetched once per CTA sweep.
 //
 // Split precision ("bf16xN").  With A = a0+a1(+a2), W = w0+w1(+w2) (bf16 planes) the triangular product
-// sum_{i+j<P} a_i*w_j is issued term by term; all terms with the same weight plane j accumulate into TMEM
-// "region" j and the epilogue adds the P regions.  P=2 gives the 3-term bf16x3 product, P=3 the 6-term one (~fp32).
+// sum_{i+j<P} a_i*w_j is issued term by term, every term accumulating into the same fp32 TMEM accumulator.
+// P=2 gives the 3-term bf16x3 product, P=3 the 6-term one (~fp32).
 //
 // kd batching.  The three kd taps of one (kh,kw) read the SAME staged window of input slab s and feed the three
 // output depths s+1, s, s-1.  Accumulators of a region are laid out in TMEM in DESCENDING depth order, so those
@@ -61,6 +61,7 @@ struct TcParams {
     int nbt, nb_rows, btile_bytes, wpart_bytes;
     int slab_vox, pitch_vox, blk_bytes, stage_bytes;
     int nstages, nwbuf;
+    int nsets;                // TMEM accumulator sets: 2 = epilogue of item i overlaps MMAs of item i+1, 1 = larger Dc
     int swap_lbo_sbo;         // debug switch for the descriptor convention
     const uint8_t* wimg;
     const float* bn_scale; const float* bn_shift; int relu;
@@ -234,6 +235,13 @@ __device__ __forceinline__ void ep_add_raw8(const uint4* q, float* f) {
         }
     }
 }
+// two fp32 -> packed bf16x2 (round-to-nearest-even), low half = first argument
+__device__ __forceinline__ uint32_t ep_pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// split 8 fp32 values into PL bf16 planes (same bits as lea_split_planes for finite inputs) and store them
 template <int PL>
 __device__ __forceinline__ void ep_store8(const lea_vol& v, int b, int cb, int d, int h, int w, const float* f) {
     uint4* base = reinterpret_cast<uint4*>(v.data);
@@ -242,14 +250,34 @@ __device__ __forceinline__ void ep_store8(const lea_vol& v, int b, int cb, int d
     uint32_t q[PL][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        uint16_t a[3], c[3];
-        lea_split_planes(f[2 * i], PL, a);
-        lea_split_planes(f[2 * i + 1], PL, c);
+        float x0 = f[2 * i], x1 = f[2 * i + 1];
 #pragma unroll
-        for (int pl = 0; pl < PL; ++pl) q[pl][i] = (uint32_t)a[pl] | ((uint32_t)c[pl] << 16);
+        for (int pl = 0; pl < PL; ++pl) {
+            const uint32_t hq = ep_pack_bf16x2(x0, x1);
+            q[pl][i] = hq;
+            if (pl + 1 < PL) {
+                x0 -= __uint_as_float(hq << 16);
+                x1 -= __uint_as_float(hq & 0xffff0000u);
+            }
+        }
     }
 #pragma unroll
     for (int pl = 0; pl < PL; ++pl) base[g + pl * ps] = make_uint4(q[pl][0], q[pl][1], q[pl][2], q[pl][3]);
+}
+
+// raw TMEM loads: 16 consecutive fp32 columns of this thread's lane, no wait
+__device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// orders later uses of r[] after the preceding tcgen05.wait::ld (the registers are "rewritten" by an empty asm)
+__device__ __forceinline__ void tc_touch16(uint32_t* r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                      "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
 }
 
 template <int KS, int NTERM, int PL>
@@ -344,7 +372,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const ItemGeom g = decode_item(p, item);
-            const int set = it & 1, aphase = (it >> 1) & 1;
+            const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
             mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201);
             tc_fence_after();
             const uint32_t set_base = tmem_base + (uint32_t)set * set_cols;
@@ -421,7 +449,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         int it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const ItemGeom g = decode_item(p, item);
-            const int set = it & 1, aphase = (it >> 1) & 1;
+            const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
             const int h = g.h0 + lh, w = g.w0 + lw;
             const bool valid = (h < p.H) && (w < p.W);
             const int nd = g.d_hi - g.d0;
@@ -454,12 +482,20 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
                         float acc[16];
-                        tc_ld16_wait(trow + (uint32_t)c16, acc);
-                        for (int gidx = 1; gidx < p.ngroups; ++gidx) {
-                            float t16[16];
-                            tc_ld16_wait(trow + (uint32_t)(gidx * p.Dc * p.NP + c16), t16);
+                        {
+                            uint32_t ra[16], rb[16];
+                            tc_ld16_nowait(trow + (uint32_t)c16, ra);
+                            if (p.ngroups == 2) tc_ld16_nowait(trow + (uint32_t)(p.Dc * p.NP + c16), rb);
+                            tc_wait_ld();
+                            tc_touch16(ra);
+                            if (p.ngroups == 2) {
+                                tc_touch16(rb);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[i] += t16[i];
+                                for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
+                            }
                         }
                         if (!valid) continue;
 #pragma unroll
@@ -624,30 +660,44 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         p.term_region[p.nterm] = region; p.term_first[p.nterm] = first; ++p.nterm;
     };
     if (s.c8) {
-        LEA_CHECK(!single, "conv3d_tc: single-pass mode is not defined for the 8-channel layout");
         p.blocks_per_cg = 2;                                   // 1 channel block x 2 planes
         add_term(0, 1, 0, 0, 1);                               // [hi|lo] x [Whi;Whi]
-        add_term(0, 1, 1, 0, 0);                               // [hi|lo] x [Wlo;0]
+        if (!single) add_term(0, 1, 1, 0, 0);                  // [hi|lo] x [Wlo;0]
         p.ngroups = 1;
     } else {
         p.blocks_per_cg = 2 * P;                               // 2 channel blocks x P planes, order [cb][plane]
         if (single) { add_term(0, P, 0, 0, 1); p.ngroups = 1; }
         else {
-            for (int pw = 0; pw < P; ++pw)                     // region pw = weight plane pw
-                for (int t = 0; t + pw < P; ++t)               // activation plane t (plane t of cb 0; cb 1 is P blocks on)
-                    add_term(t, P, pw, pw, t == 0);
-            p.ngroups = P;
+            // Product terms a_t * w_pw with t + pw < P.  The tensor core's fp32 accumulate loses ~1 ulp per
+            // accumulation step (measured: error grows linearly with the number of steps), so the dominant term
+            // hi*hi gets an accumulator of its own (region 0) and all correction terms, 2^-8 smaller, share
+            // region 1; the epilogue adds the two regions in fp32.
+            const bool split = !(opts && opts->accum_split == 2);
+            p.ngroups = (P > 1 && split) ? 2 : 1;
+            for (int pw = 0; pw < P; ++pw)                     // weight plane pw = weight tile pw
+                for (int t = 0; t + pw < P; ++t) {             // activation plane t (plane t of cb 0; cb 1 is P blocks on)
+                    const bool main_term = (pw == 0 && t == 0);
+                    const bool first_small = (pw == 0 && t == 1);
+                    add_term(t, P, pw, (main_term || p.ngroups == 1) ? 0 : 1,
+                             main_term || (first_small && p.ngroups == 2));
+                }
         }
     }
     const int accw = p.ngroups * p.NP;                         // TMEM columns per output depth
+    // long reductions: the epilogue is a few % of an item, so spend all of TMEM on depth (fewer halo slabs);
+    // short reductions: keep two accumulator sets so that the epilogue overlaps the next item's MMAs
+    // two accumulator sets let the epilogue of item i overlap the MMAs of item i+1; when that would leave fewer than
+    // 4 depth slices per item (wide N), one set with twice the depth wastes fewer halo slabs
+    p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
+    if (opts && (opts->acc_sets == 1 || opts->acc_sets == 2)) p.nsets = opts->acc_sets;
     p.pitch_vox = (p.ks == 3) ? LEA_TC_TW + 2 : LEA_TC_TW;
     p.slab_vox = p.pitch_vox * ((p.ks == 3) ? LEA_TC_TH + 2 : LEA_TC_TH);
     p.blk_bytes = p.slab_vox * 16;
     p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
     p.tiles_w = (p.W + LEA_TC_TW - 1) / LEA_TC_TW;
     p.tiles_h = (p.H + LEA_TC_TH - 1) / LEA_TC_TH;
-    int Dc = 512 / (2 * accw);
-    if (Dc > 8) Dc = 8;
+    int Dc = 512 / (p.nsets * accw);
+    if (Dc > 16) Dc = 16;
     if (Dc > p.D) Dc = p.D;
     const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
     // keep at least ~2 work items per SM when the volume is small

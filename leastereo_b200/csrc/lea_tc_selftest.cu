@@ -149,3 +149,116 @@ extern "C" int lea_tc_selftest(int32_t verbose, void* stream) {
     if (failures) lea_set_error("selftest: %d designed tcgen05 descriptor variants did not match", failures);
     return failures;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Micro-benchmark of tcgen05.mma issue/throughput on this chip (diagnostic, not part of the public header):
+// `iters` MMAs of shape M=128 x N x K=16 (bf16) from one elected thread, A from shared memory (SS) or from tensor
+// memory (TS), accumulating into `nacc` different accumulators in rotation.  Operand contents are irrelevant.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct MbParams { int n, nacc, a_in_tmem, iters, a_rot, sbo_a, b_rot, a_lbo, b_lbo; };
+
+__global__ void __launch_bounds__(128, 1) lea_tc_microbench_kernel(MbParams p, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 64 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(st_smem_u32(&tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    if (warp == 0) {
+        // the whole warp walks the loop so that descriptor arithmetic stays in uniform registers; one lane issues
+        uint32_t elected = 0;
+        asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %1;\n\tselp.u32 %0, 1, 0, px;\n\t}"
+                     : "=r"(elected) : "r"(0xffffffffu));
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t abase = st_smem_u32(smem) >> 4, bbase = (st_smem_u32(smem) + 32768) >> 4;
+        const uint32_t a_tmem = tmem + 448;                      // 8 columns of packed bf16 A (TS mode)
+        const uint32_t a_lo0 = abase | (((uint32_t)p.a_lbo >> 4) << 16), a_hi = ((uint32_t)p.sbo_a >> 4) | (1u << 14);
+        const uint32_t b_lo0 = bbase | (((uint32_t)p.b_lbo >> 4) << 16), b_hi = 8u | (1u << 14);
+        const uint32_t amask = (uint32_t)p.a_rot - 1u, dmask = (uint32_t)p.nacc - 1u, bmask = (uint32_t)p.b_rot - 1u;
+        const long long t0 = clock64();
+#pragma unroll 8
+        for (int i = 0; i < p.iters; ++i) {
+            const uint32_t d = tmem + ((uint32_t)i & dmask) * (uint32_t)p.n;
+            const uint32_t a_lo = a_lo0 + ((uint32_t)i & amask);
+            const uint32_t b_lo = b_lo0 + (((uint32_t)i >> 1) & bmask) * 24u;       // a different B tile every 2nd MMA
+            if (p.a_in_tmem) {
+                asm volatile(
+                    "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\tsetp.ne.b32 q, %0, 0;\n\tmov.b64 db, {%3, %4};\n\t"
+                    "setp.ne.b32 p, %6, 0;\n\t"
+                    "@q tcgen05.mma.cta_group::1.kind::f16 [%1], [%2], db, %5, p;\n\t}"
+                    ::"r"(elected), "r"(d), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(1u) : "memory");
+            } else {
+                asm volatile(
+                    "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+                    "mov.b64 da, {%2, %3};\n\tmov.b64 db, {%4, %5};\n\tsetp.ne.b32 p, %7, 0;\n\t"
+                    "@q tcgen05.mma.cta_group::1.kind::f16 [%1], da, db, %6, p;\n\t}"
+                    ::"r"(elected), "r"(d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(1u) : "memory");
+            }
+        }
+        const long long t_issue = clock64();
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t"
+                     "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%1];\n\t}"
+                     ::"r"(elected), "r"(st_smem_u32(&bar)) : "memory");
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(st_smem_u32(&bar)), "r"(0u) : "memory");
+            if (!ok && clock64() - t0 > 4000000000ll) break;
+        }
+        if (tid == 0) { out[2 * blockIdx.x] = clock64() - t0; out[2 * blockIdx.x + 1] = t_issue - t0; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+}  // namespace
+
+extern "C" int lea_tc_microbench(int32_t grid, void* stream) {
+    long long* d_out = nullptr;
+    if (grid < 1) grid = 1;
+    LEA_CHECK(cudaMalloc(&d_out, 2 * grid * sizeof(long long)) == cudaSuccess, "microbench: cudaMalloc failed");
+    cudaFuncSetAttribute(lea_tc_microbench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    std::vector<long long> h(2 * grid);
+    const int iters = 2000;
+    printf("[tc_microbench] grid=%d iters=%d   cycles per tcgen05.mma (M=128, K=16, bf16; floor = N/2)\n", grid, iters);
+    printf("[tc_microbench] %5s %5s %6s %6s %6s | %9s %9s %9s\n", "N", "nacc", "A", "a_rot", "b_rot", "min", "avg", "issue");
+    printf("[tc_microbench] (columns: N nacc A a_rot b_rot a_lbo b_lbo)\n");
+    struct Case { int n, a_in_tmem, a_rot, b_rot, a_lbo, b_lbo; };
+    const Case cases[] = {
+        {96, 0, 1, 1, 2880, 1536}, {96, 0, 8, 8, 2880, 1536}, {96, 0, 8, 8, 5760, 1536}, {96, 0, 8, 8, 5760, 1600},
+        {96, 0, 8, 8, 2880, 1600}, {96, 0, 8, 8, 5824, 1536}, {96, 0, 8, 8, 8640, 1536},
+        {32, 0, 8, 8, 5760, 512}, {32, 0, 8, 8, 2880, 512}, {64, 0, 8, 8, 5760, 1024}, {64, 0, 8, 8, 2880, 1088},
+        {192, 0, 8, 8, 5760, 3072}, {192, 0, 8, 8, 2880, 3136}, {144, 0, 8, 8, 5760, 2304}, {144, 0, 8, 8, 2880, 2368},
+        {128, 0, 8, 8, 5760, 2048}, {128, 0, 8, 8, 2880, 2112}, {256, 0, 8, 8, 2880, 4160},
+    };
+    for (const Case& c : cases) {
+        MbParams p{c.n, 1, c.a_in_tmem, iters, c.a_rot, 160, c.b_rot, c.a_lbo, c.b_lbo};
+        lea_tc_microbench_kernel<<<grid, 128, 64 * 1024, (cudaStream_t)stream>>>(p, d_out);
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) { lea_set_error("microbench: %s", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(h.data(), d_out, 2 * grid * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long mn = h[0]; double avg = 0, iss = 0;
+        for (int k = 0; k < grid; ++k) { if (h[2 * k] < mn) mn = h[2 * k]; avg += (double)h[2 * k]; iss += (double)h[2 * k + 1]; }
+        printf("[tc_microbench] %5d %5s a_rot %d b_rot %d a_lbo %5d b_lbo %5d | min %7.1f avg %7.1f issue %7.1f\n", c.n,
+               c.a_in_tmem ? "tmem" : "smem", c.a_rot, c.b_rot, c.a_lbo, c.b_lbo, (double)mn / iters, avg / grid / iters,
+               iss / grid / iters);
+    }
+    fflush(stdout);
+    cudaFree(d_out);
+    return 0;
+}

@@ -61,7 +61,8 @@ class MatchingPlan:
     """Launch list + buffers of ``newMatching.forward`` for one (device, B, D, H, W, planes, conv mode)."""
 
     def __init__(self, matching: newMatching, ops: Ops, B: int, spatial: Tuple[int, int, int], planes: int,
-                 device, conv_mode: str = "simt", mma_terms: int = 0, fuse: bool = True):
+                 device, conv_mode: str = "simt", mma_terms: int = 0, fuse: bool = True, tc_knobs: Optional[dict] = None):
+        tc_knobs = tc_knobs or {}
         if conv_mode not in ("simt", "tc"):
             raise ValueError("conv mode must be 'simt' or 'tc'")
         self.m = matching
@@ -71,6 +72,8 @@ class MatchingPlan:
         self.conv_mode = conv_mode
         self.mma_terms = mma_terms
         self.fuse = fuse               # graph-level rewrites: batched sibling convs, conv-before-upsample
+        self.accum_split = int(tc_knobs.get("accum_split", 0))
+        self.acc_sets = int(tc_knobs.get("acc_sets", 0))
         self.steps: List[Step] = []
         self.volumes: List[PlanesVol] = []
         self._bn_users: List[Tuple[ConvBR3d, int]] = []     # (module, offset into the BN buffers)
@@ -173,6 +176,8 @@ class MatchingPlan:
         if use_tc:
             opts = lea_tc_opts()
             opts.mma_terms = self.mma_terms
+            opts.accum_split = self.accum_split
+            opts.acc_sets = self.acc_sets
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
                                weight=weight, wcat=wcat, opts=opts, ref=src.vol.t))
 
@@ -456,13 +461,14 @@ def invalidate_cached_plans(model):
 def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops: Optional[Ops] = None) -> MatchingPlan:
     ops = ops or get_ops()
     key = (str(device), B, tuple(spatial), options["planes"], options["conv"], options["mma_terms"],
-           bool(options.get("fuse", True)), id(ops))
+           bool(options.get("fuse", True)), int(options.get("accum_split", 0)), int(options.get("acc_sets", 0)), id(ops))
     with _LOCK:
         plans = _plans(matching)
         plan = plans.get(key)
         if plan is None:
             plan = MatchingPlan(matching, ops, B, spatial, options["planes"], device, options["conv"],
-                                options["mma_terms"], bool(options.get("fuse", True)))
+                                options["mma_terms"], bool(options.get("fuse", True)),
+                                {"accum_split": options.get("accum_split", 0), "acc_sets": options.get("acc_sets", 0)})
             plans[key] = plan
     return plan
 

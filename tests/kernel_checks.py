@@ -209,8 +209,6 @@ def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False)
     for i, (B, ct, c0, ci, co, k, sp, bn, relu, res) in enumerate(cases or TC_CASES):
         if ops.tc_weight_image_bytes(ci, co, k, planes) <= 0:
             continue
-        if mma_terms == 1 and ci == 8:
-            continue
 
         def fn(p, w, x):
             img = ops.pack_weights_tc(w.contiguous(), planes)

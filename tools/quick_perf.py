@@ -74,6 +74,8 @@ def main():
                 else:
                     img = ops.pack_weights_tc(w, 2)
                     opts = lea_tc_opts()
+                    opts.accum_split = int(os.environ.get("LEA_SPLIT", "0"))
+                    opts.acc_sets = int(os.environ.get("LEA_SETS", "0"))
                     ms = timeit(lambda: ops.conv3d_tc(p, img, opts, w), iters=3, warm=1)
                 out["conv_%s_%s" % (mode, name)] = {"ms": ms, "TFLOPs": flops / ms / 1e9}
             except Exception as e:  # noqa: BLE001
