@@ -186,8 +186,14 @@ def profile_kernels(model, left, right):
     for rep in range(2):       # first repetition warms up, second is reported
         records.clear()
         cv_bytes = 4.0 * B * (2 * C * H3 * W3 + 2 * C * D3 * H3 * W3)
-        timed("cost_volume", "cost_volume", lambda: ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"],
-                                                                          out=plan.cost), 0.0, cv_bytes)
+        if plan.fxp is not None:
+            pk_bytes = 4.0 * B * 2 * C * H3 * W3 * 2
+            timed("pack_features", "pack_features",
+                  lambda: (ops.pack(fx, opt["planes"], out=plan.fxp), ops.pack(fy, opt["planes"], out=plan.fyp)), 0.0,
+                  pk_bytes)
+        else:
+            timed("cost_volume", "cost_volume", lambda: ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"],
+                                                                              out=plan.cost), 0.0, cv_bytes)
         for s in plan.steps:
             timed(s.name, s.kind, lambda s=s: plan.run_step(s), s.flops, s.bytes)
         dh_bytes = 4.0 * B * (D3 * H3 * W3 + 9 * H3 * W3)

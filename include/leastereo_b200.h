@@ -93,8 +93,17 @@ typedef struct lea_tc_opts {
                               (the tensor core loses ~1 ulp per fp32 accumulation step; this cuts the steps of the
                               dominant accumulator 3x); 2 = all terms share one accumulator (more depth per work item) */
     int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
+    const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
 } lea_tc_opts;
 int lea_conv3d_tc(const lea_conv* p, const void* wimg, const lea_tc_opts* opts, void* stream);
+/* Fused cost volume (retrain/LEAStereo.py:34-48 inside stem0's operand loader).  fx, fy: the two feature maps as
+ * 2-D planes volumes (D == 1, C channels each).  For every disparity d the loader needs x[h,w]*[w>=d] and y[h,w-d]*[w>=d];
+ * both are plain TMA box loads through a per-disparity tensor map whose base is shifted by d voxels (x) and whose
+ * width is W-d, so the out-of-bounds zero fill of TMA produces exactly the zeros of the reference loop.  The maps
+ * (2*d3 descriptors) depend only on the buffers' addresses and shapes: build once per plan, pass via cv_maps.
+ * With fused_cv the conv's `src` is ignored except for src.P; c_in must equal 2*fx.C and ksize 3. */
+int64_t lea_fused_cv_maps_bytes(int32_t d3);
+int lea_build_fused_cv_maps(const lea_vol* fx, const lea_vol* fy, int32_t d3, void* maps_dev, void* stream);
 /* self-test of the tcgen05 path on a synthetic GEMM-shaped conv; returns 0 when it matches the SIMT kernel. */
 int lea_tc_selftest(int32_t verbose, void* stream);
 

@@ -61,6 +61,8 @@ struct TcParams {
     int nbt, nb_rows, btile_bytes, wpart_bytes;
     int slab_vox, pitch_vox, blk_bytes, stage_bytes;
     int nstages, nwbuf;
+    int fused_cv, ncg_half;   // fused cost volume: channel groups [0,ncg_half) come from x, the rest from y(w-d)
+    const CUtensorMap* cvmaps; // [2*D]: x maps for d = 0..D-1, then y maps
     int nsets;                // TMEM accumulator sets: 2 = epilogue of item i overlaps MMAs of item i+1, 1 = larger Dc
     int swap_lbo_sbo;         // debug switch for the descriptor convention
     const uint8_t* wimg;
@@ -109,6 +111,14 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -342,8 +352,18 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                         mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102);
                         mbar_arrive_expect_tx(smem_u32(full + stage), (uint32_t)p.stage_bytes);
-                        tma_load_5d(smem_u32(stages + (size_t)stage * p.stage_bytes), &tmap, smem_u32(full + stage),
-                                    0, g.w0 - kHalo, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
+                        if (p.fused_cv) {
+                            // cost volume built by the loader: disparity d_in selects the tensor map; the map's
+                            // origin/width make TMA's zero fill reproduce [w >= d] (see lea_build_fused_cv_maps)
+                            const bool left = cg < p.ncg_half;
+                            const CUtensorMap* m = p.cvmaps + (left ? 0 : p.D) + d_in;
+                            tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_bytes), m, smem_u32(full + stage),
+                                        0, g.w0 - kHalo - d_in, g.h0 - kHalo,
+                                        gbase + (left ? cg : cg - p.ncg_half) * p.blocks_per_cg);
+                        } else {
+                            tma_load_5d(smem_u32(stages + (size_t)stage * p.stage_bytes), &tmap, smem_u32(full + stage),
+                                        0, g.w0 - kHalo, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
+                        }
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                     }
                 }
@@ -636,8 +656,18 @@ int device_sm_count() {
 }
 
 int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void* stream, int swap_lbo_sbo) {
-    const int P = c->src.P;
+    const bool fused = opts && opts->fused_cv;
+    const int P = fused ? opts->fx.P : c->src.P;
     const TcShape s = tc_shape(c->c_in, c->c_out, c->ksize, P);
+    if (fused) {
+        LEA_CHECK(opts->cv_maps != nullptr, "conv3d_tc: fused_cv needs cv_maps (lea_build_fused_cv_maps)");
+        LEA_CHECK(c->ksize == 3 && c->c_in == 2 * opts->fx.C && (opts->fx.C % 16) == 0,
+                  "conv3d_tc: fused_cv needs ksize 3 and c_in == 2*C with C %% 16 == 0");
+        LEA_CHECK(opts->fx.D == 1 && opts->fy.D == 1 && opts->fx.P == opts->fy.P && opts->fx.C == opts->fy.C &&
+                  opts->fx.B == opts->fy.B && opts->fx.H == opts->fy.H && opts->fx.W == opts->fy.W,
+                  "conv3d_tc: fused_cv feature volumes must be matching 2-D planes volumes");
+        LEA_CHECK(opts->d3 >= 1 && opts->d3 <= opts->fx.W, "conv3d_tc: fused_cv needs 1 <= D3 <= W3");
+    }
     LEA_CHECK(s.ok, "conv3d_tc: shape c_in=%d c_out=%d k=%d planes=%d is not taken by the tensor-core kernel",
               c->c_in, c->c_out, c->ksize, P);
     LEA_CHECK(c->dst_f32 != nullptr || (c->dst.P == P && (!c->has_res || c->res.P == P)),
@@ -646,13 +676,24 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     const int single = opts && opts->mma_terms == 1;
 
     TcParams p{};
-    p.B = c->src.B; p.D = c->src.D; p.H = c->src.H; p.W = c->src.W;
+    if (fused) {
+        p.B = opts->fx.B; p.D = opts->d3; p.H = opts->fx.H; p.W = opts->fx.W;
+        p.g0_stride_b = (opts->fx.C >> 3) * P;
+        p.g0_first = 0;
+        p.fused_cv = 1;
+        p.cvmaps = reinterpret_cast<const CUtensorMap*>(opts->cv_maps);
+    } else {
+        p.B = c->src.B; p.D = c->src.D; p.H = c->src.H; p.W = c->src.W;
+        p.g0_stride_b = (c->src.C >> 3) * P;
+        p.g0_first = (c->src_c0 >> 3) * P;
+    }
     p.P = P;
-    p.g0_stride_b = (c->src.C >> 3) * P;
-    p.g0_first = (c->src_c0 >> 3) * P;
+    LEA_CHECK(c->dst_f32 != nullptr || (c->dst.B == p.B && c->dst.D == p.D && c->dst.H == p.H && c->dst.W == p.W),
+              "conv3d_tc: output volume does not match the input geometry");
     p.ks = c->ksize; p.taps = s.taps2d * c->ksize;
     p.NP = s.NP; p.c_out = c->c_out;
     p.ncg = s.ncg;
+    p.ncg_half = s.ncg / 2;
     p.nbt = s.nbt; p.nb_rows = s.nb_rows; p.btile_bytes = s.btile_bytes; p.wpart_bytes = s.wpart_bytes;
     p.nterm = 0;
     auto add_term = [&](int aoff, int lbo, int btile, int region, int first) {
@@ -723,13 +764,17 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     PFN_encodeTiled encode = get_encode_fn();
     LEA_CHECK(encode != nullptr, "conv3d_tc: cuTensorMapEncodeTiled is not available from the driver");
     CUtensorMap tmap;
-    const cuuint64_t G = (cuuint64_t)p.B * (c->src.C >> 3) * P;
-    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.D, G};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)p.D * p.H * p.W * 16};
+    // (with fused_cv the 5-D map is unused by the kernel; it is encoded over fx only to keep one launch signature)
+    const int mapC = fused ? opts->fx.C : c->src.C;
+    const int mapD = fused ? 1 : p.D;
+    void* map_base = fused ? opts->fx.data : c->src.data;
+    const cuuint64_t G = (cuuint64_t)p.B * (mapC >> 3) * P;
+    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)mapD, G};
+    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)mapD * p.H * p.W * 16};
     cuuint32_t box[5] = {8, (cuuint32_t)p.pitch_vox, (cuuint32_t)(p.slab_vox / p.pitch_vox), 1,
                          (cuuint32_t)p.blocks_per_cg};
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, c->src.data, gdim, gstr, box, estr,
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, map_base, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
@@ -769,7 +814,6 @@ extern "C" int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in
 
 extern "C" int lea_conv3d_tc(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void* stream) {
     LEA_CHECK(c != nullptr && wimg != nullptr, "conv3d_tc: null argument");
-    LEA_CHECK(!(opts && opts->fused_cv), "conv3d_tc: fused cost-volume loader is not built yet");
     return tc_launch(c, wimg, opts, stream, 0);
 }
 
@@ -782,4 +826,41 @@ extern "C" int lea_tc_status(void) {
     int v = 0;
     cudaMemcpyFromSymbol(&v, g_lea_tc_status, sizeof(int));
     return v;
+}
+
+extern "C" int64_t lea_fused_cv_maps_bytes(int32_t d3) { return d3 > 0 ? (int64_t)2 * d3 * sizeof(CUtensorMap) : 0; }
+
+extern "C" int lea_build_fused_cv_maps(const lea_vol* fx, const lea_vol* fy, int32_t d3, void* maps_dev, void* stream) {
+    LEA_CHECK(fx && fy && maps_dev && fx->data && fy->data, "build_fused_cv_maps: null argument");
+    LEA_CHECK(fx->D == 1 && fy->D == 1 && fx->P == fy->P && fx->C == fy->C && fx->B == fy->B && fx->H == fy->H &&
+              fx->W == fy->W && (fx->C % 16) == 0, "build_fused_cv_maps: feature volumes must match (D == 1, C %% 16 == 0)");
+    LEA_CHECK(d3 >= 1 && d3 <= fx->W, "build_fused_cv_maps: need 1 <= D3 <= W3");
+    LEA_CHECK((((uintptr_t)maps_dev) & 63) == 0, "build_fused_cv_maps: maps must be 64-byte aligned");
+    PFN_encodeTiled encode = get_encode_fn();
+    LEA_CHECK(encode != nullptr, "build_fused_cv_maps: cuTensorMapEncodeTiled is not available from the driver");
+    const int P = fx->P, H = fx->H, W = fx->W;
+    const cuuint64_t G = (cuuint64_t)fx->B * (fx->C >> 3) * P;
+    std::vector<CUtensorMap> maps(2 * (size_t)d3);
+    for (int side = 0; side < 2; ++side) {
+        for (int d = 0; d < d3; ++d) {
+            // x: origin shifted right by d voxels  -> coordinate w' = w - d addresses x[h, w];   w' < 0  <=> w < d -> 0
+            // y: origin unchanged                  -> coordinate w' = w - d addresses y[h, w-d]; w' < 0  <=> w < d -> 0
+            // both: width W - d                    -> w' >= W - d <=> w >= W (right halo) -> 0
+            uint8_t* base = reinterpret_cast<uint8_t*>(side == 0 ? fx->data : fy->data) + (side == 0 ? (size_t)d * 16 : 0);
+            cuuint64_t gdim[4] = {8, (cuuint64_t)(W - d), (cuuint64_t)H, G};
+            cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+            cuuint32_t box[4] = {8, (cuuint32_t)(LEA_TC_TW + 2), (cuuint32_t)(LEA_TC_TH + 2), (cuuint32_t)(2 * P)};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult cr = encode(&maps[(size_t)side * d3 + d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box,
+                                 estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            LEA_CHECK(cr == CUDA_SUCCESS, "build_fused_cv_maps: cuTensorMapEncodeTiled failed (%d) at d=%d", (int)cr, d);
+        }
+    }
+    cudaError_t e = cudaMemcpyAsync(maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice,
+                                    (cudaStream_t)stream);
+    LEA_CHECK(e == cudaSuccess, "build_fused_cv_maps: copy failed: %s", cudaGetErrorString(e));
+    e = cudaStreamSynchronize((cudaStream_t)stream);       // the host vector goes out of scope on return
+    LEA_CHECK(e == cudaSuccess, "build_fused_cv_maps: sync failed: %s", cudaGetErrorString(e));
+    return 0;
 }

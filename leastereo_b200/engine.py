@@ -72,6 +72,7 @@ class MatchingPlan:
         self.conv_mode = conv_mode
         self.mma_terms = mma_terms
         self.fuse = fuse               # graph-level rewrites: batched sibling convs, conv-before-upsample
+        self.fuse_cv = bool(tc_knobs.get("fuse_cv", True))
         self.accum_split = int(tc_knobs.get("accum_split", 0))
         self.acc_sets = int(tc_knobs.get("acc_sets", 0))
         self.steps: List[Step] = []
@@ -126,7 +127,8 @@ class MatchingPlan:
         return dst
 
     def _emit_conv(self, name: str, mods, src: Slice, dst: Optional[Slice], *, res: bool = False,
-                   dst_f32: Optional[torch.Tensor] = None, identity_c: int = 0, raw: bool = False):
+                   dst_f32: Optional[torch.Tensor] = None, identity_c: int = 0, raw: bool = False,
+                   fused_cv: bool = False):
         """Append one ConvBR launch.
 
         ``mods``: a ConvBR3d, or a list of ConvBR3d reading the same input whose outputs are adjacent channel
@@ -159,14 +161,17 @@ class MatchingPlan:
                 weight = wcat
         if src.c != c_in:
             raise LeaError("%s: input has %d channels, conv expects %d" % (name, src.c, c_in))
+        out_spatial = dst.spatial if (fused_cv and dst is not None) else src.spatial
         if dst is not None and dst.c != c_out:
             raise LeaError("%s: output slice has %d channels, conv produces %d" % (name, dst.c, c_out))
         p = self.ops.make_conv(src.vol, src.c0, c_in, c_out, k, scale, shift, relu,
                                dst=None if dst is None else dst.vol, dst_c0=0 if dst is None else dst.c0,
                                res=dst.vol if res else None, res_c0=dst.c0 if res else 0, dst_f32=dst_f32)
-        m_vox = self.B * _prod(src.spatial)
+        m_vox = self.B * _prod(out_spatial)
         flops = 2.0 * m_vox * c_out * c_in * k ** 3
-        if dst_f32 is None:
+        if fused_cv:
+            nbytes = 2.0 * self.P * self.B * (_prod(src.spatial) * c_in + _prod(out_spatial) * c_out)
+        elif dst_f32 is None:
             nbytes = 2.0 * self.P * m_vox * (c_in + c_out * (2 if res else 1))
         else:
             nbytes = 2.0 * self.P * m_vox * c_in + 4.0 * m_vox * c_out
@@ -176,6 +181,11 @@ class MatchingPlan:
         if use_tc:
             opts = lea_tc_opts()
             opts.mma_terms = self.mma_terms
+            if fused_cv:
+                opts.fused_cv = 1
+                opts.fx, opts.fy = self.fxp.struct(), self.fyp.struct()
+                opts.d3 = out_spatial[0]
+                opts.cv_maps = self.cv_maps.data_ptr()
             opts.accum_split = self.accum_split
             opts.acc_sets = self.acc_sets
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
@@ -299,9 +309,20 @@ class MatchingPlan:
         m = self.m
         fm = m.initial_fm
         L0 = self.spatial
-        self.cost = self._vol(2 * fm, L0)
         v0, v1 = self._vol(fm, L0), self._vol(fm, L0)
-        self._emit_conv("stem0", m.stem0, Slice(self.cost, 0, 2 * fm), Slice(v0, 0, fm))
+        self.cost = self.fxp = self.fyp = self.cv_maps = None
+        can_fuse_cv = (self.fuse_cv and self.conv_mode == "tc" and fm % 16 == 0 and L0[0] <= L0[2] and
+                       self.ops.tc_weight_image_bytes(2 * fm, fm, 3, self.P) > 0)
+        if can_fuse_cv:
+            # retrain/LEAStereo.py:34-48 inside stem0's TMA loader: the 2C x D3 x H3 x W3 volume is never materialised
+            self.fxp = PlanesVol.empty(self.B, fm, self.P, 1, L0[1], L0[2], self.device)
+            self.fyp = PlanesVol.empty(self.B, fm, self.P, 1, L0[1], L0[2], self.device)
+            self.cv_maps = self.ops.build_fused_cv_maps(self.fxp, self.fyp, L0[0])
+            self._emit_conv("stem0(fused cost volume)", m.stem0, Slice(self.fxp, 0, 2 * fm), Slice(v0, 0, fm),
+                            fused_cv=True)
+        else:
+            self.cost = self._vol(2 * fm, L0)
+            self._emit_conv("stem0", m.stem0, Slice(self.cost, 0, 2 * fm), Slice(v0, 0, fm))
         self._emit_conv("stem1", m.stem1, Slice(v0, 0, fm), Slice(v1, 0, fm))
         stem0, stem1 = Slice(v0, 0, fm), Slice(v1, 0, fm)
 
@@ -436,7 +457,7 @@ def _prod(t):
 # module-level entry points used by the nn.Module boundary
 # --------------------------------------------------------------------------------------------------------
 
-DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "assume_frozen": False}
+DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fuse_cv": True, "assume_frozen": False}
 
 
 def _options(model) -> dict:
@@ -461,14 +482,16 @@ def invalidate_cached_plans(model):
 def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops: Optional[Ops] = None) -> MatchingPlan:
     ops = ops or get_ops()
     key = (str(device), B, tuple(spatial), options["planes"], options["conv"], options["mma_terms"],
-           bool(options.get("fuse", True)), int(options.get("accum_split", 0)), int(options.get("acc_sets", 0)), id(ops))
+           bool(options.get("fuse", True)), int(options.get("accum_split", 0)), int(options.get("acc_sets", 0)),
+           bool(options.get("fuse_cv", True)), id(ops))
     with _LOCK:
         plans = _plans(matching)
         plan = plans.get(key)
         if plan is None:
             plan = MatchingPlan(matching, ops, B, spatial, options["planes"], device, options["conv"],
                                 options["mma_terms"], bool(options.get("fuse", True)),
-                                {"accum_split": options.get("accum_split", 0), "acc_sets": options.get("acc_sets", 0)})
+                                {"accum_split": options.get("accum_split", 0), "acc_sets": options.get("acc_sets", 0),
+                                 "fuse_cv": options.get("fuse_cv", True)})
             plans[key] = plan
     return plan
 
@@ -492,7 +515,11 @@ def hot_path_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optional[Op
     if D3 < 1:
         raise LeaError("maxdisp %r gives an empty cost volume" % (model.maxdisp,))
     plan = get_plan(model.matching, B, (D3, H3, W3), fx.device, opt, ops)
-    ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"], out=plan.cost)
+    if plan.fxp is not None:                 # fused: stem0's loader builds the volume from the packed feature maps
+        ops.pack(fx, opt["planes"], out=plan.fxp)
+        ops.pack(fy, opt["planes"], out=plan.fyp)
+    else:
+        ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"], out=plan.cost)
     mat = plan.run(check_params=not opt["assume_frozen"])
     return ops.disp_head(mat, model.maxdisp)
 
@@ -506,6 +533,7 @@ def matching_forward(matching: newMatching, x: torch.Tensor, ops: Optional[Ops] 
     opt.update(options or {})
     x = x.detach().float().contiguous()
     B, _, D, H, W = x.shape
+    opt["fuse_cv"] = False                   # the caller hands over a materialised volume
     plan = get_plan(matching, B, (D, H, W), x.device, opt, ops)
     ops.pack(x, opt["planes"], out=plan.cost)
     return plan.run(check_params=not opt["assume_frozen"]).clone()

@@ -32,7 +32,7 @@ class lea_conv(C.Structure):
 
 class lea_tc_opts(C.Structure):
     _fields_ = [("mma_terms", C.c_int32), ("fused_cv", C.c_int32), ("fx", lea_vol), ("fy", lea_vol),
-                ("d3", C.c_int32), ("num_sms", C.c_int32), ("accum_split", C.c_int32), ("acc_sets", C.c_int32)]
+                ("d3", C.c_int32), ("num_sms", C.c_int32), ("accum_split", C.c_int32), ("acc_sets", C.c_int32), ("cv_maps", C.c_void_p)]
 
 
 # every symbol include/leastereo_b200.h declares: name -> (restype, argtypes)
@@ -52,6 +52,8 @@ SYMBOLS = {
     "lea_pack_weights_tc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "lea_conv3d_tc": (C.c_int, [_CONVP, _vp, _TCP, _vp]),
     "lea_tc_selftest": (C.c_int, [_i32, _vp]),
+    "lea_fused_cv_maps_bytes": (_i64, [_i32]),
+    "lea_build_fused_cv_maps": (C.c_int, [_VOLP, _VOLP, _i32, _vp, _vp]),
     "lea_disp_head": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "lea_disparity_regression": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
 }
@@ -249,6 +251,19 @@ class Ops:
         self._dev(wimg, ref)
         with torch.cuda.device(ref.device):
             self._check(self.lib.lea_conv3d_tc(C.byref(p), wimg.data_ptr(), C.byref(opts), self._stream(ref)))
+
+    def build_fused_cv_maps(self, fx: PlanesVol, fy: PlanesVol, d3: int) -> torch.Tensor:
+        """Device array of per-disparity TMA descriptors for the fused cost-volume loader of stem0."""
+        self._dev(fx.t, fy.t)
+        nbytes = int(self.lib.lea_fused_cv_maps_bytes(d3))
+        maps = torch.empty(nbytes + 128, dtype=torch.uint8, device=fx.t.device)
+        off = (-maps.data_ptr()) % 128                      # descriptors must be 64-byte aligned; use 128
+        maps = maps[off: off + nbytes]
+        a, b = fx.struct(), fy.struct()
+        with torch.cuda.device(fx.t.device):
+            self._check(self.lib.lea_build_fused_cv_maps(C.byref(a), C.byref(b), d3, maps.data_ptr(),
+                                                         self._stream(fx.t)))
+        return maps
 
     def tc_selftest(self, verbose: int = 1) -> int:
         return int(self.lib.lea_tc_selftest(verbose, C.c_void_p(torch.cuda.current_stream().cuda_stream)))

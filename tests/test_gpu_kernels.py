@@ -87,3 +87,23 @@ def test_conv_tc_single_pass(ops):
 def test_hot_path_golden_tc(ops, name, planes):
     rep = K.check_hot_path_golden(ops, DEV, name, planes=planes, conv="tc", mat_rtol=None)
     print(name, planes, rep)
+
+
+def test_fused_cost_volume_equals_materialised(ops):
+    """stem0 with the cost volume built inside its TMA loader must reproduce the run on the materialised volume
+    bit for bit (same operands, same MMA order)."""
+    g = load_golden("cal_48x96_d48")
+    outs = {}
+    for fuse_cv in (False, True):
+        model = K.seeded_model(int(g["maxdisp"]))
+        model.load_state_dict(K.golden_state_dict(g, model))
+        model = model.to(DEV).eval()
+        model.engine_options = {"planes": 2, "conv": "tc", "fuse_cv": fuse_cv}
+        fx, fy = torch.from_numpy(g["fx"]).to(DEV), torch.from_numpy(g["fy"]).to(DEV)
+        from leastereo_b200 import engine
+        disp = engine.hot_path_forward(model, fx, fy, ops=ops)
+        plan = engine.get_plan(model.matching, 1, (16, 16, 32), fx.device, engine._options(model), ops)
+        assert (plan.fxp is not None) == fuse_cv
+        outs[fuse_cv] = (plan.mat.clone(), disp.clone())
+    assert torch.equal(outs[False][0], outs[True][0])
+    assert torch.equal(outs[False][1], outs[True][1])
