@@ -132,15 +132,9 @@ extern "C" int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D
                              int32_t maxdisp, void* stream) {
     LEA_CHECK(mat && disp, "disp_head: null pointer");
     LEA_CHECK(B > 0 && D3 > 0 && H3 > 0 && W3 > 0 && maxdisp > 0 && B <= 65535, "disp_head: bad shape");
-    const size_t smem = (size_t)D3 * (LEA_DH_TH3 + 2) * (LEA_DH_TW3 + 2) * sizeof(float);
-    LEA_CHECK(smem <= 200 * 1024, "disp_head: D3 = %d needs %zu bytes of shared memory", D3, smem);
-#ifndef LEA_CPU_EMU
-    if (smem > 48 * 1024)
-        cudaFuncSetAttribute(lea_disp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-#endif
-    const int tiles = ((W3 + LEA_DH_TW3 - 1) / LEA_DH_TW3) * ((H3 + LEA_DH_TH3 - 1) / LEA_DH_TH3);
-    LEA_LAUNCH(lea_disp_head_kernel, dim3(tiles, B), dim3(9 * LEA_DH_TH3 * LEA_DH_TW3), smem, stream,
-               mat, disp, D3, H3, W3, maxdisp);
+    LEA_CHECK((H3 + LEA_DH_BY - 1) / LEA_DH_BY <= 65535, "disp_head: grid too large");
+    LEA_LAUNCH(lea_disp_head_kernel, dim3((W3 + LEA_DH_BX - 1) / LEA_DH_BX, (H3 + LEA_DH_BY - 1) / LEA_DH_BY, B),
+               dim3(LEA_DH_BX * LEA_DH_BY), 0, stream, mat, disp, D3, H3, W3, maxdisp);
     return LEA_POST_LAUNCH();
 }
 

@@ -338,13 +338,14 @@ lea_conv1_simt_kernel(lea_conv p, const float* __restrict__ weight) {
 //       F.interpolate(x, [maxdisp, 3*H3, 3*W3], 'trilinear', align_corners=False) -> Softmin(dim=1) -> sum_d p*d
 //     in one kernel; the maxdisp x 3H3 x 3W3 probability volume is never written.  align_corners=False index rule:
 //     scale = in/out; src = max(scale*(dst+0.5)-0.5, 0); i0 = floor(src) (<= in-1); l1 = src-i0; i1 = min(i0+1, in-1).
-//     A CTA stages the (TH3+2) x (TW3+2) x D3 low-res neighbourhood in shared memory and produces 3*TH3 x 3*TW3
-//     pixels, one thread per pixel: pass 1 finds m = min_k u[k] of the bilinearly blended column u (a valid softmin
-//     stabiliser because every up-sampled logit is a convex combination of u), pass 2 streams the maxdisp samples.
+//     One thread owns one low-res cell (h3, w3) and produces its 3x3 output pixels: with the exact x3 scale every one
+//     of them blends only the 3x3 low-res neighbourhood, so per disparity sample k the thread loads 9 values
+//     (coalesced along w3, neighbours hit L1) and forms the 9 blended logits u_p[k] with per-axis 3-tap weights.
+//     (Measured alternatives: thread-per-pixel with a shared-memory tile 168 us, 3 threads per cell 146 us, this 105 us.)
+//     Pass 1 finds m_p = min_k u_p[k] (a valid softmin stabiliser: every up-sampled logit is a convex combination of
+//     u_p); pass 2 streams the maxdisp samples with a sliding (k0, k1) window.  Cost per pair: 2*9*D3 loads per cell
+//     and maxdisp exps per pixel - the kernel is bound by the exp (MUFU) rate, not by HBM.
 // =========================================================================================================
-#define LEA_DH_TH3 4
-#define LEA_DH_TW3 8
-
 LEA_HD lea_axis_lerp lea_axis_half_pixel(int dst, int in_n, int out_n) {
     lea_axis_lerp r;
     const float scale = (float)in_n / (float)out_n;
@@ -358,56 +359,119 @@ LEA_HD lea_axis_lerp lea_axis_half_pixel(int dst, int in_n, int out_n) {
     return r;
 }
 
-__global__ void __launch_bounds__(9 * LEA_DH_TH3 * LEA_DH_TW3)
+// weights of output index 3*c + r on the three taps (c-1, c, c+1); returns false if a tap falls outside them
+LEA_HD bool lea_three_tap(int c, int r, int in_n, float* t /*[3]*/) {
+    const lea_axis_lerp a = lea_axis_half_pixel(3 * c + r, in_n, 3 * in_n);
+    const int j0 = a.i0 - c + 1, j1 = a.i1 - c + 1;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) t[j] = (j0 == j ? a.l0 : 0.0f) + (j1 == j ? a.l1 : 0.0f);   // no dynamic indexing
+    return !(j0 < 0 || j0 > 2 || j1 < 0 || j1 > 2);
+}
+
+#define LEA_DH_BX 32
+#define LEA_DH_BY 4
+
+// raw 3x3 neighbourhood of a cell at disparity sample k, and the 9 blended logits
+//   u[r*3+c] = sum_{i,j} th[r][i] * tw[c][j] * s[k][i][j]
+#define LEA_DH_LOAD(raw, k)                                                                           \
+    {                                                                                                 \
+        const float* __restrict__ pk = mb + (int64_t)(k) * H3 * W3;                                   \
+        _Pragma("unroll") for (int i = 0; i < 3; ++i)                                                 \
+            _Pragma("unroll") for (int j = 0; j < 3; ++j) raw[i * 3 + j] = __ldg(pk + ro[i] + wo[j]); \
+    }
+#define LEA_DH_COMBINE(u, raw)                                                                        \
+    {                                                                                                 \
+        float row[3][3];                                                                              \
+        _Pragma("unroll") for (int i = 0; i < 3; ++i)                                                 \
+            _Pragma("unroll") for (int c = 0; c < 3; ++c)                                             \
+                row[i][c] = tw[c][0] * raw[i * 3] + tw[c][1] * raw[i * 3 + 1] + tw[c][2] * raw[i * 3 + 2]; \
+        _Pragma("unroll") for (int r = 0; r < 3; ++r)                                                 \
+            _Pragma("unroll") for (int c = 0; c < 3; ++c)                                             \
+                u[r * 3 + c] = th[r][0] * row[0][c] + th[r][1] * row[1][c] + th[r][2] * row[2][c];    \
+    }
+
+__global__ void __launch_bounds__(LEA_DH_BX * LEA_DH_BY)
 lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
                      int D3, int H3, int W3, int maxdisp) {
-    LEA_DYN_SMEM(float, s);            // s[k][TH3+2][TW3+2]
-    constexpr int SH = LEA_DH_TH3 + 2, SW = LEA_DH_TW3 + 2, SP = SH * SW;
-    const int tiles_w = (W3 + LEA_DH_TW3 - 1) / LEA_DH_TW3;
-    const int tw = blockIdx.x % tiles_w, th = blockIdx.x / tiles_w;
-    const int b = blockIdx.y;
-    const int h3_0 = th * LEA_DH_TH3 - 1, w3_0 = tw * LEA_DH_TW3 - 1;     // low-res origin of the staged tile
-    const int tid = threadIdx.x, nthreads = 9 * LEA_DH_TH3 * LEA_DH_TW3;
+    const int w3 = blockIdx.x * LEA_DH_BX + threadIdx.x % LEA_DH_BX;
+    const int h3 = blockIdx.y * LEA_DH_BY + threadIdx.x / LEA_DH_BX;
+    const int b = blockIdx.z;
+    if (w3 >= W3 || h3 >= H3) return;
     const float* __restrict__ mb = mat + (int64_t)b * D3 * H3 * W3;
-    for (int e = tid; e < D3 * SP; e += nthreads) {
-        const int k = e / SP, r = e - k * SP;
-        const int hh = r / SW, ww = r - hh * SW;
-        int gh = h3_0 + hh, gw = w3_0 + ww;
-        gh = gh < 0 ? 0 : (gh > H3 - 1 ? H3 - 1 : gh);        // clamped reads: edge taps get weight 0 anyway
-        gw = gw < 0 ? 0 : (gw > W3 - 1 ? W3 - 1 : gw);
-        s[e] = __ldg(mb + ((int64_t)k * H3 + gh) * W3 + gw);
+    float th[3][3], tw[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) { lea_three_tap(h3, r, H3, th[r]); lea_three_tap(w3, r, W3, tw[r]); }
+    // clamped neighbour offsets (edge taps carry weight 0)
+    int ro[3], wo[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        int hh = h3 - 1 + i, ww = w3 - 1 + i;
+        hh = hh < 0 ? 0 : (hh > H3 - 1 ? H3 - 1 : hh);
+        ww = ww < 0 ? 0 : (ww > W3 - 1 ? W3 - 1 : ww);
+        ro[i] = hh * W3; wo[i] = ww;
     }
-    __syncthreads();
-    const int ow_l = tid % (3 * LEA_DH_TW3), oh_l = tid / (3 * LEA_DH_TW3);
-    const int oh = th * 3 * LEA_DH_TH3 + oh_l, ow = tw * 3 * LEA_DH_TW3 + ow_l;
-    if (oh >= 3 * H3 || ow >= 3 * W3) return;
-    const lea_axis_lerp ah = lea_axis_half_pixel(oh, H3, 3 * H3);
-    const lea_axis_lerp aw = lea_axis_half_pixel(ow, W3, 3 * W3);
-    const int o00 = (ah.i0 - h3_0) * SW + (aw.i0 - w3_0), o01 = (ah.i0 - h3_0) * SW + (aw.i1 - w3_0);
-    const int o10 = (ah.i1 - h3_0) * SW + (aw.i0 - w3_0), o11 = (ah.i1 - h3_0) * SW + (aw.i1 - w3_0);
-    const float c00 = ah.l0 * aw.l0, c01 = ah.l0 * aw.l1, c10 = ah.l1 * aw.l0, c11 = ah.l1 * aw.l1;
-#define LEA_U(k) (c00 * s[(k) * SP + o00] + c01 * s[(k) * SP + o01] + c10 * s[(k) * SP + o10] + c11 * s[(k) * SP + o11])
-    float m = LEA_U(0);
-    for (int k = 1; k < D3; ++k) { const float u = LEA_U(k); m = u < m ? u : m; }
-    // pass 2: stream the maxdisp samples with a sliding (k0, k1) window along disparity
-    float den = 0.0f, num = 0.0f;
-    int kc = -1; float u0 = 0.0f, u1 = 0.0f; int k1c = -1;
+    // pass 1: per-pixel minimum of the blended column (next sample prefetched while this one is reduced)
+    float m[9];
+    {
+        float u[9], cur[9], nxt[9];
+        LEA_DH_LOAD(cur, 0);
+        LEA_DH_COMBINE(u, cur);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) m[q] = u[q];
+        if (D3 > 1) LEA_DH_LOAD(cur, 1);
+        for (int k = 1; k < D3; ++k) {
+            if (k + 1 < D3) LEA_DH_LOAD(nxt, k + 1);
+            LEA_DH_COMBINE(u, cur);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) { m[q] = u[q] < m[q] ? u[q] : m[q]; cur[q] = nxt[q]; }
+        }
+    }
+    // pass 2: stream the maxdisp samples; (k0, k1) window along disparity
+    float den[9], num[9], u0[9], u1[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { den[q] = 0.0f; num[q] = 0.0f; u0[q] = 0.0f; u1[q] = 0.0f; }
+    int kc = -1, k1c = -1;
     for (int i = 0; i < maxdisp; ++i) {
         const lea_axis_lerp ad = lea_axis_half_pixel(i, D3, maxdisp);
         if (ad.i0 != kc) {
-            u0 = (ad.i0 == k1c) ? u1 : LEA_U(ad.i0);
-            kc = ad.i0;
-            k1c = -1;
+            if (ad.i0 == k1c) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) u0[q] = u1[q];
+            } else {
+                float raw[9];
+                LEA_DH_LOAD(raw, ad.i0);
+                LEA_DH_COMBINE(u0, raw);
+            }
+            kc = ad.i0; k1c = -1;
         }
-        if (ad.i1 != k1c) { u1 = (ad.i1 == kc) ? u0 : LEA_U(ad.i1); k1c = ad.i1; }
-        const float v = ad.l0 * u0 + ad.l1 * u1;
-        const float e = __expf(m - v);                 // softmin: exp(-(v - m)), v >= m up to rounding
-        den += e;
-        num += e * (float)i;
+        if (ad.i1 != k1c) {
+            if (ad.i1 == kc) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) u1[q] = u0[q];
+            } else {
+                float raw[9];
+                LEA_DH_LOAD(raw, ad.i1);
+                LEA_DH_COMBINE(u1, raw);
+            }
+            k1c = ad.i1;
+        }
+        const float fi = (float)i;
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const float v = ad.l0 * u0[q] + ad.l1 * u1[q];
+            const float e = __expf(m[q] - v);                  // softmin: exp(-(v - m)), v >= m up to rounding
+            den[q] += e;
+            num[q] += e * fi;
+        }
     }
-#undef LEA_U
-    disp[((int64_t)b * 3 * H3 + oh) * (3 * W3) + ow] = num / den;
+    float* __restrict__ o = disp + ((int64_t)b * 3 * H3 + 3 * h3) * (3 * W3) + 3 * w3;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) o[(int64_t)r * 3 * W3 + c] = num[r * 3 + c] / den[r * 3 + c];
 }
+#undef LEA_DH_LOAD
+#undef LEA_DH_COMBINE
 
 // DisparityRegression alone (models/build_model_2d.py:36-41)
 __global__ void __launch_bounds__(256)
