@@ -107,3 +107,101 @@ def test_fused_cost_volume_equals_materialised(ops):
         outs[fuse_cv] = (plan.mat.clone(), disp.clone())
     assert torch.equal(outs[False][0], outs[True][0])
     assert torch.equal(outs[False][1], outs[True][1])
+
+
+# ---- BASELINE.json full sizes: size-independent properties -----------------------------------------------------
+def _random_model(maxdisp, options):
+    model = K.seeded_model(maxdisp).to(DEV).eval()
+    model.engine_options = dict(options)
+    return model
+
+
+def test_cost_volume_full_kitti_bit_exact(ops):
+    """KITTI 1/3-res shape (32 x 128 x 416, D3 = 64): 886 MB volume, bit-exact against the oracle's numpy loop."""
+    g = torch.Generator().manual_seed(11)
+    x, y = torch.randn(1, 32, 128, 416, generator=g), torch.randn(1, 32, 128, 416, generator=g)
+    got = ops.cost_volume_f32(x.to(DEV), y.to(DEV), 192).cpu().numpy()
+    want = O.cost_volume_numpy(x.numpy(), y.numpy(), 192)
+    assert got.tobytes() == want.tobytes()
+    # the planes-layout kernel must hold the same values (3 planes = exact fp32)
+    vol = ops.cost_volume_planes(x.to(DEV), y.to(DEV), 192, 3)
+    assert torch.equal(ops.unpack(vol).cpu(), torch.from_numpy(want))
+
+
+def test_disp_head_full_kitti(ops):
+    g = torch.Generator().manual_seed(12)
+    mat = torch.randn(1, 1, 64, 128, 416, generator=g) * 4
+    got = ops.disp_head(mat.to(DEV), 192).cpu()
+    want = O.disp_head(mat, 192)
+    assert float((got - want).abs().max()) <= 2e-3
+
+
+def test_hot_path_kitti_tc_vs_fp32_simt(ops):
+    """Full KITTI 384x1248, D=192, random-init weights: the tensor-core bf16x3 path against the fp32 SIMT path with
+    exact (3-plane) storage - the mode that is pinned to the reference by the golden tests."""
+    torch.manual_seed(5)
+    left, right = torch.randn(1, 3, 384, 1248, device=DEV), torch.randn(1, 3, 384, 1248, device=DEV)
+    outs = {}
+    for name, opt in (("tc", {"planes": 2, "conv": "tc"}), ("simt", {"planes": 3, "conv": "simt"})):
+        model = _random_model(192, opt)
+        with torch.no_grad():
+            outs[name] = model(left, right).float().cpu()
+        del model
+        torch.cuda.empty_cache()
+    rep = O.tolerance_report(outs["tc"], outs["simt"])
+    print("KITTI tc(P=2) vs simt(P=3):", rep)
+    assert outs["tc"].shape == (1, 384, 1248) and torch.isfinite(outs["tc"]).all()
+    assert rep["ok"], rep
+
+
+def test_batch_independence_sceneflow(ops):
+    """SceneFlow 576x960 (configs[1]): in eval mode a pair's disparity must not depend on its batch-mates."""
+    torch.manual_seed(6)
+    left, right = torch.randn(3, 3, 576, 960, device=DEV), torch.randn(3, 3, 576, 960, device=DEV)
+    model = _random_model(192, {"planes": 2, "conv": "tc"})
+    with torch.no_grad():
+        full = model(left, right)
+        one = model(left[1:2], right[1:2])
+    assert full.shape == (3, 576, 960)
+    assert torch.equal(full[1:2], one)
+
+
+def test_middlebury_shape_runs(ops):
+    """Middlebury half-res 1008x1512, maxdisp 408 (configs[3], the largest cost volume): runs, finite, in range."""
+    torch.manual_seed(7)
+    left, right = torch.randn(1, 3, 1008, 1512, device=DEV), torch.randn(1, 3, 1008, 1512, device=DEV)
+    model = _random_model(408, {"planes": 2, "conv": "tc"})
+    with torch.no_grad():
+        d = model(left, right)
+    assert d.shape == (1, 1008, 1512) and torch.isfinite(d).all()
+    assert float(d.min()) >= 0.0 and float(d.max()) <= 407.0
+
+
+def test_ragged_input_size(ops):
+    """H, W not multiples of 3 and maxdisp % 3 != 0 (output is 3*ceil(H/3) x 3*ceil(W/3) like the reference)."""
+    rep = K.check_hot_path_golden(ops, DEV, "cal_46x94_d50", planes=2, conv="tc", mat_rtol=None)
+    g = load_golden("cal_46x94_d50")
+    model = K.seeded_model(50)
+    model.load_state_dict(K.golden_state_dict(g, model))
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        d = model(torch.from_numpy(g["left"]).to(DEV), torch.from_numpy(g["right"]).to(DEV))
+    assert d.shape == (1, 48, 96)
+    full = O.tolerance_report(d.cpu(), torch.from_numpy(g["disp"]))      # includes the stock-PyTorch feature net
+    assert full["ok"], full
+
+
+def test_state_dict_roundtrip_and_module_prefix(ops):
+    g = load_golden("cal_b2_24x48_d24")
+    model = K.seeded_model(24)
+    sd = K.golden_state_dict(g, model)
+    model.load_state_dict({"module." + k: v for k, v in sd.items()})      # DataParallel-style checkpoint (train.py:376)
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        d = model(torch.from_numpy(g["left"]).to(DEV), torch.from_numpy(g["right"]).to(DEV))
+    assert O.tolerance_report(d.cpu(), torch.from_numpy(g["disp"]))["ok"]
+    # parameters changed in place must be picked up (BN refresh + weight re-pack)
+    with torch.no_grad():
+        model.matching.stem0.conv.weight.mul_(1.5)
+        d2 = model(torch.from_numpy(g["left"]).to(DEV), torch.from_numpy(g["right"]).to(DEV))
+    assert not torch.equal(d, d2)

@@ -1,0 +1,64 @@
+"""CPU tests (-m "not gpu") of the multi-GPU partitioning logic with the gloo backend, world_size 2 and 3.
+The forward function is the oracle here (the CUDA path needs a GPU); what is under test is the sharding/gather code
+the bench and a multi-GPU caller use: pair order, ragged and empty shards."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import load_golden, golden_state_dict
+from leastereo_b200.sharding import shard_range, sharded_inference
+
+
+def test_shard_range_properties():
+    for n in range(0, 20):
+        for ws in range(1, 9):
+            blocks = [shard_range(n, r, ws) for r in range(ws)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, n_pairs, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from oracle import leastereo_oracle as O
+    g = load_golden("cal_b2_24x48_d24")
+    sd = golden_state_dict(g)
+    left = torch.from_numpy(g["left"]).repeat((n_pairs + 1) // 2, 1, 1, 1)[:n_pairs]
+    right = torch.from_numpy(g["right"]).repeat((n_pairs + 1) // 2, 1, 1, 1)[:n_pairs]
+    left = left + 0.01 * torch.arange(n_pairs, dtype=torch.float32).view(-1, 1, 1, 1)   # make every pair distinct
+
+    def fwd(l, r):
+        return O.leastereo_forward(sd, l, r, int(g["maxdisp"]))
+
+    out = sharded_inference(fwd, left, right, rank, world)
+    if rank == 0:
+        torch.save({"sharded": out, "full": fwd(left, right)}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_pairs", [(2, 3), (3, 2)])
+def test_sharded_inference_matches_single_process(tmp_path, world, n_pairs):
+    out_path = str(tmp_path / "out.pt")
+    mp.spawn(_worker, args=(world, _free_port(), n_pairs, out_path), nprocs=world, join=True)
+    res = torch.load(out_path)
+    assert res["sharded"].shape == res["full"].shape
+    # BN is in eval mode, so a pair's result does not depend on its batch-mates: sharding must be exact up to the
+    # fp32 re-ordering noise of the CPU convs, which pick different algorithms for different batch sizes
+    # (that noise floor is max 9e-3 px, mean 4e-4 px on this network)
+    diff = (res["sharded"] - res["full"]).abs()
+    assert float(diff.max()) <= 0.05 and float(diff.mean()) <= 1e-3
