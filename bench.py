@@ -52,22 +52,59 @@ def load_peaks():
 
 # ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU during the timed region."""
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML every 10 ms; nvidia-smi fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # NVML clocks-event (throttle) reason bits
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index: int):
-        self.index, self.samples, self._stop, self._t = index, [], threading.Event(), None
+        self.index, self._stop, self._t = index, threading.Event(), None
+        self.sm, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                return int(ids[index])
+        return index
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self.nvml is not None:
+                    n = self.nvml
+                    self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                    try:
+                        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    except Exception:  # noqa: BLE001
+                        r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    for name, bit in self.BITS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                    self.power.append(n.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                    self._stop.wait(0.01)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [s.strip() for s in out.strip().split(",")]
+                f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 7:
-                    self.samples.append(f)
+                    self.sm.append(float(f[0])); self.max_mhz = float(f[1])
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(name)
             except Exception:  # noqa: BLE001
                 pass
             self._stop.wait(0.2)
@@ -82,17 +119,10 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, reasons, mx = [], set(), None
-        for f in self.samples:
-            try:
-                sm.append(float(f[0])); mx = float(f[1])
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "power_w_max": round(max(self.power), 1) if self.power else None,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------------------
