@@ -115,6 +115,32 @@ int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D3, int32_t 
 int lea_disparity_regression(const float* p, float* out, int32_t B, int32_t maxdisp, int32_t H, int32_t W,
                              void* stream);
 
+/* ---- training side (what the reference gets from autograd, train.py:156-160) --------------------- */
+/* Per-channel reductions over a channel slice, written as `chunks` partial rows partial[(chunk*2+which)*c + ch]
+ * (the caller adds the chunks).  mode 0: sum x, sum x^2 (BatchNorm3d batch statistics, operations_3d.py:38,44).
+ * mode 1: with g = dy*[relu mask of x*scale+shift], xh = (x-mean)*invstd:  sum g, sum g*xh  (BN backward). */
+int lea_channel_reduce(const lea_vol* x, int32_t x_c0, const lea_vol* dy, int32_t dy_c0, int32_t c, int32_t mode,
+                       int32_t relu, const float* scale, const float* shift, const float* mean, const float* invstd,
+                       float* partial, int32_t chunks, void* stream);
+/* dst = [dst +] relu?(x*scale[ch] + shift[ch])  - BN apply in train mode and the state sums (skip_model_3d.py:70). */
+int lea_affine_relu(const lea_vol* x, int32_t x_c0, const lea_vol* dst, int32_t dst_c0, int32_t c, const float* scale,
+                    const float* shift, int32_t relu, int32_t accumulate, void* stream);
+/* dx = ka[ch]*g - kb[ch] - xh*kc[ch]  (BN(train)+ReLU backward; ka = gamma*invstd, kb = ka*mean(g), kc = ka*mean(g*xh)). */
+int lea_bn_relu_bwd(const lea_vol* x, int32_t x_c0, const lea_vol* dy, int32_t dy_c0, const lea_vol* dx, int32_t dx_c0,
+                    int32_t c, int32_t relu, const float* scale, const float* shift, const float* mean,
+                    const float* invstd, const float* ka, const float* kb, const float* kc, void* stream);
+/* dw[c_out][c_in][k^3] += sum_voxels dout * in(shifted)   (fp32, atomically accumulated: zero dw first). */
+int lea_conv3d_wgrad(const lea_vol* in, int32_t in_c0, int32_t c_in, const lea_vol* dout, int32_t dout_c0, int32_t c_out,
+                     int32_t ksize, float* dw, void* stream);
+/* dsrc += transpose of the align_corners=True trilinear resample applied to ddst. */
+int lea_trilinear_ac_bwd(const lea_vol* ddst, int32_t ddst_c0, const lea_vol* dsrc, int32_t dsrc_c0, int32_t c,
+                         void* stream);
+/* transpose of the cost-volume construction (LEAStereo.py:42-48): dcost (2C channels) -> dx, dy (B, C, H, W) fp32. */
+int lea_cost_volume_bwd(const lea_vol* dcost, int32_t C, float* dx, float* dy, void* stream);
+/* backward of lea_disp_head: dmat (B, D3, H3, W3) += J^T gout; dmat must be zero-initialised by the caller. */
+int lea_disp_head_bwd(const float* mat, const float* gout, float* dmat, int32_t B, int32_t D3, int32_t H3, int32_t W3,
+                      int32_t maxdisp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,4 +20,6 @@ static int lea_post_launch(const char* what) {
 #define LEA_POST_LAUNCH() lea_post_launch(__func__)
 
 #include "lea_simt_kernels.cuh"
+#include "lea_train_kernels.cuh"
 #include "lea_api_simt.inl"
+#include "lea_api_train.inl"

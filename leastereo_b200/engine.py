@@ -499,13 +499,15 @@ def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops:
 def _require_inference(module):
     if module.training:
         raise NotImplementedError(
-            "leastereo_b200: train-mode BatchNorm and the backward kernels of the hot path are not built yet "
-            "(DESIGN.md, 'what comes next'); call .eval() - there is deliberately no autograd/PyTorch fallback")
+            "leastereo_b200: this entry point is inference-only; train-mode BatchNorm and the backward kernels run "
+            "through LEAStereo.forward (leastereo_b200/training.py) - there is deliberately no PyTorch fallback")
 
 
 def hot_path_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optional[Ops] = None) -> torch.Tensor:
     """cost volume -> matching net -> disparity head on feature maps (B, C, H3, W3) -> (B, 3*H3, 3*W3)."""
-    _require_inference(model)
+    if model.training:
+        from .training import hot_path_train_forward      # batch-statistics BN + backward kernels
+        return hot_path_train_forward(model, fx, fy, ops)
     ops = ops or get_ops()
     opt = _options(model)
     fx = fx.detach().float().contiguous()

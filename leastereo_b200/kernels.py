@@ -56,7 +56,17 @@ SYMBOLS = {
     "lea_build_fused_cv_maps": (C.c_int, [_VOLP, _VOLP, _i32, _vp, _vp]),
     "lea_disp_head": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "lea_disparity_regression": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "lea_channel_reduce": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "lea_affine_relu": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp, _vp, _i32, _i32, _vp]),
+    "lea_bn_relu_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lea_conv3d_wgrad": (C.c_int, [_VOLP, _i32, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp]),
+    "lea_trilinear_ac_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp]),
+    "lea_cost_volume_bwd": (C.c_int, [_VOLP, _i32, _vp, _vp, _vp]),
+    "lea_disp_head_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
+# symbols only the CUDA build has (tcgen05 path); the CPU emulation used by the no-GPU tests lacks them
+DEVICE_ONLY = {"lea_tc_weight_image_bytes", "lea_pack_weights_tc", "lea_conv3d_tc", "lea_tc_selftest",
+               "lea_fused_cv_maps_bytes", "lea_build_fused_cv_maps"}
 
 
 class LeaError(RuntimeError):
@@ -281,6 +291,86 @@ class Ops:
             self._check(self.lib.lea_disp_head(mat.data_ptr(), out.data_ptr(), B, D3, H3, W3, int(maxdisp),
                                                self._stream(mat)))
         return out
+
+    # ---- training side ------------------------------------------------------------------------------------
+    def _dev_ctx(self, t: torch.Tensor):
+        return torch.cuda.device(t.device) if t.is_cuda else _null()
+
+    @staticmethod
+    def _ptr(t: Optional[torch.Tensor]):
+        return None if t is None else t.data_ptr()
+
+    def channel_reduce(self, x: PlanesVol, x_c0: int, c: int, mode: int = 0, dy: Optional[PlanesVol] = None,
+                       dy_c0: int = 0, relu: bool = False, scale=None, shift=None, mean=None, invstd=None,
+                       chunks: int = 64) -> torch.Tensor:
+        """Per-channel (sum, sum of squares) [mode 0] or BN-backward sums [mode 1]; returns float64 (2, c)."""
+        self._dev(x.t)
+        vox = x.B * x.D * x.H * x.W
+        chunks = max(1, min(chunks, (vox + 255) // 256))
+        partial = torch.empty((chunks, 2, c), dtype=torch.float32, device=x.t.device)
+        xs = x.struct()
+        ds = dy.struct() if dy is not None else xs
+        with self._dev_ctx(x.t):
+            self._check(self.lib.lea_channel_reduce(C.byref(xs), x_c0, C.byref(ds), dy_c0, c, mode, int(bool(relu)),
+                                                    self._ptr(scale), self._ptr(shift), self._ptr(mean),
+                                                    self._ptr(invstd), partial.data_ptr(), chunks, self._stream(x.t)))
+        return partial.double().sum(dim=0)
+
+    def affine_relu(self, x: PlanesVol, x_c0: int, dst: PlanesVol, dst_c0: int, c: int, scale=None, shift=None,
+                    relu: bool = False, accumulate: bool = False):
+        self._dev(x.t, dst.t)
+        xs, ds = x.struct(), dst.struct()
+        with self._dev_ctx(x.t):
+            self._check(self.lib.lea_affine_relu(C.byref(xs), x_c0, C.byref(ds), dst_c0, c, self._ptr(scale),
+                                                 self._ptr(shift), int(bool(relu)), int(bool(accumulate)),
+                                                 self._stream(x.t)))
+
+    def bn_relu_bwd(self, x: PlanesVol, x_c0: int, dy: PlanesVol, dy_c0: int, dx: PlanesVol, dx_c0: int, c: int,
+                    relu: bool, scale, shift, mean, invstd, ka, kb, kc):
+        self._dev(x.t, dy.t, dx.t)
+        xs, ys, ds = x.struct(), dy.struct(), dx.struct()
+        with self._dev_ctx(x.t):
+            self._check(self.lib.lea_bn_relu_bwd(C.byref(xs), x_c0, C.byref(ys), dy_c0, C.byref(ds), dx_c0, c,
+                                                 int(bool(relu)), scale.data_ptr(), shift.data_ptr(), mean.data_ptr(),
+                                                 invstd.data_ptr(), ka.data_ptr(), kb.data_ptr(), kc.data_ptr(),
+                                                 self._stream(x.t)))
+
+    def conv3d_wgrad(self, src: PlanesVol, src_c0: int, c_in: int, dout: PlanesVol, dout_c0: int, c_out: int,
+                     ksize: int, dw: torch.Tensor):
+        self._dev(src.t, dout.t, dw)
+        assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == c_out * c_in * ksize ** 3
+        a, b = src.struct(), dout.struct()
+        with self._dev_ctx(src.t):
+            self._check(self.lib.lea_conv3d_wgrad(C.byref(a), src_c0, c_in, C.byref(b), dout_c0, c_out, ksize,
+                                                  dw.data_ptr(), self._stream(src.t)))
+
+    def trilinear_ac_bwd(self, ddst: PlanesVol, ddst_c0: int, dsrc: PlanesVol, dsrc_c0: int, c: int):
+        self._dev(ddst.t, dsrc.t)
+        a, b = ddst.struct(), dsrc.struct()
+        with self._dev_ctx(ddst.t):
+            self._check(self.lib.lea_trilinear_ac_bwd(C.byref(a), ddst_c0, C.byref(b), dsrc_c0, c, self._stream(ddst.t)))
+
+    def cost_volume_bwd(self, dcost: PlanesVol, Cn: int):
+        self._dev(dcost.t)
+        dx = torch.empty((dcost.B, Cn, dcost.H, dcost.W), dtype=torch.float32, device=dcost.t.device)
+        dy = torch.empty_like(dx)
+        a = dcost.struct()
+        with self._dev_ctx(dcost.t):
+            self._check(self.lib.lea_cost_volume_bwd(C.byref(a), Cn, dx.data_ptr(), dy.data_ptr(), self._stream(dcost.t)))
+        return dx, dy
+
+    def disp_head_bwd(self, mat: torch.Tensor, gout: torch.Tensor, maxdisp: int) -> torch.Tensor:
+        mat, gout = self._f32(mat), self._f32(gout)
+        self._dev(mat, gout)
+        if mat.dim() == 5:
+            mat = mat[:, 0]
+        B, D3, H3, W3 = mat.shape
+        assert tuple(gout.shape) == (B, 3 * H3, 3 * W3)
+        dmat = torch.zeros_like(mat)
+        with self._dev_ctx(mat):
+            self._check(self.lib.lea_disp_head_bwd(mat.data_ptr(), gout.data_ptr(), dmat.data_ptr(), B, D3, H3, W3,
+                                                   int(maxdisp), self._stream(mat)))
+        return dmat
 
     def disparity_regression(self, p: torch.Tensor, maxdisp: int) -> torch.Tensor:
         p = self._f32(p)

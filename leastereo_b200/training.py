@@ -1,0 +1,400 @@
+"""Train-mode execution of the hot path: forward with batch-statistics BatchNorm and the full backward
+(reference: ``train.py:153-160`` - ``model.train()``, ``loss.backward()`` through
+``retrain/LEAStereo.py:34-51``, ``retrain/skip_model_3d.py``, ``models/operations_3d.py:41-47``,
+``models/build_model_2d.py:52-57``).
+
+Correctness-first design: every layer is one node with a ``forward`` and a ``backward`` over pre-allocated planes
+volumes (value buffer + gradient buffer per activation).  ConvBR in train mode = conv (raw, tensor-core or SIMT kernel)
+-> per-channel batch statistics (``lea_channel_reduce``) -> normalise + ReLU (+ state-sum accumulate)
+(``lea_affine_relu``); its backward = two per-channel reductions + ``lea_bn_relu_bwd`` -> data gradient (the forward
+conv kernel with transposed, tap-flipped weights, accumulated into the input's gradient) + weight gradient
+(``lea_conv3d_wgrad``).  BatchNorm statistics are per replica (what nn.DataParallel gives the reference);
+running statistics follow momentum 0.1 / unbiased variance.  There is no autograd/PyTorch fallback for any of this.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from .engine import Slice, _prod
+from .kernels import LeaError, Ops, PlanesVol, get_ops, lea_tc_opts
+from .modules import ConvBR3d, Identity3d, newMatching
+from .structure import scale_dimension
+
+
+class _Node:
+    def forward(self):
+        raise NotImplementedError
+
+    def backward(self):
+        raise NotImplementedError
+
+
+class TrainPlan:
+    def __init__(self, matching: newMatching, ops: Ops, B: int, spatial, planes: int, device, conv_mode: str, maxdisp):
+        self.m, self.ops, self.B, self.spatial, self.P = matching, ops, B, tuple(int(v) for v in spatial), planes
+        self.device = torch.device(device)
+        self.conv_mode = conv_mode
+        self.maxdisp = maxdisp
+        self.nodes: List[_Node] = []
+        self.grads: Dict[int, PlanesVol] = {}
+        self.values: List[PlanesVol] = []
+        self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self._build()
+
+    # ---- buffers ----------------------------------------------------------------------------------------
+    def vol(self, c, spatial) -> PlanesVol:
+        v = PlanesVol.empty(self.B, c, self.P, *spatial, self.device)
+        self.values.append(v)
+        return v
+
+    def grad_of(self, v: PlanesVol) -> PlanesVol:
+        g = self.grads.get(id(v))
+        if g is None:
+            g = PlanesVol.empty(v.B, v.C, v.P, v.D, v.H, v.W, self.device)
+            self.grads[id(v)] = g
+        return g
+
+    def add_param_grad(self, p: torch.nn.Parameter, g: torch.Tensor):
+        if p in self.param_grads:
+            self.param_grads[p] = self.param_grads[p] + g
+        else:
+            self.param_grads[p] = g
+
+    # ---- conv launch helper (raw conv: no BN, no ReLU) ----------------------------------------------------
+    def conv_raw(self, src: Slice, weight: torch.Tensor, dst: Optional[Slice], accumulate: bool = False,
+                 dst_f32: Optional[torch.Tensor] = None):
+        c_out, c_in, k = weight.shape[0], weight.shape[1], weight.shape[2]
+        if src.c != c_in:
+            raise LeaError("conv_raw: %d input channels, weight expects %d" % (src.c, c_in))
+        weight = weight.contiguous()
+        # the kernels take at most 64 output channels per launch
+        for o0 in range(0, c_out, 64):
+            oc = min(64, c_out - o0)
+            w = weight[o0:o0 + oc].contiguous() if (o0 > 0 or oc < c_out) else weight
+            d = None if dst is None else Slice(dst.vol, dst.c0 + o0, oc)
+            p = self.ops.make_conv(src.vol, src.c0, c_in, oc, k, None, None, False,
+                                   dst=None if d is None else d.vol, dst_c0=0 if d is None else d.c0,
+                                   res=d.vol if (accumulate and d is not None) else None,
+                                   res_c0=d.c0 if (accumulate and d is not None) else 0, dst_f32=dst_f32)
+            if self.conv_mode == "tc" and self.ops.tc_weight_image_bytes(c_in, oc, k, self.P) > 0:
+                img = self.ops.pack_weights_tc(w, self.P)
+                self.ops.conv3d_tc(p, img, lea_tc_opts(), src.vol.t)
+            else:
+                self.ops.conv3d_simt(p, w, src.vol.t)
+
+    # ---- graph construction (unfused mirror of retrain/skip_model_3d.py) -----------------------------------
+    def _convbr(self, name, mod: ConvBR3d, src: Slice, dst: Slice, accumulate=False):
+        self.nodes.append(_ConvBRNode(self, name, mod, src, dst, accumulate))
+
+    def _resample(self, name, src: Slice, spatial) -> Slice:
+        dst = Slice(self.vol(src.c, spatial), 0, src.c)
+        self.nodes.append(_ResampleNode(self, name, src, dst))
+        return dst
+
+    def _cell(self, i, s0: Slice, s1: Slice, out: Optional[Slice] = None):
+        cell = self.m.cells[i]
+        spec = cell.spec
+        name = "cells.%d" % i
+        prev_input = s1
+        c_out = spec.c_out
+        if spec.downup_sample != 0:
+            sp = tuple(scale_dimension(n, spec.scale) for n in s1.spatial)
+            s1 = self._resample(name + ".resample_s1", s1, sp)
+        if s0.spatial != s1.spatial:
+            s0 = self._resample(name + ".resample_s0", s0, s1.spatial)
+        sp = s1.spatial
+        bm = self.m._block_multiplier
+        n_states = 2 + len(spec.steps)
+        first = n_states - bm
+        if out is None:
+            out = Slice(self.vol(bm * c_out, sp), 0, bm * c_out)
+        elif out.spatial != sp or out.c != bm * c_out:
+            raise LeaError("cell %d output does not fit its skip-concat slot" % i)
+
+        def slot(q):
+            pos = q - first
+            return Slice(out.vol, out.c0 + pos * c_out, c_out) if pos >= 0 else Slice(self.vol(c_out, sp), 0, c_out)
+
+        if s0.c != c_out:
+            d0 = slot(0)
+            self._convbr(name + ".pre_preprocess", cell.pre_preprocess, s0, d0)
+            s0 = d0
+        elif first <= 0:
+            d0 = slot(0)
+            self.nodes.append(_CopyNode(self, name + ".s0_copy", s0, d0, False))
+            s0 = d0
+        d1 = slot(1)
+        self._convbr(name + ".preprocess", cell.preprocess, s1, d1)
+        states = [s0, d1]
+        for k, step in enumerate(spec.steps):
+            dst = slot(2 + k)
+            for n, (j, opi) in enumerate(step):
+                op = cell._ops[opi]
+                if isinstance(op, Identity3d):
+                    self.nodes.append(_CopyNode(self, "%s._ops.%d(skip)" % (name, opi), states[j], dst, n > 0))
+                else:
+                    self._convbr("%s._ops.%d" % (name, opi), op, states[j], dst, accumulate=n > 0)
+            states.append(dst)
+        return prev_input, out
+
+    def _build(self):
+        m = self.m
+        fm = m.initial_fm
+        L0 = self.spatial
+        self.cost = self.vol(2 * fm, L0)
+        v0, v1 = self.vol(fm, L0), self.vol(fm, L0)
+        self._convbr("stem0", m.stem0, Slice(self.cost, 0, 2 * fm), Slice(v0, 0, fm))
+        self._convbr("stem1", m.stem1, Slice(v0, 0, fm), Slice(v1, 0, fm))
+        stem0, stem1 = Slice(v0, 0, fm), Slice(v1, 0, fm)
+        out0 = self._cell(0, stem0, stem1)
+        spec1 = m.cells[1].spec
+        sp1 = out0[1].spatial if spec1.downup_sample == 0 else \
+            tuple(scale_dimension(n, spec1.scale) for n in out0[1].spatial)
+        cw = m._block_multiplier * spec1.c_out
+        skip = self.vol(3 * cw, sp1)
+        out1 = self._cell(1, out0[0], out0[1], Slice(skip, 0, cw))
+        out2 = self._cell(2, out1[0], out1[1])
+        out3 = self._cell(3, out2[0], out2[1])
+        out4 = self._cell(4, out3[0], out3[1], Slice(skip, cw, cw))
+        x5 = Slice(self.vol(m.conv1.conv.out_channels, sp1), 0, m.conv1.conv.out_channels)
+        self._convbr("conv1", m.conv1, Slice(skip, 0, 2 * cw), x5)
+        out5 = self._cell(5, out4[0], x5)
+        out6 = self._cell(6, out5[0], out5[1])
+        out7 = self._cell(7, out6[0], out6[1])
+        out8 = self._cell(8, out7[0], out7[1], Slice(skip, 2 * cw, cw))
+        x9 = Slice(self.vol(m.conv2.conv.out_channels, sp1), 0, m.conv2.conv.out_channels)
+        self._convbr("conv2", m.conv2, Slice(skip, cw, 2 * cw), x9)
+        out9 = self._cell(9, out8[0], x9)
+        out10 = self._cell(10, out9[0], out9[1])
+        out11 = self._cell(11, out10[0], out10[1])
+        last = out11[1]
+        d, h, w = L0
+
+        def conv_to(name, mod, src):
+            dst = Slice(self.vol(mod.conv.out_channels, src.spatial), 0, mod.conv.out_channels)
+            self._convbr(name, mod, src, dst)
+            return dst
+
+        if last.spatial[1] == h:
+            feat = last
+        elif last.spatial[1] == h // 2:
+            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, last), L0)
+        elif last.spatial[1] == h // 4:
+            t = self._resample("head.upsample_12", conv_to("last_12", m.last_12, last), (d // 2, h // 2, w // 2))
+            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, t), L0)
+        elif last.spatial[1] == h // 8:
+            t = self._resample("head.upsample_24", conv_to("last_24", m.last_24, last), (d // 4, h // 4, w // 4))
+            t = self._resample("head.upsample_12", conv_to("last_12", m.last_12, t), (d // 2, h // 2, w // 2))
+            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, t), L0)
+        else:
+            raise LeaError("matching net ends on a level the reference head does not handle")
+        self.mat = torch.empty((self.B, 1, d, h, w), dtype=torch.float32, device=self.device)
+        self.nodes.append(_Last3Node(self, "last_3", m.last_3, feat))
+
+    # ---- execution ----------------------------------------------------------------------------------------
+    def forward(self, fx: torch.Tensor, fy: torch.Tensor) -> torch.Tensor:
+        self.ops.cost_volume_planes(fx, fy, self.maxdisp, self.P, out=self.cost)
+        for n in self.nodes:
+            n.forward()
+        return self.ops.disp_head(self.mat, self.maxdisp)
+
+    def backward(self, gdisp: torch.Tensor):
+        self.param_grads = {}
+        for g in self.grads.values():
+            g.t.zero_()
+        for v in self.values:                      # make sure every value buffer has a (zeroed) gradient buffer
+            if id(v) not in self.grads:
+                self.grad_of(v).t.zero_()
+        self.dmat = self.ops.disp_head_bwd(self.mat, gdisp.contiguous().float(), self.maxdisp)
+        for n in reversed(self.nodes):
+            n.backward()
+        dfx, dfy = self.ops.cost_volume_bwd(self.grad_of(self.cost), self.m.initial_fm)
+        return dfx, dfy, self.param_grads
+
+
+class _ConvBRNode(_Node):
+    """Conv3d -> BatchNorm3d(train) -> ReLU (flags per module), output optionally accumulated (state sums)."""
+
+    def __init__(self, plan: TrainPlan, name, mod: ConvBR3d, src: Slice, dst: Slice, accumulate: bool):
+        self.plan, self.name, self.mod, self.src, self.dst, self.accumulate = plan, name, mod, src, dst, accumulate
+        c_out = mod.conv.out_channels
+        if not mod.use_bn:
+            raise LeaError("%s: ConvBR without BN is only supported as the last_3 head" % name)
+        self.x = Slice(plan.vol(c_out, src.spatial), 0, c_out)        # raw conv output, kept for the backward
+        self.dx = None
+
+    def forward(self):
+        plan, mod, ops = self.plan, self.mod, self.plan.ops
+        c = mod.conv.out_channels
+        plan.conv_raw(self.src, mod.conv.weight.detach(), self.x)
+        n = float(self.x.vol.B * _prod(self.x.spatial))
+        sums = ops.channel_reduce(self.x.vol, self.x.c0, c, mode=0)
+        mean = sums[0] / n
+        var = (sums[1] / n - mean * mean).clamp_min(0.0)
+        bn = mod.bn
+        invstd = 1.0 / torch.sqrt(var + bn.eps)
+        gamma, beta = bn.weight.detach().double(), bn.bias.detach().double()
+        self.mean, self.invstd = mean.float().contiguous(), invstd.float().contiguous()
+        self.scale = (gamma * invstd).float().contiguous()
+        self.shift = (beta - mean * gamma * invstd).float().contiguous()
+        ops.affine_relu(self.x.vol, self.x.c0, self.dst.vol, self.dst.c0, c, self.scale, self.shift, mod.relu,
+                        self.accumulate)
+        with torch.no_grad():                       # running statistics (momentum, unbiased variance)
+            mom = bn.momentum if bn.momentum is not None else 0.1
+            bn.running_mean.mul_(1 - mom).add_(mom * mean.to(bn.running_mean.dtype))
+            bn.running_var.mul_(1 - mom).add_(mom * (var * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype))
+            bn.num_batches_tracked += 1
+
+    def backward(self):
+        plan, mod, ops = self.plan, self.mod, self.plan.ops
+        c = mod.conv.out_channels
+        k = mod.conv.weight.shape[2]
+        dy = plan.grad_of(self.dst.vol)
+        n = float(self.x.vol.B * _prod(self.x.spatial))
+        sums = ops.channel_reduce(self.x.vol, self.x.c0, c, mode=1, dy=dy, dy_c0=self.dst.c0, relu=mod.relu,
+                                  scale=self.scale, shift=self.shift, mean=self.mean, invstd=self.invstd)
+        sum_g, sum_gx = sums[0], sums[1]
+        gamma = mod.bn.weight.detach().double()
+        ka = gamma * self.invstd.double()
+        kb = ka * sum_g / n
+        kc = ka * sum_gx / n
+        if mod.bn.weight.requires_grad:
+            plan.add_param_grad(mod.bn.weight, sum_gx.float())
+        if mod.bn.bias.requires_grad:
+            plan.add_param_grad(mod.bn.bias, sum_g.float())
+        if self.dx is None:
+            self.dx = Slice(PlanesVol.empty(self.x.vol.B, c, plan.P, *self.x.spatial, plan.device), 0, c)
+        ops.bn_relu_bwd(self.x.vol, self.x.c0, dy, self.dst.c0, self.dx.vol, 0, c, mod.relu, self.scale, self.shift,
+                        self.mean, self.invstd, ka.float().contiguous(), kb.float().contiguous(),
+                        kc.float().contiguous())
+        w = mod.conv.weight.detach()
+        if mod.conv.weight.requires_grad:
+            dw = torch.zeros_like(w, dtype=torch.float32)
+            ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dx.vol, 0, c, k, dw)
+            plan.add_param_grad(mod.conv.weight, dw)
+        # data gradient: conv with transposed, tap-flipped weights, accumulated into the input's gradient
+        wt = w.flip(2, 3, 4).transpose(0, 1).contiguous()
+        dsrc = plan.grad_of(self.src.vol)
+        plan.conv_raw(self.dx, wt, Slice(dsrc, self.src.c0, self.src.c), accumulate=True)
+
+
+class _Last3Node(_Node):
+    """``last_3``: Conv 32->1, no BN, no ReLU (skip_model_3d.py:132); fp32 output ``mat``."""
+
+    def __init__(self, plan: TrainPlan, name, mod: ConvBR3d, src: Slice):
+        self.plan, self.name, self.mod, self.src = plan, name, mod, src
+        self.dpad = None
+
+    def forward(self):
+        self.plan.conv_raw(self.src, self.mod.conv.weight.detach(), None, dst_f32=self.plan.mat)
+
+    def backward(self):
+        plan, mod, ops = self.plan, self.mod, self.plan.ops
+        w = mod.conv.weight.detach()                                  # (1, C, 3, 3, 3)
+        B, _, D, H, W = plan.mat.shape
+        dm8 = torch.zeros((B, 8, D, H, W), dtype=torch.float32, device=plan.device)
+        dm8[:, 0] = plan.dmat
+        self.dpad = ops.pack(dm8, plan.P, out=self.dpad)
+        if mod.conv.weight.requires_grad:
+            dw = torch.zeros_like(w, dtype=torch.float32)
+            ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dpad, 0, 1, 3, dw)
+            plan.add_param_grad(mod.conv.weight, dw)
+        wt = torch.zeros((w.shape[1], 8, 3, 3, 3), dtype=torch.float32, device=plan.device)
+        wt[:, 0] = w.flip(2, 3, 4)[0]
+        dsrc = plan.grad_of(self.src.vol)
+        plan.conv_raw(Slice(self.dpad, 0, 8), wt, Slice(dsrc, self.src.c0, self.src.c), accumulate=True)
+
+
+class _ResampleNode(_Node):
+    def __init__(self, plan: TrainPlan, name, src: Slice, dst: Slice):
+        self.plan, self.name, self.src, self.dst = plan, name, src, dst
+
+    def forward(self):
+        self.plan.ops.trilinear_ac(self.src.vol, self.src.c0, self.src.c, self.dst.vol, self.dst.c0)
+
+    def backward(self):
+        plan = self.plan
+        plan.ops.trilinear_ac_bwd(plan.grad_of(self.dst.vol), self.dst.c0, plan.grad_of(self.src.vol), self.src.c0,
+                                  self.src.c)
+
+
+class _CopyNode(_Node):
+    """``skip_connect`` (Identity) inside a step sum, or a state copy into the concat buffer."""
+
+    def __init__(self, plan: TrainPlan, name, src: Slice, dst: Slice, accumulate: bool):
+        self.plan, self.name, self.src, self.dst, self.accumulate = plan, name, src, dst, accumulate
+
+    def forward(self):
+        self.plan.ops.affine_relu(self.src.vol, self.src.c0, self.dst.vol, self.dst.c0, self.src.c, None, None, False,
+                                  self.accumulate)
+
+    def backward(self):
+        plan = self.plan
+        plan.ops.affine_relu(plan.grad_of(self.dst.vol), self.dst.c0, plan.grad_of(self.src.vol), self.src.c0,
+                             self.src.c, None, None, False, True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# autograd glue
+# ------------------------------------------------------------------------------------------------------------
+
+def used_parameters(plan: "TrainPlan") -> List[torch.nn.Parameter]:
+    """Parameters that take part in this plan's forward (the reference leaves last_12/last_24/last_3.bn without
+    gradients when the net ends on level 1)."""
+    out: List[torch.nn.Parameter] = []
+    seen = set()
+    for node in plan.nodes:
+        mod = getattr(node, "mod", None)
+        if mod is None:
+            continue
+        cands = [mod.conv.weight] + ([mod.bn.weight, mod.bn.bias] if (mod.use_bn and isinstance(node, _ConvBRNode)) else [])
+        for p in cands:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                out.append(p)
+    return out
+
+
+class _HotPathTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan: TrainPlan, fx, fy, *params):
+        ctx.plan = plan
+        ctx.params = params
+        with torch.no_grad():
+            disp = plan.forward(fx.detach().float().contiguous(), fy.detach().float().contiguous())
+        return disp
+
+    @staticmethod
+    def backward(ctx, gdisp):
+        plan = ctx.plan
+        with torch.no_grad():
+            dfx, dfy, pg = plan.backward(gdisp)
+        grads = []
+        for p in ctx.params:
+            g = pg.get(p)
+            grads.append(None if g is None else g.reshape(p.shape).to(p.dtype))
+        return (None, dfx, dfy) + tuple(grads)
+
+
+_TRAIN_PLANS: Dict[tuple, TrainPlan] = {}
+
+
+def hot_path_train_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optional[Ops] = None) -> torch.Tensor:
+    """Train-mode hot path with autograd support: disparity (B, 3*H3, 3*W3) whose backward fills the gradients of the
+    matching net's parameters and flows into the feature maps."""
+    ops = ops or get_ops()
+    opt = dict(getattr(model, "engine_options", None) or {})
+    planes = int(opt.get("train_planes", opt.get("planes", 2)))
+    conv = opt.get("conv", "tc") if ops.device_build else "simt"
+    B, Cn, H3, W3 = fx.shape
+    D3 = int(model.maxdisp / 3)
+    key = (id(model.matching), str(fx.device), B, D3, H3, W3, planes, conv, id(ops))
+    plan = _TRAIN_PLANS.get(key)
+    if plan is None:
+        _TRAIN_PLANS.clear()                       # one live training plan: buffers are large
+        plan = TrainPlan(model.matching, ops, B, (D3, H3, W3), planes, fx.device, conv, model.maxdisp)
+        _TRAIN_PLANS[key] = plan
+    params = used_parameters(plan)
+    return _HotPathTrainFn.apply(plan, fx, fy, *params)

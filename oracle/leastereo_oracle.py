@@ -82,10 +82,14 @@ def conv_br(sd: Dict[str, torch.Tensor], prefix: str, x: torch.Tensor, *, dims: 
             if batch_stats is not None:
                 n = x.numel() / x.shape[1]
                 batch_stats[prefix] = (mean.clone(), var * (n / max(n - 1.0, 1.0)))
+            # written out so that autograd differentiates through the batch statistics (train-mode BN)
+            shape = [1, -1] + [1] * (x.dim() - 2)
+            x = (x - mean.view(shape)) * torch.rsqrt(var.view(shape) + BN_EPS) * sd[prefix + ".bn.weight"].view(shape) \
+                + sd[prefix + ".bn.bias"].view(shape)
         else:
             mean, var = sd[prefix + ".bn.running_mean"], sd[prefix + ".bn.running_var"]
-        x = F.batch_norm(x, mean.clone(), var.clone(), sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"],
-                         False, 0.0, BN_EPS)
+            x = F.batch_norm(x, mean.clone(), var.clone(), sd[prefix + ".bn.weight"], sd[prefix + ".bn.bias"],
+                             False, 0.0, BN_EPS)
     if relu:
         x = F.relu(x)
     return x
@@ -326,3 +330,36 @@ def tolerance_report(d_test: torch.Tensor, d_ref: torch.Tensor) -> dict:
     frac = float((diff <= 0.1).double().mean())
     return {"frac_within_0p1": frac, "mean_abs": float(diff.mean()), "max_abs": float(diff.max()),
             "ok": bool(frac >= 0.999 and float(diff.mean()) <= 0.01)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# training step (train.py:130-160): train-mode BN, smooth-L1 on valid pixels, autograd gradients
+# --------------------------------------------------------------------------------------------------------
+
+def cost_volume_torch(x: torch.Tensor, y: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    """Differentiable statement of retrain/LEAStereo.py:34-48 (same slice assignments)."""
+    B, C, H, W = x.shape
+    D = int(maxdisp / 3)
+    cost = x.new_zeros((B, 2 * C, D, H, W))
+    for i in range(D):
+        if i >= W:
+            break
+        if i > 0:
+            cost[:, :C, i, :, i:] = x[:, :, :, i:]
+            cost[:, C:, i, :, i:] = y[:, :, :, :-i]
+        else:
+            cost[:, :C, i] = x
+            cost[:, C:, i] = y
+    return cost
+
+
+def hot_path_train(sd, fx: torch.Tensor, fy: torch.Tensor, maxdisp: int, arch=SHIPPED_ARCH, batch_stats=None):
+    """Train-mode hot path on feature maps, differentiable w.r.t. fx, fy and every tensor of ``sd``."""
+    cost = cost_volume_torch(fx, fy, maxdisp)
+    mat = matching_forward(sd, cost, arch, training=True, batch_stats=batch_stats)
+    return disp_head(mat, maxdisp), mat
+
+
+def train_loss(disp: torch.Tensor, target: torch.Tensor, maxdisp: int) -> torch.Tensor:
+    mask = (target < maxdisp) & (target > 0.001)                 # train.py:116-118
+    return F.smooth_l1_loss(disp[mask], target[mask], reduction="mean")   # train.py:157

@@ -31,6 +31,8 @@ extern unsigned char* emu_dyn_smem;
 #define __ldg(p) (*(p))
 #define __expf(x) expf(x)
 static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
+#include <atomic>
+static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
 using std::min;
 using std::max;
 

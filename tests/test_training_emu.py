@@ -1,0 +1,111 @@
+"""CPU tests (-m "not gpu") of the TRAIN-mode hot path (batch-statistics BN forward + full backward) through the CPU
+emulation of the kernels, against the oracle's autograd gradients.  Exact storage (3 planes) + fp32 SIMT convs, so the
+tolerances are tight."""
+import pytest
+import torch
+
+import kernel_checks as K
+from conftest import load_golden, golden_state_dict, seeded_model
+from oracle import leastereo_oracle as O
+from test_emu_kernels import emu_ops  # noqa: F401  (fixture)
+
+DEV = torch.device("cpu")
+
+
+def _rel(a, b):
+    return float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30)
+
+
+def check_train_step(ops, device, planes=3, conv="simt", tol=2e-3):
+    g = load_golden("cal_b2_24x48_d24")
+    maxdisp = int(g["maxdisp"])
+    model = seeded_model(maxdisp)
+    model.load_state_dict(golden_state_dict(g, model))
+    model = model.to(device).train()
+    model.engine_options = {"planes": planes, "train_planes": planes, "conv": conv}
+    fx = torch.from_numpy(g["fx"]).to(device).requires_grad_(True)
+    fy = torch.from_numpy(g["fy"]).to(device).requires_grad_(True)
+    gen = torch.Generator().manual_seed(3)
+    target = (torch.rand(fx.shape[0], 24, 48, generator=gen) * maxdisp * 0.5).to(device)
+
+    from leastereo_b200.training import hot_path_train_forward
+    sd_before = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    disp = hot_path_train_forward(model, fx, fy, ops=ops)
+    loss = O.train_loss(disp, target, maxdisp)
+    loss.backward()
+
+    # ---- oracle: same weights as leaves, autograd
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd_before.items()}
+    ofx = torch.from_numpy(g["fx"]).requires_grad_(True)
+    ofy = torch.from_numpy(g["fy"]).requires_grad_(True)
+    stats = {}
+    odisp, omat = O.hot_path_train(sd, ofx, ofy, maxdisp, batch_stats=stats)
+    oloss = O.train_loss(odisp, target.cpu(), maxdisp)
+    oloss.backward()
+
+    assert _rel(disp.detach().cpu(), odisp.detach()) <= tol, "train-mode forward"
+    assert abs(float(loss) - float(oloss)) <= tol * max(1.0, abs(float(oloss)))
+    assert _rel(fx.grad.cpu(), ofx.grad) <= tol * 5, ("dfx", _rel(fx.grad.cpu(), ofx.grad))
+    assert _rel(fy.grad.cpu(), ofy.grad) <= tol * 5, ("dfy", _rel(fy.grad.cpu(), ofy.grad))
+    worst = ("", 0.0)
+    n_checked = 0
+    for name, p in model.matching.named_parameters():
+        og = sd["matching." + name].grad
+        if og is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
+            continue
+        assert p.grad is not None, "missing gradient for " + name
+        scale = max(float(og.abs().max()), 1e-12)
+        err = float((p.grad.cpu() - og).abs().max()) / scale
+        if err > worst[1]:
+            worst = (name, err)
+        n_checked += 1
+    assert n_checked > 250
+    assert worst[1] <= tol * 10, worst
+    # running statistics follow momentum 0.1 with the unbiased batch variance
+    for prefix in ("matching.stem0", "matching.cells.5._ops.3", "matching.last_6"):
+        mean, var_unbiased = stats[prefix]
+        rm = 0.9 * sd_before[prefix + ".bn.running_mean"] + 0.1 * mean.detach()
+        rv = 0.9 * sd_before[prefix + ".bn.running_var"] + 0.1 * var_unbiased.detach()
+        assert _rel(model.state_dict()[prefix + ".bn.running_mean"].cpu(), rm) <= 1e-3
+        assert _rel(model.state_dict()[prefix + ".bn.running_var"].cpu(), rv) <= 1e-3
+        assert int(model.state_dict()[prefix + ".bn.num_batches_tracked"]) == int(sd_before[prefix + ".bn.num_batches_tracked"]) + 1
+    return worst
+
+
+def test_train_step_matches_autograd(emu_ops):
+    worst = check_train_step(emu_ops, DEV)
+    print("worst parameter-gradient relative error:", worst)
+
+
+def test_backward_kernels_individually(emu_ops):
+    """Trilinear backward and cost-volume backward against autograd on random data."""
+    import torch.nn.functional as F
+    from leastereo_b200.kernels import PlanesVol
+    ops = emu_ops
+    for src_sp, dst_sp in [((4, 3, 6), (8, 6, 12)), ((8, 6, 12), (4, 3, 6)), ((3, 5, 4), (5, 9, 7)), ((2, 2, 2), (1, 1, 1))]:
+        x = torch.randn(1, 8, *src_sp, requires_grad=True)
+        y = F.interpolate(x, dst_sp, mode="trilinear", align_corners=True)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        ddst = ops.pack(gy, 3)
+        dsrc = PlanesVol.empty(1, 8, 3, *src_sp, DEV)
+        dsrc.t.zero_()
+        ops.trilinear_ac_bwd(ddst, 0, dsrc, 0, 8)
+        assert _rel(ops.unpack(dsrc), x.grad) <= 1e-5, (src_sp, dst_sp)
+    fx = torch.randn(2, 8, 5, 12, requires_grad=True)
+    fy = torch.randn(2, 8, 5, 12, requires_grad=True)
+    cost = O.cost_volume_torch(fx, fy, 15)
+    gc = torch.randn_like(cost)
+    cost.backward(gc)
+    dx, dy = ops.cost_volume_bwd(ops.pack(gc, 3), 8)
+    assert _rel(dx, fx.grad) <= 1e-5 and _rel(dy, fy.grad) <= 1e-5
+    # disparity head backward
+    mat = (torch.randn(1, 1, 8, 5, 7) * 2).requires_grad_(True)
+    for maxdisp in (24, 25):
+        mat.grad = None
+        d = O.disp_head(mat, maxdisp)
+        go = torch.randn_like(d)
+        d.backward(go)
+        dm = ops.disp_head_bwd(mat.detach(), go, maxdisp)
+        assert _rel(dm, mat.grad[:, 0]) <= 2e-4, maxdisp
