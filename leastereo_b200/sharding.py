@@ -50,3 +50,36 @@ def sharded_inference(forward_fn, left: torch.Tensor, right: torch.Tensor, rank:
         h3, w3 = -(-left.shape[2] // 3), -(-left.shape[3] // 3)
         out = torch.zeros((0, 3 * h3, 3 * w3), dtype=torch.float32, device=left.device)
     return gather_disparities(out, left.shape[0], rank, world_size, group)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# training: batch-sharded data parallelism (train.py:71 uses nn.DataParallel; here one process per GPU)
+# ----------------------------------------------------------------------------------------------------------------
+
+def allreduce_gradients(parameters: Sequence[torch.nn.Parameter], world_size: int, group=None) -> int:
+    """Averages the gradients of `parameters` across ranks with ONE all-reduce over a flat fp32 bucket
+    (1.72 M elements = 6.9 MB for LEAStereo: latency-bound, so a single bucket beats per-tensor calls; over NVLink 5 /
+    NVSwitch NCCL reduces it in a few tens of microseconds).  Parameters without a gradient on this rank (the
+    reference's unused heads never get one) contribute zeros, so every rank reduces the same layout.
+    BatchNorm statistics stay per replica, as under nn.DataParallel.  Returns the number of elements reduced."""
+    import torch.distributed as dist
+    params = [p for p in parameters if p.requires_grad]
+    if world_size <= 1 or not params:
+        return 0
+    device = params[0].device
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=device)
+    off = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is not None:
+            flat[off: off + n].copy_(p.grad.reshape(-1))
+        off += n
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world_size)
+    off = 0
+    for p in params:
+        n = p.numel()
+        if p.grad is not None:
+            p.grad.copy_(flat[off: off + n].view_as(p.grad))
+        off += n
+    return int(flat.numel())

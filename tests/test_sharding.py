@@ -62,3 +62,31 @@ def test_sharded_inference_matches_single_process(tmp_path, world, n_pairs):
     # (that noise floor is max 9e-3 px, mean 4e-4 px on this network)
     diff = (res["sharded"] - res["full"]).abs()
     assert float(diff.max()) <= 0.05 and float(diff.mean()) <= 1e-3
+
+
+def _grad_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from leastereo_b200.sharding import allreduce_gradients
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.zeros(3, 4)), torch.nn.Parameter(torch.zeros(5)),
+              torch.nn.Parameter(torch.zeros(2, 2)), torch.nn.Parameter(torch.zeros(7), requires_grad=False)]
+    params[0].grad = torch.full((3, 4), float(rank + 1))
+    params[1].grad = torch.arange(5.0) * (rank + 1)
+    # params[2] never receives a gradient (like the reference's unused heads); params[3] is frozen
+    n = allreduce_gradients(params, world)
+    if rank == 0:
+        torch.save({"n": n, "g0": params[0].grad, "g1": params[1].grad, "g2": params[2].grad}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_flat_bucket(tmp_path):
+    out_path = str(tmp_path / "g.pt")
+    mp.spawn(_grad_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    res = torch.load(out_path)
+    assert res["n"] == 12 + 5 + 4
+    assert torch.allclose(res["g0"], torch.full((3, 4), 1.5))
+    assert torch.allclose(res["g1"], torch.arange(5.0) * 1.5)
+    assert res["g2"] is None
