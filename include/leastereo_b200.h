@@ -115,6 +115,14 @@ int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D3, int32_t 
 int lea_disparity_regression(const float* p, float* out, int32_t B, int32_t maxdisp, int32_t H, int32_t W,
                              void* stream);
 
+/* ---- feature-net producer (retrain/new_model_2d.py:93-94,130-131) ---------------------------- */
+/* stem0 (3 -> c_mid, 3x3, stride 1) + BN + ReLU fused with stem1 (c_mid -> c_out, 3x3, stride 3) + BN + ReLU:
+ * img (B, 3, H, W) fp32 -> channel slice of a depth-1 planes volume at 1/3 resolution.  w0 (c_mid, 3, 3, 3),
+ * w1 (c_out, c_mid, 3, 3) in PyTorch layout; scale/shift = eval-mode BatchNorm folded by the host. */
+int lea_feature_stem(const float* img, int32_t B, int32_t H, int32_t W, const float* w0, const float* scale0,
+                     const float* shift0, int32_t c_mid, const float* w1, const float* scale1, const float* shift1,
+                     int32_t c_out, const lea_vol* dst, int32_t dst_c0, void* stream);
+
 /* ---- training side (what the reference gets from autograd, train.py:156-160) --------------------- */
 /* Per-channel reductions over a channel slice, written as `chunks` partial rows partial[(chunk*2+which)*c + ch]
  * (the caller adds the chunks).  mode 0: sum x, sum x^2 (BatchNorm3d batch statistics, operations_3d.py:38,44).

@@ -146,3 +146,20 @@ extern "C" int lea_disparity_regression(const float* p, float* out, int32_t B, i
                p, out, maxdisp, H * W);
     return LEA_POST_LAUNCH();
 }
+
+
+extern "C" int lea_feature_stem(const float* img, int32_t B, int32_t H, int32_t W,
+                                const float* w0, const float* scale0, const float* shift0, int32_t c_mid,
+                                const float* w1, const float* scale1, const float* shift1, int32_t c_out,
+                                const lea_vol* dst, int32_t dst_c0, void* stream) {
+    LEA_CHECK(img && w0 && scale0 && shift0 && w1 && scale1 && shift1, "feature_stem: null pointer");
+    if (lea_check_vol(dst, "feature_stem") || lea_check_slice(dst, dst_c0, c_out, "feature_stem")) return 1;
+    LEA_CHECK(c_mid >= 1 && c_mid <= LEA_FS_MAXMID && c_out <= LEA_FS_MAXOUT, "feature_stem: supports c_mid <= %d, c_out <= %d",
+              LEA_FS_MAXMID, LEA_FS_MAXOUT);
+    LEA_CHECK(dst->B == B && dst->D == 1 && dst->H == (H - 1) / 3 + 1 && dst->W == (W - 1) / 3 + 1,
+              "feature_stem: output volume must be (B, c, 1, ceil(H/3), ceil(W/3))");
+    LEA_CHECK(dst->H <= 65535 && B <= 65535, "feature_stem: grid too large");
+    LEA_LAUNCH(lea_feature_stem_kernel, dim3((dst->W + 127) / 128, dst->H, B), dim3(128), 0, stream,
+               img, H, W, w0, scale0, shift0, c_mid, w1, scale1, shift1, c_out, *dst, dst_c0);
+    return LEA_POST_LAUNCH();
+}

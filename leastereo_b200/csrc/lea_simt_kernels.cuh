@@ -484,3 +484,100 @@ lea_disparity_regression_kernel(const float* __restrict__ p, float* __restrict__
     for (int d = 0; d < maxdisp; ++d) acc += __ldg(pb + (int64_t)d * HW) * (float)d;
     out[(int64_t)b * HW + q] = acc;
 }
+
+
+// =========================================================================================================
+// F1  fused feature stems (retrain/new_model_2d.py:93-94, 130-131): stem0 = ConvBR2d(3 -> c_mid, 3x3, s1, p1) on the
+//     full-resolution image, stem1 = ConvBR2d(c_mid -> c_out, 3x3, stride 3, p1).  stem1's 3x3 windows do not overlap
+//     (stride 3 = kernel 3), so one thread per stem1 output pixel recomputes exactly the 9 stem0 pixels it needs from
+//     a 5x5x3 image patch; the c_mid x H x W stem0 activation (61 MB per KITTI image) is never written.
+//     Output: 1/3-resolution planes volume (depth 1).  fp32 FMA, eval-mode BN folded to scale/shift by the host.
+// =========================================================================================================
+#define LEA_FS_MAXMID 16
+#define LEA_FS_MAXOUT 32
+__global__ void __launch_bounds__(128)
+lea_feature_stem_kernel(const float* __restrict__ img, int H, int W,
+                        const float* __restrict__ w0, const float* __restrict__ sc0, const float* __restrict__ sh0,
+                        int c_mid, const float* __restrict__ w1, const float* __restrict__ sc1,
+                        const float* __restrict__ sh1, int c_out, lea_vol dst, int dst_c0) {
+    __shared__ float w0s[27 * LEA_FS_MAXMID];                    // [c*9 + a*3 + b][m]
+    __shared__ float w1s[9 * LEA_FS_MAXMID * LEA_FS_MAXOUT];     // [(i*3+j)*c_mid + m][o]
+    __shared__ float bn0[2 * LEA_FS_MAXMID], bn1[2 * LEA_FS_MAXOUT];
+    const int tid = threadIdx.x;
+    for (int e = tid; e < 27 * LEA_FS_MAXMID; e += 128) {
+        const int t = e / LEA_FS_MAXMID, m = e % LEA_FS_MAXMID;
+        w0s[e] = m < c_mid ? __ldg(w0 + m * 27 + t) : 0.0f;
+    }
+    for (int e = tid; e < 9 * LEA_FS_MAXMID * LEA_FS_MAXOUT; e += 128) {
+        const int o = e % LEA_FS_MAXOUT, r = e / LEA_FS_MAXOUT;
+        const int m = r % LEA_FS_MAXMID, pos = r / LEA_FS_MAXMID;
+        w1s[e] = (o < c_out && m < c_mid) ? __ldg(w1 + ((int64_t)o * c_mid + m) * 9 + pos) : 0.0f;
+    }
+    if (tid < LEA_FS_MAXMID) { bn0[tid] = tid < c_mid ? sc0[tid] : 0.0f; bn0[LEA_FS_MAXMID + tid] = tid < c_mid ? sh0[tid] : 0.0f; }
+    if (tid < LEA_FS_MAXOUT) { bn1[tid] = tid < c_out ? sc1[tid] : 0.0f; bn1[LEA_FS_MAXOUT + tid] = tid < c_out ? sh1[tid] : 0.0f; }
+    __syncthreads();
+    const int w3 = blockIdx.x * 128 + tid;
+    const int h3 = blockIdx.y, b = blockIdx.z;
+    if (w3 >= dst.W) return;
+    // 5x5x3 image patch around (3*h3, 3*w3), zero outside the image
+    float patch[3][5][5];
+    const float* __restrict__ ib = img + (int64_t)b * 3 * H * W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int e = 0; e < 5; ++e) {
+                const int y = 3 * h3 - 2 + a, x = 3 * w3 - 2 + e;
+                patch[c][a][e] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(ib + ((int64_t)c * H + y) * W + x) : 0.0f;
+            }
+    float acc[LEA_FS_MAXOUT];
+#pragma unroll
+    for (int o = 0; o < LEA_FS_MAXOUT; ++o) acc[o] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int py = 3 * h3 - 1 + i, px = 3 * w3 - 1 + j;          // stem0 pixel feeding tap (i, j) of stem1
+            if (py < 0 || py >= H || px < 0 || px >= W) continue;        // stem1's zero padding
+            float mid[LEA_FS_MAXMID];
+#pragma unroll
+            for (int m = 0; m < LEA_FS_MAXMID; ++m) mid[m] = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int e = 0; e < 3; ++e) {
+                        const float v = patch[c][i + a][j + e];
+                        const float4* wr = reinterpret_cast<const float4*>(w0s + (c * 9 + a * 3 + e) * LEA_FS_MAXMID);
+#pragma unroll
+                        for (int m4 = 0; m4 < LEA_FS_MAXMID / 4; ++m4) {
+                            const float4 q = wr[m4];
+                            mid[m4 * 4 + 0] += v * q.x; mid[m4 * 4 + 1] += v * q.y;
+                            mid[m4 * 4 + 2] += v * q.z; mid[m4 * 4 + 3] += v * q.w;
+                        }
+                    }
+#pragma unroll
+            for (int m = 0; m < LEA_FS_MAXMID; ++m) {
+                float t = mid[m] * bn0[m] + bn0[LEA_FS_MAXMID + m];
+                t = t > 0.0f ? t : 0.0f;
+                const float4* wr = reinterpret_cast<const float4*>(w1s + ((i * 3 + j) * LEA_FS_MAXMID + m) * LEA_FS_MAXOUT);
+#pragma unroll
+                for (int o4 = 0; o4 < LEA_FS_MAXOUT / 4; ++o4) {
+                    const float4 q = wr[o4];
+                    acc[o4 * 4 + 0] += t * q.x; acc[o4 * 4 + 1] += t * q.y;
+                    acc[o4 * 4 + 2] += t * q.z; acc[o4 * 4 + 3] += t * q.w;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < LEA_FS_MAXOUT; ++o) {
+        const float t = acc[o] * bn1[o] + bn1[LEA_FS_MAXOUT + o];
+        acc[o] = t > 0.0f ? t : 0.0f;
+    }
+#pragma unroll
+    for (int cb = 0; cb < LEA_FS_MAXOUT / 8; ++cb)
+        if (cb * 8 < c_out) lea_vol_store8(dst, b, (dst_c0 >> 3) + cb, 0, h3, w3, acc + cb * 8);
+}

@@ -22,7 +22,10 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .kernels import LeaError, Ops, PlanesVol, get_ops, lea_tc_opts
-from .modules import ConvBR3d, Identity3d, newMatching
+from .modules import ConvBR2d, ConvBR3d, Identity2d, Identity3d, newFeature, newMatching
+
+_IDENTITY = (Identity2d, Identity3d)
+_CONVBR = (ConvBR2d, ConvBR3d)
 from .structure import scale_dimension
 
 _LOCK = threading.Lock()
@@ -81,8 +84,9 @@ class MatchingPlan:
         self._bn_channels = 0
         self._eye: Dict[int, torch.Tensor] = {}
         self._resampled: Dict[tuple, Slice] = {}
+        self.flat2d = False
         self._param_key = None
-        total_bn = sum(mod.conv.out_channels for mod in matching.modules() if isinstance(mod, ConvBR3d))
+        total_bn = sum(mod.conv.out_channels for mod in matching.modules() if isinstance(mod, _CONVBR))
         self.bn_scale = torch.ones(total_bn, dtype=torch.float32, device=self.device)
         self.bn_shift = torch.zeros(total_bn, dtype=torch.float32, device=self.device)
         self._build()
@@ -145,6 +149,7 @@ class MatchingPlan:
             mods = tuple(mods) if isinstance(mods, (list, tuple)) else (mods,)
             w0 = mods[0].conv.weight
             c_in, k = w0.shape[1], w0.shape[2]
+            is2d = w0.dim() == 4                   # 2-D conv run as a k^3 conv on a depth-1 volume (zero kd != 1 taps)
             c_out = sum(m.conv.out_channels for m in mods)
             relu = mods[0].relu and not raw
             use_bn = mods[0].use_bn and not raw
@@ -154,10 +159,10 @@ class MatchingPlan:
             scale = shift = None
             if use_bn:
                 scale, shift = self._bn_slices(mods)
-            if len(mods) == 1:
+            if len(mods) == 1 and not is2d:
                 weight = w0.detach()
             else:
-                wcat = torch.empty((c_out, c_in, k, k, k), dtype=torch.float32, device=self.device)
+                wcat = torch.zeros((c_out, c_in, k, k, k), dtype=torch.float32, device=self.device)
                 weight = wcat
         if src.c != c_in:
             raise LeaError("%s: input has %d channels, conv expects %d" % (name, src.c, c_in))
@@ -214,16 +219,19 @@ class MatchingPlan:
             r = self._resample(name + ".resample", src, spatial)
             self._emit_conv(name, mod, r, dst)
 
-    def _cell(self, i: int, s0: Slice, s1: Slice, out: Optional[Slice] = None) -> Tuple[Slice, Slice]:
-        cell = self.m.cells[i]
+    def _cell(self, i: int, s0: Slice, s1: Slice, out: Optional[Slice] = None, cell=None, bm=None,
+              prefix: str = "") -> Tuple[Slice, Slice]:
+        cell = cell if cell is not None else self.m.cells[i]
         spec = cell.spec
-        name = "cells.%d" % i
+        name = "%scells.%d" % (prefix, i)
         prev_input = s1
         c_out = spec.c_out
         sp = s1.spatial
         if spec.downup_sample != 0:
             sp = tuple(scale_dimension(n, spec.scale) for n in s1.spatial)
-        bm = self.m._block_multiplier
+            if self.flat2d:
+                sp = (1,) + sp[1:]             # a 2-D net runs as depth-1 volumes: only H and W are resampled
+        bm = bm if bm is not None else self.m._block_multiplier
         n_states = 2 + len(spec.steps)
         first_in_concat = n_states - bm
         if first_in_concat < 0:
@@ -275,14 +283,14 @@ class MatchingPlan:
                 tgt, opi = todo[0]
                 op = cell._ops[opi]
                 group = [(tgt, opi)]
-                if self.fuse and not isinstance(op, Identity3d):
+                if self.fuse and not isinstance(op, _IDENTITY):
                     # extend with siblings: consecutive target slots, same first-writer status, all convs
                     for (t2, o2) in todo[1:]:
                         pt, _ = group[-1]
                         same_buf = (state_slot(t2).vol is state_slot(pt).vol and
                                     state_slot(t2).c0 == state_slot(pt).c0 + c_out)
                         if (t2 == pt + 1 and same_buf and written.get(t2, False) == written.get(tgt, False)
-                                and not isinstance(cell._ops[o2], Identity3d)
+                                and not isinstance(cell._ops[o2], _IDENTITY)
                                 and (len(group) + 1) * c_out <= self._max_batched_c_out()):
                             group.append((t2, o2))
                         else:
@@ -291,7 +299,7 @@ class MatchingPlan:
                 first = state_slot(group[0][0])
                 dst = Slice(first.vol, first.c0, c_out * len(group))
                 res = written.get(tgt, False)
-                if isinstance(op, Identity3d):
+                if isinstance(op, _IDENTITY):
                     self._emit_conv("%s._ops.%d(skip)" % (name, opi), None, state_slot(j), dst, res=res,
                                     identity_c=c_out)
                 else:
@@ -310,13 +318,16 @@ class MatchingPlan:
         fm = m.initial_fm
         L0 = self.spatial
         v0, v1 = self._vol(fm, L0), self._vol(fm, L0)
-        self.cost = self.fxp = self.fyp = self.cv_maps = None
+        self.cost = self.fxp = self.fyp = self.fxy = self.cv_maps = None
         can_fuse_cv = (self.fuse_cv and self.conv_mode == "tc" and fm % 16 == 0 and L0[0] <= L0[2] and
                        self.ops.tc_weight_image_bytes(2 * fm, fm, 3, self.P) > 0)
         if can_fuse_cv:
             # retrain/LEAStereo.py:34-48 inside stem0's TMA loader: the 2C x D3 x H3 x W3 volume is never materialised
-            self.fxp = PlanesVol.empty(self.B, fm, self.P, 1, L0[1], L0[2], self.device)
-            self.fyp = PlanesVol.empty(self.B, fm, self.P, 1, L0[1], L0[2], self.device)
+            # one allocation for both feature maps (left block, right block) so that the native feature net can
+            # write its batched (left+right) output straight into the loader's operands
+            self.fxy = PlanesVol.empty(2 * self.B, fm, self.P, 1, L0[1], L0[2], self.device)
+            self.fxp = PlanesVol(self.fxy.t[: self.B])
+            self.fyp = PlanesVol(self.fxy.t[self.B:])
             self.cv_maps = self.ops.build_fused_cv_maps(self.fxp, self.fyp, L0[0])
             self._emit_conv("stem0(fused cost volume)", m.stem0, Slice(self.fxp, 0, 2 * fm), Slice(v0, 0, fm),
                             fused_cv=True)
@@ -415,7 +426,11 @@ class MatchingPlan:
                         if not (w.is_contiguous() and w.dtype == torch.float32 and w.device == self.device):
                             raise LeaError("%s: weights must be contiguous fp32 on %s" % (s.name, self.device))
                     if s.wcat is not None:
-                        torch.cat([mod.conv.weight.detach() for mod in s.mods], dim=0, out=s.wcat)
+                        ws = [mod.conv.weight.detach() for mod in s.mods]
+                        if ws[0].dim() == 4:       # 2-D weights go into the middle depth slice of the k^3 kernel
+                            s.wcat[:, :, s.wcat.shape[2] // 2].copy_(torch.cat(ws, dim=0))
+                        else:
+                            torch.cat(ws, dim=0, out=s.wcat)
                     else:
                         s.weight = s.mods[0].conv.weight.detach()
                 if s.kind == "conv_tc":
@@ -431,6 +446,12 @@ class MatchingPlan:
             self.ops.conv3d_simt(s.p, s.weight, s.ref)
         elif s.kind == "conv_tc":
             self.ops.conv3d_tc(s.p, s.image, s.opts, s.ref)
+        elif s.kind == "repack":
+            src, dst, c = s.rs
+            self.ops.affine_relu(src, 0, dst, 0, c, None, None, False, False)
+        elif s.kind == "feature_stem":
+            img, w0, sc0, sh0, w1, sc1, sh1, dst = s.rs
+            self.ops.feature_stem(img, w0, sc0, sh0, w1, sc1, sh1, dst, 0)
         else:
             raise LeaError("unknown step " + s.kind)
 
@@ -440,10 +461,86 @@ class MatchingPlan:
             self.refresh_params()
         for s in self.steps:
             self.run_step(s)
-        return self.mat
+        return getattr(self, "mat", None)
 
     def conv_flops(self) -> float:
         return sum(s.flops for s in self.steps)
+
+
+class FeaturePlan(MatchingPlan):
+    """Launch list of the 2D feature net (``retrain/new_model_2d.py:129-165``) for a batch of left+right images.
+
+    SURVEY.md §8(f) row 1.  The net runs on the same kernels as the 3D net: activations are depth-1 planes volumes,
+    a 3x3 conv is a 3x3x3 conv whose kd != 1 taps are zero (only the kd = 1 MMA is issued at depth 1, so nothing is
+    wasted), bilinear align_corners=True resampling is the trilinear kernel at depth 1.  stem0+stem1 (the only
+    full-resolution / strided layers) are one fused CUDA-core kernel.  The last 1x1 conv writes directly into the
+    operand buffer of the fused cost-volume loader (left block | right block)."""
+
+    def __init__(self, feature: newFeature, ops: Ops, B2: int, H: int, W: int, planes: int, device, out: PlanesVol,
+                 mma_terms: int = 0, fuse: bool = True, tc_knobs: Optional[dict] = None, conv_mode: str = "tc"):
+        self.img_hw = (int(H), int(W))
+        self.out = out
+        h3, w3 = (H - 1) // 3 + 1, (W - 1) // 3 + 1
+        super().__init__(feature, ops, B2, (1, h3, w3), planes, device, conv_mode, mma_terms, fuse, tc_knobs)
+
+    def _build(self):
+        f = self.m
+        self.flat2d = True
+        L0 = self.spatial
+        H, W = self.img_hw
+        fm = f._filter_multiplier * f._block_multiplier
+        if f.stem1.conv.stride[0] != 3 or f.stem0.conv.out_channels > 16 or fm > 32 or \
+                self.out.spatial != L0 or self.out.C != fm or self.out.B != self.B:
+            raise LeaError("native feature net: unsupported stem geometry")
+        self.img = torch.empty((self.B, 3, H, W), dtype=torch.float32, device=self.device)
+        stem1 = Slice(self._vol(fm, L0), 0, fm)
+        sc0, sh0 = self._bn_slices([f.stem0])
+        sc1, sh1 = self._bn_slices([f.stem1])
+        flops = 2.0 * self.B * (H * W * f.stem0.conv.out_channels * 27 + _prod(L0) * fm * f.stem0.conv.out_channels * 9)
+        self.steps.append(Step("feature_stem", "feature.stem0+stem1", flops, 4.0 * self.B * 3 * H * W,
+                               mods=(f.stem0, f.stem1), rs=(self.img, None, sc0, sh0, None, sc1, sh1, stem1.vol)))
+        stem2 = Slice(self._vol(fm, L0), 0, fm)
+        self._emit_conv("feature.stem2", f.stem2, stem1, stem2)
+        out = (stem1, stem2)
+        for i, cell in enumerate(f.cells):
+            out = self._cell(i, out[0], out[1], cell=cell, bm=f._block_multiplier, prefix="feature.")
+        last = out[1]
+        _, h, w = L0
+
+        def conv_to(name, mod, src: Slice) -> Slice:
+            dst = Slice(self._vol(mod.conv.out_channels, src.spatial), 0, mod.conv.out_channels)
+            self._emit_conv(name, mod, src, dst)
+            return dst
+
+        if last.spatial[1] == h:
+            feat = last
+        elif last.spatial[1] == h // 2:
+            feat = self._resample("feature.upsample_6", conv_to("feature.last_6", f.last_6, last), L0)
+        elif last.spatial[1] == h // 4:
+            t = self._resample("feature.upsample_12", conv_to("feature.last_12", f.last_12, last), (1, h // 2, w // 2))
+            feat = self._resample("feature.upsample_6", conv_to("feature.last_6", f.last_6, t), L0)
+        else:
+            raise LeaError("feature net ends on a level the native path does not handle")
+        if self.out.P == self.P:
+            self._emit_conv("feature.last_3", f.last_3, feat, Slice(self.out, 0, fm))
+        else:
+            # the feature net runs with its own plane count (3 = exact storage / bf16x6: it is tiny, and its rounding
+            # errors are amplified by the whole matching net); convert to the matching net's operand format at the end
+            tmp = Slice(self._vol(fm, L0), 0, fm)
+            self._emit_conv("feature.last_3", f.last_3, feat, tmp)
+            self.steps.append(Step("repack", "feature.to_operand_planes", 0.0,
+                                   2.0 * self.B * _prod(L0) * fm * (self.P + self.out.P), rs=(tmp.vol, self.out, fm)))
+
+    def refresh_params(self, force: bool = False):
+        key = self._current_param_key()
+        if not force and key == self._param_key:
+            return
+        super().refresh_params(force=True)
+        for s in self.steps:
+            if s.kind == "feature_stem":
+                img, _, sc0, sh0, _, sc1, sh1, dst = s.rs
+                s.rs = (img, s.mods[0].conv.weight.detach().contiguous(), sc0, sh0,
+                        s.mods[1].conv.weight.detach().contiguous(), sc1, sh1, dst)
 
 
 def _prod(t):
@@ -457,7 +554,8 @@ def _prod(t):
 # module-level entry points used by the nn.Module boundary
 # --------------------------------------------------------------------------------------------------------
 
-DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fuse_cv": True, "assume_frozen": False}
+DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fuse_cv": True, "feature": "native",
+                   "assume_frozen": False}
 
 
 def _options(model) -> dict:
@@ -522,6 +620,42 @@ def hot_path_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optional[Op
         ops.pack(fy, opt["planes"], out=plan.fyp)
     else:
         ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"], out=plan.cost)
+    mat = plan.run(check_params=not opt["assume_frozen"])
+    return ops.disp_head(mat, model.maxdisp)
+
+
+def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[Ops] = None) -> Optional[torch.Tensor]:
+    """Feature net + hot path entirely on the native kernels (eval mode).  Returns None when the configuration is not
+    taken by the native feature path (the caller then runs the stock-PyTorch feature net + ``hot_path_forward``)."""
+    opt = _options(model)
+    if model.training or opt.get("feature", "native") != "native" or opt["conv"] != "tc" or left.shape != right.shape:
+        return None
+    ops = ops or get_ops()
+    B, _, H, W = left.shape
+    D3 = int(model.maxdisp / 3)
+    h3, w3 = (H - 1) // 3 + 1, (W - 1) // 3 + 1
+    if D3 < 1:
+        raise LeaError("maxdisp %r gives an empty cost volume" % (model.maxdisp,))
+    plan = get_plan(model.matching, B, (D3, h3, w3), left.device, opt, ops)
+    if plan.fxy is None:
+        return None
+    key = ("feature", str(left.device), B, H, W, int(opt.get("feature_planes", 3)), opt["mma_terms"], id(ops), id(plan))
+    with _LOCK:
+        plans = _plans(model.feature)
+        fplan = plans.get(key)
+        if fplan is None:
+            try:
+                fplan = FeaturePlan(model.feature, ops, 2 * B, H, W, int(opt.get("feature_planes", 3)), left.device, plan.fxy,
+                                    opt["mma_terms"], bool(opt.get("fuse", True)),
+                                    {"accum_split": opt.get("accum_split", 0), "acc_sets": opt.get("acc_sets", 0)})
+            except LeaError:
+                fplan = False
+            plans[key] = fplan
+    if fplan is False:
+        return None
+    fplan.img[:B].copy_(left.detach().float())
+    fplan.img[B:].copy_(right.detach().float())
+    fplan.run(check_params=not opt["assume_frozen"])
     mat = plan.run(check_params=not opt["assume_frozen"])
     return ops.disp_head(mat, model.maxdisp)
 

@@ -56,6 +56,7 @@ SYMBOLS = {
     "lea_build_fused_cv_maps": (C.c_int, [_VOLP, _VOLP, _i32, _vp, _vp]),
     "lea_disp_head": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "lea_disparity_regression": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "lea_feature_stem": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _VOLP, _i32, _vp]),
     "lea_channel_reduce": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "lea_affine_relu": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp, _vp, _i32, _i32, _vp]),
     "lea_bn_relu_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -291,6 +292,16 @@ class Ops:
             self._check(self.lib.lea_disp_head(mat.data_ptr(), out.data_ptr(), B, D3, H3, W3, int(maxdisp),
                                                self._stream(mat)))
         return out
+
+    def feature_stem(self, img: torch.Tensor, w0, sc0, sh0, w1, sc1, sh1, dst: PlanesVol, dst_c0: int = 0):
+        img = self._f32(img)
+        self._dev(img, dst.t)
+        B, _, H, W = img.shape
+        d = dst.struct()
+        with torch.cuda.device(img.device) if img.is_cuda else _null():
+            self._check(self.lib.lea_feature_stem(img.data_ptr(), B, H, W, w0.data_ptr(), sc0.data_ptr(), sh0.data_ptr(),
+                                                  w0.shape[0], w1.data_ptr(), sc1.data_ptr(), sh1.data_ptr(), w1.shape[0],
+                                                  C.byref(d), dst_c0, self._stream(img)))
 
     # ---- training side ------------------------------------------------------------------------------------
     def _dev_ctx(self, t: torch.Tensor):

@@ -73,7 +73,11 @@ class LEAStereo(nn.Module):
             return self.feature(x), self.feature(y)
 
     def forward(self, x, y):
-        from .engine import hot_path_forward
+        from .engine import full_forward, hot_path_forward
+        if not self.training and x.is_cuda:
+            out = full_forward(self, x, y)          # native feature net + hot path (engine option feature="native")
+            if out is not None:
+                return out
         fx, fy = self.extract_features(x, y)
         return hot_path_forward(self, fx, fy)
 

@@ -227,3 +227,28 @@ def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False)
         assert err <= tol, (i, planes, mma_terms, err, tol)
         worst = max(worst, err)
     return worst
+
+
+# ---------------------------------------------------------------------------------------------------------
+# native feature net (2D net on depth-1 planes volumes + fused stems) against the stock-PyTorch module
+# ---------------------------------------------------------------------------------------------------------
+def check_feature_plan(ops, device, name="cal_46x94_d50", planes=3, conv="simt", tol=2e-4):
+    g = load_golden(name)
+    model = seeded_model(int(g["maxdisp"]))
+    model.load_state_dict(golden_state_dict(g, model))
+    model = model.to(device).eval()
+    left = torch.from_numpy(g["left"]).to(device)
+    right = torch.from_numpy(g["right"]).to(device)
+    B, _, H, W = left.shape
+    h3, w3 = (H - 1) // 3 + 1, (W - 1) // 3 + 1
+    out = PlanesVol.empty(2 * B, 32, planes, 1, h3, w3, device)
+    plan = engine.FeaturePlan(model.feature, ops, 2 * B, H, W, planes, device, out, conv_mode=conv)
+    plan.img[:B].copy_(left)
+    plan.img[B:].copy_(right)
+    plan.run()
+    got = ops.unpack(out)[:, :, 0].cpu()
+    want = torch.cat([torch.from_numpy(g["fx"]), torch.from_numpy(g["fy"])], dim=0)     # the reference's feature maps
+    err = float((got - want).abs().max()) / float(want.abs().max())
+    assert got.shape == want.shape
+    assert err <= tol, err
+    return err

@@ -80,3 +80,9 @@ def test_hot_path_golden_two_planes(emu_ops):
     # 2 planes (the bf16x3 operand format): activations carry 16 significant bits between layers
     rep = K.check_hot_path_golden(emu_ops, DEV, "cal_b2_24x48_d24", planes=2, mat_rtol=5e-3)
     print(rep)
+
+
+def test_native_feature_net(emu_ops):
+    # ragged image size (46x94): partial tiles, stride-3 stem with H, W not multiples of 3
+    err = K.check_feature_plan(emu_ops, DEV, "cal_46x94_d50", planes=3, conv="simt")
+    print("native feature net vs reference feature maps: rel err", err)

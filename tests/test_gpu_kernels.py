@@ -205,3 +205,29 @@ def test_state_dict_roundtrip_and_module_prefix(ops):
         model.matching.stem0.conv.weight.mul_(1.5)
         d2 = model(torch.from_numpy(g["left"]).to(DEV), torch.from_numpy(g["right"]).to(DEV))
     assert not torch.equal(d, d2)
+
+
+# ---- native feature net ------------------------------------------------------------------------
+def test_native_feature_net_simt(ops):
+    assert K.check_feature_plan(ops, DEV, "cal_46x94_d50", planes=3, conv="simt") <= 2e-4
+
+
+def test_native_feature_net_tc(ops):
+    err = K.check_feature_plan(ops, DEV, "cal_48x96_d48", planes=2, conv="tc", tol=5e-4)
+    print("native feature net (tc, 2 planes) rel err", err)
+
+
+@pytest.mark.parametrize("name", ["raw_48x96_d48", "cal_48x96_d48", "cal_46x94_d50", "cal_b2_24x48_d24"])
+def test_full_forward_native_vs_golden(ops, name):
+    """Images in, disparity out, everything on the native kernels (default engine options) against the reference."""
+    g = load_golden(name)
+    model = K.seeded_model(int(g["maxdisp"]))
+    model.load_state_dict(K.golden_state_dict(g, model))
+    model = model.to(DEV).eval()
+    with torch.no_grad():
+        d = model(torch.from_numpy(g["left"]).to(DEV), torch.from_numpy(g["right"]).to(DEV))
+    from leastereo_b200 import engine
+    assert any(isinstance(p, engine.FeaturePlan) for p in engine._plans(model.feature).values()), "native feature path not taken"
+    rep = O.tolerance_report(d.cpu(), torch.from_numpy(g["disp"]))
+    print(name, rep)
+    assert rep["ok"], rep
