@@ -737,12 +737,19 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
     p.tiles_w = (p.W + LEA_TC_TW - 1) / LEA_TC_TW;
     p.tiles_h = (p.H + LEA_TC_TH - 1) / LEA_TC_TH;
-    int Dc = 512 / (p.nsets * accw);
-    if (Dc > 16) Dc = 16;
-    if (Dc > p.D) Dc = p.D;
+    int dc_max = 512 / (p.nsets * accw);
+    if (dc_max > 16) dc_max = 16;
+    if (dc_max > p.D) dc_max = p.D;
     const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
-    // keep at least ~2 work items per SM when the volume is small
-    while (Dc > 1 && (int64_t)p.B * ((p.D + Dc - 1) / Dc) * p.tiles_h * p.tiles_w < 2 * num_sms) Dc = (Dc + 1) / 2;
+    // Depth slices per work item: an item of Dc slices streams Dc + 2*halo slabs at a fixed MMA cost per slab, and the
+    // persistent grid runs ceil(items / SMs) items per CTA - pick the Dc that minimises slabs on the busiest SM.
+    int Dc = 1;
+    int64_t best = -1;
+    for (int cand = 1; cand <= dc_max; ++cand) {
+        const int64_t items = (int64_t)p.B * ((p.D + cand - 1) / cand) * p.tiles_h * p.tiles_w;
+        const int64_t cost = ((items + num_sms - 1) / num_sms) * (cand + (p.ks == 3 ? 2 : 0));
+        if (best < 0 || cost < best || (cost == best && cand > Dc)) { best = cost; Dc = cand; }
+    }
     p.Dc = Dc;
     p.dchunks = (p.D + Dc - 1) / Dc;
     const int64_t total = (int64_t)p.B * p.dchunks * p.tiles_h * p.tiles_w;
