@@ -59,7 +59,7 @@ struct TcParams {
     int term_aoff[kMaxTerms], term_lbo_blocks[kMaxTerms], term_btile[kMaxTerms], term_region[kMaxTerms];
     int term_first[kMaxTerms];   // 1 = first term written into its region (carries the zero-init)
     int nbt, nb_rows, btile_bytes, wpart_bytes;
-    int slab_vox, pitch_vox, blk_bytes, stage_bytes;
+    int slab_vox, pitch_vox, blk_bytes, stage_bytes, stage_stride;   // stride = bytes rounded up to 128 (TMA alignment)
     int nstages, nwbuf;
     int fused_cv, ncg_half;   // fused cost volume: channel groups [0,ncg_half) come from x, the rest from y(w-d)
     const CUtensorMap* cvmaps; // [2*D]: x maps for d = 0..D-1, then y maps
@@ -357,11 +357,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             // origin/width make TMA's zero fill reproduce [w >= d] (see lea_build_fused_cv_maps)
                             const bool left = cg < p.ncg_half;
                             const CUtensorMap* m = p.cvmaps + (left ? 0 : p.D) + d_in;
-                            tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_bytes), m, smem_u32(full + stage),
+                            tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_stride), m, smem_u32(full + stage),
                                         0, g.w0 - kHalo - d_in, g.h0 - kHalo,
                                         gbase + (left ? cg : cg - p.ncg_half) * p.blocks_per_cg);
                         } else {
-                            tma_load_5d(smem_u32(stages + (size_t)stage * p.stage_bytes), &tmap, smem_u32(full + stage),
+                            tma_load_5d(smem_u32(stages + (size_t)stage * p.stage_stride), &tmap, smem_u32(full + stage),
                                         0, g.w0 - kHalo, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
                         }
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
@@ -402,7 +402,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                     mbar_wait(smem_u32(full + stage), sphase, 203);
                     tc_fence_after();
-                    const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_bytes) >> 4;
+                    const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
                     // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi)
                     int kd_a, kd_b;
                     if (KS == 3) {
@@ -558,7 +558,9 @@ static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
         if (nterm == 2) return lea_conv_tc_kernel<KS, 2, 2>;      // 8-channel layout
         return lea_conv_tc_kernel<KS, 3, 2>;                       // bf16x3
     }
-    return nterm == 1 ? lea_conv_tc_kernel<KS, 1, 3> : lea_conv_tc_kernel<KS, 6, 3>;   // bf16x6
+    if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 3>;
+    if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3>;          // 8-channel layout, 3 planes
+    return lea_conv_tc_kernel<KS, 6, 3>;                           // bf16x6
 }
 static TcKernelFn tc_kernel_for(int ks, int nterm, int planes) {
     return ks == 3 ? tc_kernel_for_ks<3>(nterm, planes) : tc_kernel_for_ks<1>(nterm, planes);
@@ -580,11 +582,11 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) 
     if (!(ks == 1 || ks == 3) || P < 1 || P > 3) return s;
     if (!(c_out == 1 || (c_out % 8 == 0 && c_out >= 8 && c_out <= 64))) return s;
     s.c8 = (c_in == 8);
-    if (s.c8 ? (P != 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
+    if (s.c8 ? (P < 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
     s.NP = (c_out + 15) & ~15;                                 // UMMA N granularity at M = 128
     s.taps2d = ks * ks;
     s.nb_rows = ks * s.NP;
-    if (s.c8) { s.nbt = 2; s.ncg = 1; s.ngroups = 1; }
+    if (s.c8) { s.nbt = P; s.ncg = 1; s.ngroups = 1; }
     else      { s.nbt = P; s.ncg = c_in / 16; s.ngroups = P; }
     s.btile_bytes = 2 * s.nb_rows * 16;
     s.wpart_bytes = s.taps2d * s.nbt * s.btile_bytes;
@@ -610,9 +612,13 @@ __global__ void lea_pack_weights_tc_kernel(const float* __restrict__ w, lea_u4* 
     int plane, ci0;
     bool zero = false;
     if (s.c8) {
+        // K16 = two plane blocks of the same 8 channels.  P=2: tile0 [w0;w0], tile1 [w1;0].
+        //                                                  P=3: tile0 [w0;w0], tile1 [w1;w1], tile2 [w2;w0].
         ci0 = 0;
         if (bt == 0) plane = 0;
-        else { plane = 1; zero = (khalf == 1); }
+        else if (P == 2) { plane = 1; zero = (khalf == 1); }
+        else if (bt == 1) plane = 1;
+        else plane = (khalf == 0) ? 2 : 0;
     } else {
         plane = bt; ci0 = cg * 16 + khalf * 8;
     }
@@ -701,10 +707,14 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         p.term_region[p.nterm] = region; p.term_first[p.nterm] = first; ++p.nterm;
     };
     if (s.c8) {
-        p.blocks_per_cg = 2;                                   // 1 channel block x 2 planes
-        add_term(0, 1, 0, 0, 1);                               // [hi|lo] x [Whi;Whi]
-        if (!single) add_term(0, 1, 1, 0, 0);                  // [hi|lo] x [Wlo;0]
+        p.blocks_per_cg = P;                                   // 1 channel block x P planes
         p.ngroups = 1;
+        add_term(0, 1, 0, 0, 1);                               // [a0|a1] x [w0;w0]
+        if (!single && P == 2) add_term(0, 1, 1, 0, 0);        // [a0|a1] x [w1;0]
+        if (!single && P == 3) {
+            add_term(0, 1, 1, 0, 0);                           // [a0|a1] x [w1;w1]
+            add_term(0, 2, 2, 0, 0);                           // [a0|a2] x [w2;w0]
+        }
     } else {
         p.blocks_per_cg = 2 * P;                               // 2 channel blocks x P planes, order [cb][plane]
         if (single) { add_term(0, P, 0, 0, 1); p.ngroups = 1; }
@@ -735,6 +745,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.slab_vox = p.pitch_vox * ((p.ks == 3) ? LEA_TC_TH + 2 : LEA_TC_TH);
     p.blk_bytes = p.slab_vox * 16;
     p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
+    p.stage_stride = (p.stage_bytes + 127) & ~127;
     p.tiles_w = (p.W + LEA_TC_TW - 1) / LEA_TC_TW;
     p.tiles_h = (p.H + LEA_TC_TH - 1) / LEA_TC_TH;
     int dc_max = 512 / (p.nsets * accw);
@@ -756,8 +767,8 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     LEA_CHECK(total < (1ll << 31), "conv3d_tc: too many work items");
     p.total_items = (int)total;
     const int wstride = (p.wpart_bytes + 127) & ~127;
-    p.nwbuf = (2 * wstride + 3 * p.stage_bytes + kHeaderBytes <= kSmemBudget) ? 2 : 1;
-    int nst = (kSmemBudget - kHeaderBytes - p.nwbuf * wstride) / p.stage_bytes;
+    p.nwbuf = (2 * wstride + 3 * p.stage_stride + kHeaderBytes <= kSmemBudget) ? 2 : 1;
+    int nst = (kSmemBudget - kHeaderBytes - p.nwbuf * wstride) / p.stage_stride;
     if (nst > kMaxStages) nst = kMaxStages;
     LEA_CHECK(nst >= 2, "conv3d_tc: shared memory too small for this shape (weights part %d B)", p.wpart_bytes);
     p.nstages = nst;
@@ -766,7 +777,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.bn_scale = c->bn_scale; p.bn_shift = c->bn_shift; p.relu = c->relu;
     p.dst = c->dst; p.dst_c0 = c->dst_c0; p.res = c->res; p.res_c0 = c->res_c0; p.has_res = c->has_res;
     p.dst_f32 = c->dst_f32;
-    const size_t smem = (size_t)kHeaderBytes + (size_t)p.nwbuf * wstride + (size_t)p.nstages * p.stage_bytes;
+    const size_t smem = (size_t)kHeaderBytes + (size_t)p.nwbuf * wstride + (size_t)p.nstages * p.stage_stride;
 
     PFN_encodeTiled encode = get_encode_fn();
     LEA_CHECK(encode != nullptr, "conv3d_tc: cuTensorMapEncodeTiled is not available from the driver");
