@@ -98,6 +98,29 @@ LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w,
     int64_t g = lea_vol_group(v, b, cb, 0, d, h, w);
     const int64_t ps = lea_vol_plane_stride(v);
     uint32_t q[3][4];
+#if defined(__CUDA_ARCH__)
+    // device: hardware round-to-nearest-even packing (cvt.rn.bf16x2.f32); same bits as the software path below for
+    // finite inputs
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float x0 = f[2 * i], x1 = f[2 * i + 1];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            uint32_t hq = 0;
+            if (p < v.P) {
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hq) : "f"(x1), "f"(x0));
+                x0 -= __uint_as_float(hq << 16);
+                x1 -= __uint_as_float(hq & 0xffff0000u);
+            }
+            q[p][i] = hq;
+        }
+    }
+    for (int p = 0; p < v.P; ++p) {
+        lea_u4 o; o.x = q[p][0]; o.y = q[p][1]; o.z = q[p][2]; o.w = q[p][3];
+        base[g + p * ps] = o;
+    }
+    return;
+#endif
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint16_t a[3], c[3];
