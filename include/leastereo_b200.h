@@ -107,6 +107,17 @@ int lea_build_fused_cv_maps(const lea_vol* fx, const lea_vol* fy, int32_t d3, vo
 /* self-test of the tcgen05 path on a synthetic GEMM-shaped conv; returns 0 when it matches the SIMT kernel. */
 int lea_tc_selftest(int32_t verbose, void* stream);
 
+/* ---- matching-net head without the up-sampled volume: retrain/skip_model_3d.py:162-169 (upsample_6 -> last_3) ---- */
+/* last_3 (Conv3d C->1, 3x3x3, no BN/ReLU, skip_model_3d.py:132) and the trilinear align_corners=True up-sample are both
+ * linear, so last_3's channel contraction runs first on the SMALL volume (a 1x1x1 conv C -> 27 "tap" channels,
+ * channel t = kd*9+kh*3+kw, padded to 32; any ConvBR kernel above does it) and this entry point then evaluates
+ *     mat(d,h,w) = sum_t [tap inside the volume] * upsample(q[t])(d+kd-1, h+kh-1, w+kw-1)
+ * separably (three small kernels; workspace = lea_head_taps_workspace_bytes).  q: planes volume (B, >=32, D1, H1, W1)
+ * with the tap channels at q_c0; mat: fp32 (B, 1, D, H, W).  Each axis must satisfy out >= 2*in-1 or out == in. */
+int64_t lea_head_taps_workspace_bytes(int32_t B, int32_t D1, int32_t H1, int32_t D, int32_t H, int32_t W);
+int lea_head_taps(const lea_vol* q, int32_t q_c0, float* mat, int32_t D, int32_t H, int32_t W, float* workspace,
+                  void* stream);
+
 /* ---- disparity head: models/build_model_2d.py:27-57 ------------------------------------------------------------ */
 /* mat (B, D3, H3, W3) fp32 -> disp (B, 3*H3, 3*W3) fp32; upsample + softmin + regression in one kernel. */
 int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D3, int32_t H3, int32_t W3,

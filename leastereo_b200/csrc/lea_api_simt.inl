@@ -138,6 +138,31 @@ extern "C" int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D
     return LEA_POST_LAUNCH();
 }
 
+extern "C" int64_t lea_head_taps_workspace_bytes(int32_t B, int32_t D1, int32_t H1, int32_t D, int32_t H, int32_t W) {
+    if (B <= 0 || D1 <= 0 || H1 <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    (void)D;
+    return (int64_t)sizeof(float) * B * D1 * W * ((int64_t)9 * H1 + (int64_t)3 * H);
+}
+
+extern "C" int lea_head_taps(const lea_vol* q, int32_t q_c0, float* mat, int32_t D, int32_t H, int32_t W,
+                             float* workspace, void* stream) {
+    LEA_CHECK(mat && workspace, "head_taps: null pointer");
+    if (lea_check_vol(q, "head_taps")) return 1;
+    LEA_CHECK((q_c0 & 7) == 0 && q_c0 >= 0 && q_c0 + 32 <= q->C, "head_taps: needs 27 tap channels padded to 32 at an "
+              "8-aligned offset (slice [%d,+32) of %d channels)", q_c0, q->C);
+    LEA_CHECK((D >= 2 * q->D - 1 || D == q->D) && (H >= 2 * q->H - 1 || H == q->H) && (W >= 2 * q->W - 1 || W == q->W),
+              "head_taps: every axis must be up-sampled by >= 2x-1 (or kept): (%d,%d,%d) -> (%d,%d,%d)",
+              q->D, q->H, q->W, D, H, W);
+    LEA_CHECK((int64_t)q->D * H <= 65535 && (int64_t)D * H <= 65535 && q->B <= 65535, "head_taps: grid too large");
+    float* R = workspace;
+    float* S = workspace + (int64_t)q->B * 9 * q->D * q->H * W;
+    const int gx = (W + 127) / 128;
+    LEA_LAUNCH(lea_head_taps_w_kernel, dim3(gx, q->D * q->H, q->B), dim3(128), 0, stream, *q, q_c0, R, W);
+    LEA_LAUNCH(lea_head_taps_h_kernel, dim3(gx, q->D * H, q->B), dim3(128), 0, stream, R, S, q->D, q->H, H, W);
+    LEA_LAUNCH(lea_head_taps_d_kernel, dim3(gx, D * H, q->B), dim3(128), 0, stream, S, mat, q->D, D, H, W);
+    return LEA_POST_LAUNCH();
+}
+
 extern "C" int lea_disparity_regression(const float* p, float* out, int32_t B, int32_t maxdisp, int32_t H, int32_t W,
                                         void* stream) {
     LEA_CHECK(p && out, "disparity_regression: null pointer");

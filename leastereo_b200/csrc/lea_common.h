@@ -119,8 +119,7 @@ LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w,
         lea_u4 o; o.x = q[p][0]; o.y = q[p][1]; o.z = q[p][2]; o.w = q[p][3];
         base[g + p * ps] = o;
     }
-    return;
-#endif
+#else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint16_t a[3], c[3];
@@ -133,6 +132,7 @@ LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w,
         lea_u4 o; o.x = q[p][0]; o.y = q[p][1]; o.z = q[p][2]; o.w = q[p][3];
         base[g + p * ps] = o;
     }
+#endif
 }
 
 // error reporting shared by every API translation unit

@@ -56,6 +56,7 @@ class Step:
     opts: object = None
     image: Optional[torch.Tensor] = None      # packed tcgen05 weight image
     ref: Optional[torch.Tensor] = None
+    wfn: object = None             # callable(step): fills step.wcat with weights DERIVED from the modules' parameters
     # resample
     rs: tuple = ()
 
@@ -76,6 +77,7 @@ class MatchingPlan:
         self.mma_terms = mma_terms
         self.fuse = fuse               # graph-level rewrites: batched sibling convs, conv-before-upsample
         self.fuse_cv = bool(tc_knobs.get("fuse_cv", True))
+        self.fuse_head = bool(tc_knobs.get("fuse_head", True))
         self.accum_split = int(tc_knobs.get("accum_split", 0))
         self.acc_sets = int(tc_knobs.get("acc_sets", 0))
         self.steps: List[Step] = []
@@ -195,6 +197,32 @@ class MatchingPlan:
             opts.acc_sets = self.acc_sets
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
                                weight=weight, wcat=wcat, opts=opts, ref=src.vol.t))
+
+    def _emit_tap_projection(self, name: str, mod: ConvBR3d, src: Slice, dst: Slice):
+        """1x1x1 conv C -> k^3 "tap" channels with weights W[t, c] = mod.weight[0, c, kd, kh, kw], t = kd*9+kh*3+kw:
+        the channel contraction of a single-output 3x3x3 conv, run BEFORE the up-sample it follows
+        (skip_model_3d.py:162-169; see ``lea_head_taps``).  Rows >= k^3 of the padded weight stay zero."""
+        w3 = mod.conv.weight
+        c_in, taps = w3.shape[1], w3.shape[2] * w3.shape[3] * w3.shape[4]
+        if w3.shape[0] != 1 or taps > dst.c or src.c != c_in:
+            raise LeaError("%s: tap projection needs a single-output conv and %d <= %d tap channels" % (name, taps, dst.c))
+        wcat = torch.zeros((dst.c, c_in, 1, 1, 1), dtype=torch.float32, device=self.device)
+
+        def fill(step, mod=mod, taps=taps, c_in=c_in):
+            step.wcat[:taps].copy_(mod.conv.weight.detach().reshape(c_in, taps).t().reshape(taps, c_in, 1, 1, 1))
+
+        p = self.ops.make_conv(src.vol, src.c0, c_in, dst.c, 1, None, None, False, dst=dst.vol, dst_c0=dst.c0)
+        m_vox = self.B * _prod(src.spatial)
+        use_tc = self.conv_mode == "tc" and self.ops.tc_weight_image_bytes(c_in, dst.c, 1, self.P) > 0
+        opts = None
+        if use_tc:
+            opts = lea_tc_opts()
+            opts.mma_terms = self.mma_terms
+            opts.accum_split = self.accum_split
+            opts.acc_sets = self.acc_sets
+        self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, 2.0 * m_vox * taps * c_in,
+                               2.0 * self.P * m_vox * (c_in + dst.c), p=p, mods=(mod,), weight=wcat, wcat=wcat, opts=opts,
+                               ref=src.vol.t, wfn=fill))
 
     def _identity_weight(self, c: int) -> torch.Tensor:
         if c not in self._eye:
@@ -370,20 +398,36 @@ class MatchingPlan:
             self._emit_conv(name, mod, src, dst)
             return dst
 
+        # `pre` = input of the final up-sample to L0 (None when the net already ends on level 0)
         if last.spatial[1] == h:
-            feat = last
+            feat, pre = last, None
         elif last.spatial[1] == h // 2:
-            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, last), L0)
+            pre = conv_to("last_6", m.last_6, last)
         elif last.spatial[1] == h // 4:
             t = self._resample("head.upsample_12", conv_to("last_12", m.last_12, last), (d // 2, h // 2, w // 2))
-            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, t), L0)
+            pre = conv_to("last_6", m.last_6, t)
         elif last.spatial[1] == h // 8:
             t = self._resample("head.upsample_24", conv_to("last_24", m.last_24, last), (d // 4, h // 4, w // 4))
             t = self._resample("head.upsample_12", conv_to("last_12", m.last_12, t), (d // 2, h // 2, w // 2))
-            feat = self._resample("head.upsample_6", conv_to("last_6", m.last_6, t), L0)
+            pre = conv_to("last_6", m.last_6, t)
         else:
             raise LeaError("matching net ends on a level the reference head does not handle (H3=%d, last H=%d)"
                            % (h, last.spatial[1]))
+        l3 = m.last_3
+        fusable = (pre is not None and self.fuse and self.fuse_head and tuple(l3.conv.weight.shape[2:]) == (3, 3, 3)
+                   and l3.conv.out_channels == 1 and not l3.use_bn and not l3.relu
+                   and all(o >= 2 * i - 1 for o, i in zip(L0, pre.spatial)))
+        if fusable:
+            # upsample_6 -> last_3 without the up-sampled volume: last_3's channel contraction runs on the small
+            # volume (27 tap channels), the separable interpolation + tap shifts are summed by lea_head_taps
+            q = Slice(self._vol(32, pre.spatial), 0, 32)
+            self._emit_tap_projection("last_3.taps(low-res)", l3, pre, q)
+            ws = self.ops.head_taps_workspace(q.vol, L0)
+            nbytes = 2.0 * self.P * self.B * _prod(pre.spatial) * 32 + 4.0 * self.B * _prod(L0)
+            self.steps.append(Step("head_taps", "head.upsample_6+last_3", 0.0, nbytes, rs=(q.vol, 0, self.mat, ws)))
+            return
+        if pre is not None:
+            feat = self._resample("head.upsample_6", pre, L0)
         if feat.spatial != L0:
             raise LeaError("head input %s does not match the cost volume %s" % (feat.spatial, L0))
         self._emit_conv("last_3", m.last_3, feat, None, dst_f32=self.mat)
@@ -425,7 +469,9 @@ class MatchingPlan:
                         w = mod.conv.weight
                         if not (w.is_contiguous() and w.dtype == torch.float32 and w.device == self.device):
                             raise LeaError("%s: weights must be contiguous fp32 on %s" % (s.name, self.device))
-                    if s.wcat is not None:
+                    if s.wfn is not None:
+                        s.wfn(s)
+                    elif s.wcat is not None:
                         ws = [mod.conv.weight.detach() for mod in s.mods]
                         if ws[0].dim() == 4:       # 2-D weights go into the middle depth slice of the k^3 kernel
                             s.wcat[:, :, s.wcat.shape[2] // 2].copy_(torch.cat(ws, dim=0))
@@ -446,6 +492,9 @@ class MatchingPlan:
             self.ops.conv3d_simt(s.p, s.weight, s.ref)
         elif s.kind == "conv_tc":
             self.ops.conv3d_tc(s.p, s.image, s.opts, s.ref)
+        elif s.kind == "head_taps":
+            q, q_c0, mat, ws = s.rs
+            self.ops.head_taps(q, q_c0, mat, ws)
         elif s.kind == "repack":
             src, dst, c = s.rs
             self.ops.affine_relu(src, 0, dst, 0, c, None, None, False, False)
@@ -581,7 +630,7 @@ def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops:
     ops = ops or get_ops()
     key = (str(device), B, tuple(spatial), options["planes"], options["conv"], options["mma_terms"],
            bool(options.get("fuse", True)), int(options.get("accum_split", 0)), int(options.get("acc_sets", 0)),
-           bool(options.get("fuse_cv", True)), id(ops))
+           bool(options.get("fuse_cv", True)), bool(options.get("fuse_head", True)), id(ops))
     with _LOCK:
         plans = _plans(matching)
         plan = plans.get(key)
@@ -589,7 +638,7 @@ def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops:
             plan = MatchingPlan(matching, ops, B, spatial, options["planes"], device, options["conv"],
                                 options["mma_terms"], bool(options.get("fuse", True)),
                                 {"accum_split": options.get("accum_split", 0), "acc_sets": options.get("acc_sets", 0),
-                                 "fuse_cv": options.get("fuse_cv", True)})
+                                 "fuse_cv": options.get("fuse_cv", True), "fuse_head": options.get("fuse_head", True)})
             plans[key] = plan
     return plan
 

@@ -54,6 +54,8 @@ SYMBOLS = {
     "lea_tc_selftest": (C.c_int, [_i32, _vp]),
     "lea_fused_cv_maps_bytes": (_i64, [_i32]),
     "lea_build_fused_cv_maps": (C.c_int, [_VOLP, _VOLP, _i32, _vp, _vp]),
+    "lea_head_taps_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
+    "lea_head_taps": (C.c_int, [_VOLP, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
     "lea_disp_head": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "lea_disparity_regression": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "lea_feature_stem": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _VOLP, _i32, _vp]),
@@ -278,6 +280,24 @@ class Ops:
 
     def tc_selftest(self, verbose: int = 1) -> int:
         return int(self.lib.lea_tc_selftest(verbose, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    # ---- matching-net head (upsample_6 -> last_3 without the up-sampled volume) ----------------------------
+    def head_taps_workspace(self, q: PlanesVol, spatial) -> torch.Tensor:
+        D, H, W = (int(v) for v in spatial)
+        n = int(self.lib.lea_head_taps_workspace_bytes(q.B, q.D, q.H, D, H, W))
+        return torch.empty(max(n // 4, 1), dtype=torch.float32, device=q.t.device)
+
+    def head_taps(self, q: PlanesVol, q_c0: int, mat: torch.Tensor, workspace: Optional[torch.Tensor] = None):
+        """mat (B, 1, D, H, W) fp32 <- sum over the 27 tap channels of q, up-sampled and shifted (see the header)."""
+        self._dev(q.t, mat)
+        assert mat.dtype == torch.float32 and mat.is_contiguous() and mat.dim() == 5 and mat.shape[1] == 1
+        D, H, W = (int(v) for v in mat.shape[2:])
+        ws = workspace if workspace is not None else self.head_taps_workspace(q, (D, H, W))
+        qs = q.struct()
+        with torch.cuda.device(mat.device) if mat.is_cuda else _null():
+            self._check(self.lib.lea_head_taps(C.byref(qs), q_c0, mat.data_ptr(), D, H, W, ws.data_ptr(),
+                                               self._stream(mat)))
+        self.launches += 2                      # three kernels behind one entry point
 
     # ---- disparity head ---------------------------------------------------------------------------------
     def disp_head(self, mat: torch.Tensor, maxdisp: int) -> torch.Tensor:

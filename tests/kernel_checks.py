@@ -147,6 +147,26 @@ def check_disp_head(ops, device):
     assert float(((got - want).abs() <= 0.1).float().mean()) >= 0.99
 
 
+def check_head_taps(ops, device):
+    """lea_head_taps (+ the 1x1x1 tap projection) against  conv3d(interpolate(x, align_corners=True), w3, padding=1)
+    - retrain/skip_model_3d.py:162-169 - on up-sampling shapes incl. odd sizes, a kept axis and a size-1 axis."""
+    cases = [((4, 6, 8), (8, 12, 16)), ((3, 5, 4), (5, 9, 7)), ((4, 6, 8), (8, 6, 16)), ((1, 3, 5), (1, 6, 10)),
+             ((2, 2, 2), (7, 9, 5))]
+    for i, (src_sp, dst_sp) in enumerate(cases):
+        B, Cn = 2, 16
+        x = _rand((B, Cn) + src_sp, 40 + i, device)
+        w3 = _rand((1, Cn, 3, 3, 3), 60 + i, device, scale=0.3)
+        q = torch.einsum("bcdhw,ct->btdhw", x, w3.reshape(Cn, 27))
+        qv = PlanesVol.empty(B, 40, 3, *src_sp, device)
+        qv.t.zero_()
+        ops.pack(F.pad(q, (0, 0, 0, 0, 0, 0, 0, 5)).contiguous(), 3, out=qv, c0=8)      # taps at channels 8..34
+        mat = torch.empty((B, 1) + dst_sp, dtype=torch.float32, device=device)
+        ops.head_taps(qv, 8, mat)
+        want = F.conv3d(F.interpolate(x.cpu(), dst_sp, mode="trilinear", align_corners=True), w3.cpu(), None, 1, 1)
+        err = float((mat.cpu() - want).abs().max()) / max(1.0, float(want.abs().max()))
+        assert err <= 5e-6, (src_sp, dst_sp, err)
+
+
 def check_disparity_regression(ops, device):
     p = torch.softmax(_rand((2, 24, 5, 7), 5, device), dim=1).contiguous()
     got = ops.disparity_regression(p, 24).cpu()

@@ -66,6 +66,10 @@ def test_disp_head(emu_ops):
     K.check_disp_head(emu_ops, DEV)
 
 
+def test_head_taps(emu_ops):
+    K.check_head_taps(emu_ops, DEV)
+
+
 def test_disparity_regression(emu_ops):
     K.check_disparity_regression(emu_ops, DEV)
 

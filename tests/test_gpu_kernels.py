@@ -56,6 +56,10 @@ def test_disp_head(ops):
     K.check_disp_head(ops, DEV)
 
 
+def test_head_taps(ops):
+    K.check_head_taps(ops, DEV)
+
+
 def test_disparity_regression(ops):
     K.check_disparity_regression(ops, DEV)
 
