@@ -218,6 +218,10 @@ def profile_kernels(model, left, right):
 
     for rep in range(2):       # first repetition warms up, second is reported
         records.clear()
+        torch.cuda.synchronize()
+        # let the host run ahead of the GPU: with an idle GPU a small kernel's event pair would time the host launch
+        # path (~20 us per ctypes call) instead of the kernel
+        torch.cuda._sleep(int(2.5e7))
         cv_bytes = 4.0 * B * (2 * C * H3 * W3 + 2 * C * D3 * H3 * W3)
         if fplan is not None:
             fplan.img[:B].copy_(left); fplan.img[B:].copy_(right)
@@ -249,7 +253,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=1, help="stereo pairs per GPU per step")
+    ap.add_argument("--batch", type=int, default=4,
+                    help="stereo pairs per GPU per step (BASELINE configs[2] sweeps batch 1-64; throughput saturates at 4)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--conv", default=os.environ.get("LEA_CONV", "tc"), choices=["tc", "simt"])
     ap.add_argument("--planes", type=int, default=int(os.environ.get("LEA_PLANES", "2")))
@@ -257,6 +262,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-launches", default=None, help="write the per-launch profile to this JSON file")
+    ap.add_argument("--knob", action="append", default=[], help="engine option override name=int (development)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -285,6 +291,9 @@ def main():
 
     H, W, maxdisp, B = WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["maxdisp"], args.batch
     options = {"planes": args.planes, "conv": args.conv, "mma_terms": args.mma_terms, "assume_frozen": True}
+    for kv in args.knob:
+        k, v = kv.split("=")
+        options[k] = int(v)
     model = build_model(maxdisp, device, options)
     left_h, right_h = synthetic_pairs(B, H, W, seed=1 + rank)
     left_h, right_h = left_h.pin_memory(), right_h.pin_memory()

@@ -94,6 +94,9 @@ typedef struct lea_tc_opts {
                               dominant accumulator 3x); 2 = all terms share one accumulator (more depth per work item) */
     int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
     const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
+    int32_t resident_weights;  /* 0 = auto (all channel groups' weights stay in shared memory when they fit), 2 = never */
+    int32_t depth_chunk;       /* 1x1x1 convs only: 0 = auto, n = depth slices per work item (development knob) */
+    int32_t tile_w_log2;       /* 1x1x1 convs only: 0 = auto, 3..7 = tile of 2^n voxels along w by 128/2^n along h */
 } lea_tc_opts;
 int lea_conv3d_tc(const lea_conv* p, const void* wimg, const lea_tc_opts* opts, void* stream);
 /* Fused cost volume (retrain/LEAStereo.py:34-48 inside stem0's operand loader).  fx, fy: the two feature maps as

@@ -41,9 +41,10 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kMaxTerms = 6;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 24;   // deep enough that 8 KB 1x1x1 stages keep ~1.5 us of HBM latency covered
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kHeaderBytes = 1024;
+static_assert(8 * (2 * kMaxStages + 8) + 4 <= 512, "barriers + TMEM slot must fit below the BN vectors at byte 512");
 constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;    // ~2 s: a stuck pipeline traps instead of hanging
 
 struct TcParams {
@@ -61,6 +62,8 @@ struct TcParams {
     int nbt, nb_rows, btile_bytes, wpart_bytes;
     int slab_vox, pitch_vox, blk_bytes, stage_bytes, stage_stride;   // stride = bytes rounded up to 128 (TMA alignment)
     int nstages, nwbuf;
+    int tw_log2;              // tile = (1 << tw_log2) voxels along w x (128 >> tw_log2) along h  (3 for k = 3)
+    int wres;                 // 1 = the weight parts of ALL channel groups stay resident in shared memory (loaded once per CTA)
     int fused_cv, ncg_half;   // fused cost volume: channel groups [0,ncg_half) come from x, the rest from y(w-d)
     const CUtensorMap* cvmaps; // [2*D]: x maps for d = 0..D-1, then y maps
     int nsets;                // TMEM accumulator sets: 2 = epilogue of item i overlaps MMAs of item i+1, 1 = larger Dc
@@ -111,6 +114,13 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
         " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
@@ -173,7 +183,7 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
     g.b = r;
     g.d0 = dc * p.Dc;
     g.d_hi = min(g.d0 + p.Dc, p.D);
-    g.h0 = th * LEA_TC_TH; g.w0 = tw * LEA_TC_TW;
+    g.h0 = th * (128 >> p.tw_log2); g.w0 = tw << p.tw_log2;
     if (p.ks == 3) { g.dlo = max(g.d0 - 1, 0); g.dhi = min(g.d_hi, p.D - 1); }
     else           { g.dlo = g.d0;             g.dhi = g.d_hi - 1; }
     return g;
@@ -303,7 +313,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint64_t* accfull = wempty + 2;                 // [2]
     uint64_t* accempty = accfull + 2;               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
-    float* s_scale = reinterpret_cast<float*>(smem + 256);      // [64]
+    float* s_scale = reinterpret_cast<float*>(smem + 512);      // [64]  (barriers occupy the first 8*(2*kMaxStages+8) B)
     float* s_shift = s_scale + 64;                              // [64]
     uint8_t* wbuf = smem + kHeaderBytes;
     const int wbuf_stride = (p.wpart_bytes + 127) & ~127;
@@ -340,15 +350,23 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0, sphase = 0, wb = 0, wphase = 0;
+            if (p.wres) {                         // all weight parts fit: load them once, they stay for every item
+                mbar_arrive_expect_tx(smem_u32(wfull), (uint32_t)(p.ncg * p.wpart_bytes));
+                for (int cg = 0; cg < p.ncg; ++cg)
+                    bulk_load(smem_u32(wbuf + (size_t)cg * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
+                              (uint32_t)p.wpart_bytes, smem_u32(wfull));
+            }
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const ItemGeom g = decode_item(p, item);
                 const int gbase = g.b * p.g0_stride_b + p.g0_first;
                 for (int cg = 0; cg < p.ncg; ++cg) {
-                    mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101);
-                    mbar_arrive_expect_tx(smem_u32(wfull + wb), (uint32_t)p.wpart_bytes);
-                    bulk_load(smem_u32(wbuf + (size_t)wb * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
-                              (uint32_t)p.wpart_bytes, smem_u32(wfull + wb));
-                    if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                    if (!p.wres) {
+                        mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101);
+                        mbar_arrive_expect_tx(smem_u32(wfull + wb), (uint32_t)p.wpart_bytes);
+                        bulk_load(smem_u32(wbuf + (size_t)wb * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
+                                  (uint32_t)p.wpart_bytes, smem_u32(wfull + wb));
+                        if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                    }
                     for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                         mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102);
                         mbar_arrive_expect_tx(smem_u32(full + stage), (uint32_t)p.stage_bytes);
@@ -357,12 +375,12 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             // origin/width make TMA's zero fill reproduce [w >= d] (see lea_build_fused_cv_maps)
                             const bool left = cg < p.ncg_half;
                             const CUtensorMap* m = p.cvmaps + (left ? 0 : p.D) + d_in;
-                            tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_stride), m, smem_u32(full + stage),
-                                        0, g.w0 - kHalo - d_in, g.h0 - kHalo,
+                            tma_load_3d(smem_u32(stages + (size_t)stage * p.stage_stride), m, smem_u32(full + stage),
+                                        (g.w0 - kHalo - d_in) * 8, g.h0 - kHalo,
                                         gbase + (left ? cg : cg - p.ncg_half) * p.blocks_per_cg);
                         } else {
-                            tma_load_5d(smem_u32(stages + (size_t)stage * p.stage_stride), &tmap, smem_u32(full + stage),
-                                        0, g.w0 - kHalo, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
+                            tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_stride), &tmap, smem_u32(full + stage),
+                                        (g.w0 - kHalo) * 8, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
                         }
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                     }
@@ -390,6 +408,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per (kh,kw) / 16
         const uint32_t set_cols = (uint32_t)(p.ngroups * p.Dc * p.NP);
         int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
+        if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const ItemGeom g = decode_item(p, item);
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
@@ -397,8 +416,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             tc_fence_after();
             const uint32_t set_base = tmem_base + (uint32_t)set * set_cols;
             for (int cg = 0; cg < p.ncg; ++cg) {
-                mbar_wait(smem_u32(wfull + wb), wphase, 202);
-                const uint32_t w16 = (smem_u32(wbuf + (size_t)wb * wbuf_stride) >> 4) | b_lbo_field;
+                if (!p.wres) mbar_wait(smem_u32(wfull + wb), wphase, 202);
+                const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                     mbar_wait(smem_u32(full + stage), sphase, 203);
                     tc_fence_after();
@@ -452,8 +471,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     tc_commit_if(elected, smem_u32(empty + stage));
                     if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                 }
-                tc_commit_if(elected, smem_u32(wempty + wb));
-                if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                if (!p.wres) {
+                    tc_commit_if(elected, smem_u32(wempty + wb));
+                    if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                }
             }
             tc_commit_if(elected, smem_u32(accfull + set));
         }
@@ -464,7 +485,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         constexpr int kJB = 4;
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;                 // tile row = TMEM lane
-        const int lh = m / LEA_TC_TW, lw = m % LEA_TC_TW;
+        const int lh = m >> p.tw_log2, lw = m & ((1 << p.tw_log2) - 1);
         const int64_t sp = (int64_t)p.D * p.H * p.W;
         int it = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
@@ -741,13 +762,27 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // 4 depth slices per item (wide N), one set with twice the depth wastes fewer halo slabs
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
     if (opts && (opts->acc_sets == 1 || opts->acc_sets == 2)) p.nsets = opts->acc_sets;
-    p.pitch_vox = (p.ks == 3) ? LEA_TC_TW + 2 : LEA_TC_TW;
-    p.slab_vox = p.pitch_vox * ((p.ks == 3) ? LEA_TC_TH + 2 : LEA_TC_TH);
+    // tile shape: 8 x 16 for k = 3 (the tap windows need the 8-row core-matrix groups to be rows of the slab); a
+    // 1x1x1 conv has no halo, its slab is 128 consecutive rows whatever the shape, so it takes the widest tile the
+    // volume fills without padding (longer contiguous runs for TMA and for the epilogue's stores)
+    p.tw_log2 = 3;
+    if (p.ks == 1) {
+        int64_t best_area = -1;
+        for (int l2 = 3; l2 <= 5; ++l2) {
+            const int tw = 1 << l2, th = 128 >> l2;
+            const int64_t area = (int64_t)((p.W + tw - 1) / tw) * tw * (((p.H + th - 1) / th) * th);
+            if (best_area < 0 || area <= best_area) { best_area = area; p.tw_log2 = l2; }
+        }
+        if (opts && opts->tile_w_log2 >= 3 && opts->tile_w_log2 <= 7) p.tw_log2 = opts->tile_w_log2;
+    }
+    const int tile_w = 1 << p.tw_log2, tile_h = 128 >> p.tw_log2;
+    p.pitch_vox = (p.ks == 3) ? tile_w + 2 : tile_w;
+    p.slab_vox = p.pitch_vox * ((p.ks == 3) ? tile_h + 2 : tile_h);
     p.blk_bytes = p.slab_vox * 16;
     p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
     p.stage_stride = (p.stage_bytes + 127) & ~127;
-    p.tiles_w = (p.W + LEA_TC_TW - 1) / LEA_TC_TW;
-    p.tiles_h = (p.H + LEA_TC_TH - 1) / LEA_TC_TH;
+    p.tiles_w = (p.W + tile_w - 1) / tile_w;
+    p.tiles_h = (p.H + tile_h - 1) / tile_h;
     int dc_max = 512 / (p.nsets * accw);
     if (dc_max > 16) dc_max = 16;
     if (dc_max > p.D) dc_max = p.D;
@@ -761,6 +796,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         const int64_t cost = ((items + num_sms - 1) / num_sms) * (cand + (p.ks == 3 ? 2 : 0));
         if (best < 0 || cost < best || (cost == best && cand > Dc)) { best = cost; Dc = cand; }
     }
+    if (opts && opts->depth_chunk > 0 && p.ks == 1) Dc = opts->depth_chunk < dc_max ? opts->depth_chunk : dc_max;
     p.Dc = Dc;
     p.dchunks = (p.D + Dc - 1) / Dc;
     const int64_t total = (int64_t)p.B * p.dchunks * p.tiles_h * p.tiles_w;
@@ -768,6 +804,11 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.total_items = (int)total;
     const int wstride = (p.wpart_bytes + 127) & ~127;
     p.nwbuf = (2 * wstride + 3 * p.stage_stride + kHeaderBytes <= kSmemBudget) ? 2 : 1;
+    // every channel group's weight part resident (one load per CTA instead of one per item and group) when that
+    // still leaves a useful activation ring
+    p.wres = (kHeaderBytes + (int64_t)p.ncg * wstride + 6 * (int64_t)p.stage_stride <= kSmemBudget) ? 1 : 0;
+    if (opts && opts->resident_weights == 2) p.wres = 0;
+    if (p.wres) p.nwbuf = p.ncg;
     int nst = (kSmemBudget - kHeaderBytes - p.nwbuf * wstride) / p.stage_stride;
     if (nst > kMaxStages) nst = kMaxStages;
     LEA_CHECK(nst >= 2, "conv3d_tc: shared memory too small for this shape (weights part %d B)", p.wpart_bytes);
@@ -787,12 +828,14 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     const int mapD = fused ? 1 : p.D;
     void* map_base = fused ? opts->fx.data : c->src.data;
     const cuuint64_t G = (cuuint64_t)p.B * (mapC >> 3) * P;
-    cuuint64_t gdim[5] = {8, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)mapD, G};
-    cuuint64_t gstr[4] = {16, (cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)mapD * p.H * p.W * 16};
-    cuuint32_t box[5] = {8, (cuuint32_t)p.pitch_vox, (cuuint32_t)(p.slab_vox / p.pitch_vox), 1,
+    // the 8-channel group and w are contiguous in memory: one merged inner dimension of W*8 elements, so that a box
+    // row is one 128..512-byte run for the TMA engine instead of 8..32 separate 16-byte rows
+    cuuint64_t gdim[4] = {(cuuint64_t)p.W * 8, (cuuint64_t)p.H, (cuuint64_t)mapD, G};
+    cuuint64_t gstr[3] = {(cuuint64_t)p.W * 16, (cuuint64_t)p.H * p.W * 16, (cuuint64_t)mapD * p.H * p.W * 16};
+    cuuint32_t box[4] = {(cuuint32_t)p.pitch_vox * 8, (cuuint32_t)(p.slab_vox / p.pitch_vox), 1,
                          (cuuint32_t)p.blocks_per_cg};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, map_base, gdim, gstr, box, estr,
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, map_base, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
@@ -865,11 +908,11 @@ extern "C" int lea_build_fused_cv_maps(const lea_vol* fx, const lea_vol* fy, int
             // y: origin unchanged                  -> coordinate w' = w - d addresses y[h, w-d]; w' < 0  <=> w < d -> 0
             // both: width W - d                    -> w' >= W - d <=> w >= W (right halo) -> 0
             uint8_t* base = reinterpret_cast<uint8_t*>(side == 0 ? fx->data : fy->data) + (side == 0 ? (size_t)d * 16 : 0);
-            cuuint64_t gdim[4] = {8, (cuuint64_t)(W - d), (cuuint64_t)H, G};
-            cuuint64_t gstr[3] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
-            cuuint32_t box[4] = {8, (cuuint32_t)(LEA_TC_TW + 2), (cuuint32_t)(LEA_TC_TH + 2), (cuuint32_t)(2 * P)};
-            cuuint32_t estr[4] = {1, 1, 1, 1};
-            CUresult cr = encode(&maps[(size_t)side * d3 + d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstr, box,
+            cuuint64_t gdim[3] = {(cuuint64_t)(W - d) * 8, (cuuint64_t)H, G};
+            cuuint64_t gstr[2] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16};
+            cuuint32_t box[3] = {(cuuint32_t)(LEA_TC_TW + 2) * 8, (cuuint32_t)(LEA_TC_TH + 2), (cuuint32_t)(2 * P)};
+            cuuint32_t estr[3] = {1, 1, 1};
+            CUresult cr = encode(&maps[(size_t)side * d3 + d], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             LEA_CHECK(cr == CUDA_SUCCESS, "build_fused_cv_maps: cuTensorMapEncodeTiled failed (%d) at d=%d", (int)cr, d);

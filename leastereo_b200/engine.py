@@ -80,6 +80,9 @@ class MatchingPlan:
         self.fuse_head = bool(tc_knobs.get("fuse_head", True))
         self.accum_split = int(tc_knobs.get("accum_split", 0))
         self.acc_sets = int(tc_knobs.get("acc_sets", 0))
+        self.tile_w_log2 = int(tc_knobs.get("tile_w_log2", 0))
+        self.resident_weights = int(tc_knobs.get("resident_weights", 0))
+        self.depth_chunk = int(tc_knobs.get("depth_chunk", 0))
         self.steps: List[Step] = []
         self.volumes: List[PlanesVol] = []
         self._bn_users: List[Tuple[ConvBR3d, int]] = []     # (module, offset into the BN buffers)
@@ -195,6 +198,9 @@ class MatchingPlan:
                 opts.cv_maps = self.cv_maps.data_ptr()
             opts.accum_split = self.accum_split
             opts.acc_sets = self.acc_sets
+            opts.tile_w_log2 = self.tile_w_log2
+            opts.resident_weights = self.resident_weights
+            opts.depth_chunk = self.depth_chunk
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
                                weight=weight, wcat=wcat, opts=opts, ref=src.vol.t))
 
@@ -220,6 +226,9 @@ class MatchingPlan:
             opts.mma_terms = self.mma_terms
             opts.accum_split = self.accum_split
             opts.acc_sets = self.acc_sets
+            opts.tile_w_log2 = self.tile_w_log2
+            opts.resident_weights = self.resident_weights
+            opts.depth_chunk = self.depth_chunk
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, 2.0 * m_vox * taps * c_in,
                                2.0 * self.P * m_vox * (c_in + dst.c), p=p, mods=(mod,), weight=wcat, wcat=wcat, opts=opts,
                                ref=src.vol.t, wfn=fill))
@@ -607,6 +616,11 @@ DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fus
                    "assume_frozen": False}
 
 
+# tensor-core kernel / plan-rewrite knobs an ``engine_options`` dict may carry (defaults = what the product runs)
+_TC_KNOBS = {"accum_split": 0, "acc_sets": 0, "fuse_cv": True, "fuse_head": True, "tile_w_log2": 0,
+             "resident_weights": 0, "depth_chunk": 0}
+
+
 def _options(model) -> dict:
     o = dict(DEFAULT_OPTIONS)
     o.update(getattr(model, "engine_options", None) or {})
@@ -628,17 +642,15 @@ def invalidate_cached_plans(model):
 
 def get_plan(matching: newMatching, B: int, spatial, device, options: dict, ops: Optional[Ops] = None) -> MatchingPlan:
     ops = ops or get_ops()
+    knobs = {k: options.get(k, d) for k, d in _TC_KNOBS.items()}
     key = (str(device), B, tuple(spatial), options["planes"], options["conv"], options["mma_terms"],
-           bool(options.get("fuse", True)), int(options.get("accum_split", 0)), int(options.get("acc_sets", 0)),
-           bool(options.get("fuse_cv", True)), bool(options.get("fuse_head", True)), id(ops))
+           bool(options.get("fuse", True)), tuple(sorted(knobs.items())), id(ops))
     with _LOCK:
         plans = _plans(matching)
         plan = plans.get(key)
         if plan is None:
             plan = MatchingPlan(matching, ops, B, spatial, options["planes"], device, options["conv"],
-                                options["mma_terms"], bool(options.get("fuse", True)),
-                                {"accum_split": options.get("accum_split", 0), "acc_sets": options.get("acc_sets", 0),
-                                 "fuse_cv": options.get("fuse_cv", True), "fuse_head": options.get("fuse_head", True)})
+                                options["mma_terms"], bool(options.get("fuse", True)), knobs)
             plans[key] = plan
     return plan
 
@@ -696,7 +708,7 @@ def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[O
             try:
                 fplan = FeaturePlan(model.feature, ops, 2 * B, H, W, int(opt.get("feature_planes", 3)), left.device, plan.fxy,
                                     opt["mma_terms"], bool(opt.get("fuse", True)),
-                                    {"accum_split": opt.get("accum_split", 0), "acc_sets": opt.get("acc_sets", 0)})
+                                    {k: opt.get(k, d) for k, d in _TC_KNOBS.items()})
             except LeaError:
                 fplan = False
             plans[key] = fplan

@@ -40,6 +40,8 @@ def main():
         conv(16, 48, 3, (32, 64, 208), False)
     if "l0res" in which:
         conv(8, 8, 3, (64, 128, 416), True)
+    if "pp64" in which:
+        conv(64, 16, 1, (32, 64, 208), False)
     if "cv" in which:
         x = torch.randn(B, C, H3, W3, device=dev); y = torch.randn(B, C, H3, W3, device=dev)
         for _ in range(2):

@@ -14,9 +14,12 @@ from leastereo_b200.kernels import get_ops, PlanesVol, lea_tc_opts  # noqa: E402
 
 
 def timeit(fn, iters=5, warm=2):
+    """Median device time of fn's launches.  A long spin kernel is queued first so that the host runs ahead of the
+    GPU and the event pairs bracket back-to-back GPU work (otherwise small kernels measure the host launch path)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    torch.cuda._sleep(int(4e6 * (iters + 1)))
     evs = []
     for _ in range(iters):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
