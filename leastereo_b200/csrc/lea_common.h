@@ -92,11 +92,8 @@ LEA_HD void lea_vol_load8(const lea_vol& v, int b, int cb, int d, int h, int w, 
     lea_unpack8(base[g], f, false);
     for (int p = 1; p < v.P; ++p) lea_unpack8(base[g + p * ps], f, true);
 }
-// write 8 channels of one voxel, splitting into the volume's planes
-LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w, const float* f) {
-    lea_u4* base = (lea_u4*)v.data;
-    int64_t g = lea_vol_group(v, b, cb, 0, d, h, w);
-    const int64_t ps = lea_vol_plane_stride(v);
+// write 8 fp32 values as P bf16 planes: plane p goes to g0[p * ps]
+LEA_HD void lea_store8_at(lea_u4* g0, int64_t ps, int P, const float* f) {
     uint32_t q[3][4];
 #if defined(__CUDA_ARCH__)
     // device: hardware round-to-nearest-even packing (cvt.rn.bf16x2.f32); same bits as the software path below for
@@ -107,7 +104,7 @@ LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w,
 #pragma unroll
         for (int p = 0; p < 3; ++p) {
             uint32_t hq = 0;
-            if (p < v.P) {
+            if (p < P) {
                 asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hq) : "f"(x1), "f"(x0));
                 x0 -= __uint_as_float(hq << 16);
                 x1 -= __uint_as_float(hq & 0xffff0000u);
@@ -115,24 +112,34 @@ LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w,
             q[p][i] = hq;
         }
     }
-    for (int p = 0; p < v.P; ++p) {
-        lea_u4 o; o.x = q[p][0]; o.y = q[p][1]; o.z = q[p][2]; o.w = q[p][3];
-        base[g + p * ps] = o;
-    }
 #else
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint16_t a[3], c[3];
-        lea_split_planes(f[2 * i], v.P, a);
-        lea_split_planes(f[2 * i + 1], v.P, c);
+        lea_split_planes(f[2 * i], P, a);
+        lea_split_planes(f[2 * i + 1], P, c);
 #pragma unroll
         for (int p = 0; p < 3; ++p) q[p][i] = (uint32_t)a[p] | ((uint32_t)c[p] << 16);
     }
-    for (int p = 0; p < v.P; ++p) {
-        lea_u4 o; o.x = q[p][0]; o.y = q[p][1]; o.z = q[p][2]; o.w = q[p][3];
-        base[g + p * ps] = o;
-    }
 #endif
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        if (p < P) {
+            lea_u4 o; o.x = q[p][0]; o.y = q[p][1]; o.z = q[p][2]; o.w = q[p][3];
+            g0[p * ps] = o;
+        }
+    }
+}
+// write 8 channels of one voxel, splitting into the volume's planes
+LEA_HD void lea_vol_store8(const lea_vol& v, int b, int cb, int d, int h, int w, const float* f) {
+    lea_store8_at((lea_u4*)v.data + lea_vol_group(v, b, cb, 0, d, h, w), lea_vol_plane_stride(v), v.P, f);
+}
+// read 8 fp32 values stored as P planes at g0[p * ps]
+LEA_HD void lea_load8_at(const lea_u4* g0, int64_t ps, int P, float* f) {
+    lea_unpack8(g0[0], f, false);
+#pragma unroll
+    for (int p = 1; p < 3; ++p)
+        if (p < P) lea_unpack8(g0[p * ps], f, true);
 }
 
 // error reporting shared by every API translation unit

@@ -147,24 +147,26 @@ lea_trilinear_ac_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c,
     const lea_axis_lerp ad = lea_axis_ac(d, src.D, dst.D);
     const lea_axis_lerp ah = lea_axis_ac(h, src.H, dst.H);
     const lea_axis_lerp aw = lea_axis_ac(w, src.W, dst.W);
-    const int scb = (src_c0 >> 3) + cb;
+    // one base pointer + small offsets instead of a 64-bit index chain per load (the kernel is instruction-bound)
+    const int64_t sHW = (int64_t)src.H * src.W, sPS = sHW * src.D;
+    const lea_u4* sbase = (const lea_u4*)src.data + ((int64_t)b * (src.C >> 3) + (src_c0 >> 3) + cb) * src.P * sPS;
     float out[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) out[j] = 0.0f;
 #pragma unroll
     for (int zd = 0; zd < 2; ++zd) {
         const float wd = zd ? ad.l1 : ad.l0;
-        const int id = zd ? ad.i1 : ad.i0;
+        const lea_u4* sd = sbase + (int64_t)(zd ? ad.i1 : ad.i0) * sHW;
         float accd[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) accd[j] = 0.0f;
 #pragma unroll
         for (int zh = 0; zh < 2; ++zh) {
             const float wh = zh ? ah.l1 : ah.l0;
-            const int ih = zh ? ah.i1 : ah.i0;
+            const lea_u4* sh = sd + (zh ? ah.i1 : ah.i0) * src.W;
             float a[8], bb[8];
-            lea_vol_load8(src, b, scb, id, ih, aw.i0, a);
-            lea_vol_load8(src, b, scb, id, ih, aw.i1, bb);
+            lea_load8_at(sh + aw.i0, sPS, src.P, a);
+            lea_load8_at(sh + aw.i1, sPS, src.P, bb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) accd[j] += wh * (aw.l0 * a[j] + aw.l1 * bb[j]);
         }
@@ -179,7 +181,108 @@ lea_trilinear_ac_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c,
 #pragma unroll
         for (int j = 0; j < 8; ++j) out[j] = out[j] > 0.0f ? out[j] : 0.0f;
     }
-    lea_vol_store8(dst, b, (dst_c0 >> 3) + cb, d, h, w, out);
+    const int64_t dHW = (int64_t)dst.H * dst.W, dPS = dHW * dst.D;
+    lea_store8_at((lea_u4*)dst.data + ((int64_t)b * (dst.C >> 3) + (dst_c0 >> 3) + cb) * dst.P * dPS + d * dHW +
+                  (int64_t)h * dst.W + w, dPS, dst.P, out);
+}
+
+// Up-sampling variant: one thread owns an output column (h, w) of a chunk of LEA_UP_DCH depths and marches along d.
+// The (h, w)-interpolated values of the two low-res depth slices in use stay in registers; a new slice costs 4 corner
+// loads, and with out/in ~ 2 along d only every second output needs one -> ~5 loads per output instead of 16.
+// Same blend order (w, then h, then d) as the kernel above.
+#define LEA_UP_DCH 8
+struct lea_up_ctx {
+    const lea_u4* sbase;          // (b, channel block, plane 0, depth 0) of the source
+    int64_t sHW, sPS;             // source slice / plane strides in 16-byte groups
+    int o00, o01, o10, o11;       // the four (h, w) corners inside a slice
+    float wh0, wh1, ww0, ww1;
+    int P;
+};
+LEA_D void lea_up_slice(const lea_up_ctx& c, int id, float* o /*[8]*/) {
+    const lea_u4* sp = c.sbase + (int64_t)id * c.sHW;
+    float a[8], bb[8], e[8], g[8];
+    lea_load8_at(sp + c.o00, c.sPS, c.P, a);
+    lea_load8_at(sp + c.o01, c.sPS, c.P, bb);
+    lea_load8_at(sp + c.o10, c.sPS, c.P, e);
+    lea_load8_at(sp + c.o11, c.sPS, c.P, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float v = 0.0f;
+        v += c.wh0 * (c.ww0 * a[j] + c.ww1 * bb[j]);
+        v += c.wh1 * (c.ww0 * e[j] + c.ww1 * g[j]);
+        o[j] = v;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+lea_trilinear_ac_up_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c,
+                           const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int relu) {
+    const int w = blockIdx.x * 128 + threadIdx.x;
+    if (w >= dst.W) return;
+    const int h = blockIdx.y % dst.H, dch = blockIdx.y / dst.H;
+    const int cbn = c >> 3;
+    const int b = blockIdx.z / cbn, cb = blockIdx.z - b * cbn;
+    const lea_axis_lerp ah = lea_axis_ac(h, src.H, dst.H);
+    const lea_axis_lerp aw = lea_axis_ac(w, src.W, dst.W);
+    lea_up_ctx cx;
+    cx.sHW = (int64_t)src.H * src.W;
+    cx.sPS = cx.sHW * src.D;
+    cx.P = src.P;
+    cx.sbase = (const lea_u4*)src.data + ((int64_t)b * (src.C >> 3) + (src_c0 >> 3) + cb) * src.P * cx.sPS;
+    cx.o00 = ah.i0 * src.W + aw.i0; cx.o01 = ah.i0 * src.W + aw.i1;
+    cx.o10 = ah.i1 * src.W + aw.i0; cx.o11 = ah.i1 * src.W + aw.i1;
+    cx.wh0 = ah.l0; cx.wh1 = ah.l1; cx.ww0 = aw.l0; cx.ww1 = aw.l1;
+    const int64_t dHW = (int64_t)dst.H * dst.W, dPS = dHW * dst.D;
+    lea_u4* dbase = (lea_u4*)dst.data + ((int64_t)b * (dst.C >> 3) + (dst_c0 >> 3) + cb) * dst.P * dPS +
+                    (int64_t)h * dst.W + w;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = bn_scale ? __ldg(bn_scale + cb * 8 + j) : 1.0f;
+        sh[j] = bn_scale ? __ldg(bn_shift + cb * 8 + j) : 0.0f;
+    }
+    const float dscale = dst.D > 1 ? (float)(src.D - 1) / (float)(dst.D - 1) : 0.0f;      // as in lea_axis_ac
+    float A[8], Bv[8];
+    int cur0 = -1, cur1 = -1;
+    const int d_end = min(dst.D, (dch + 1) * LEA_UP_DCH);
+    for (int d = dch * LEA_UP_DCH; d < d_end; ++d) {
+        const float sd = dscale * (float)d;
+        int i0 = (int)floorf(sd);
+        if (i0 > src.D - 1) i0 = src.D - 1;
+        float l1 = sd - (float)i0;
+        l1 = l1 < 0.0f ? 0.0f : (l1 > 1.0f ? 1.0f : l1);
+        const int i1 = i0 + (i0 < src.D - 1 ? 1 : 0);
+        const float l0 = 1.0f - l1;
+        if (i0 != cur0) {
+            if (i0 == cur1) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) A[j] = Bv[j];
+            } else {
+                lea_up_slice(cx, i0, A);
+            }
+            cur0 = i0;
+        }
+        if (i1 != cur1) {
+            if (i1 == cur0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) Bv[j] = A[j];
+            } else {
+                lea_up_slice(cx, i1, Bv);
+            }
+            cur1 = i1;
+        }
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = 0.0f;
+            v += l0 * A[j];
+            v += l1 * Bv[j];
+            if (bn_scale) v = v * sc[j] + sh[j];
+            if (relu) v = v > 0.0f ? v : 0.0f;
+            out[j] = v;
+        }
+        lea_store8_at(dbase + (int64_t)d * dHW, dPS, dst.P, out);
+    }
 }
 
 // =========================================================================================================
@@ -514,6 +617,8 @@ lea_head_taps_w_kernel(lea_vol q, int q_c0, float* __restrict__ R, int W) {
     if (w >= W) return;
     const int j = blockIdx.y % q.H, i = blockIdx.y / q.H, b = blockIdx.z;
     const lea_up3 u = lea_up3_weights(w, q.W, W);
+    const int64_t PS = (int64_t)q.D * q.H * q.W, CBS = PS * q.P;           // plane / channel-block strides (groups)
+    const lea_u4* row = (const lea_u4*)q.data + ((int64_t)b * (q.C >> 3) + (q_c0 >> 3)) * CBS + ((int64_t)i * q.H + j) * q.W;
     float acc[9];
 #pragma unroll
     for (int c = 0; c < 9; ++c) acc[c] = 0.0f;
@@ -523,7 +628,7 @@ lea_head_taps_w_kernel(lea_vol q, int q_c0, float* __restrict__ R, int W) {
         const int k = min(u.base + m, q.W - 1);
         float t[32];
 #pragma unroll
-        for (int cb = 0; cb < 4; ++cb) lea_vol_load8(q, b, (q_c0 >> 3) + cb, i, j, k, t + cb * 8);
+        for (int cb = 0; cb < 4; ++cb) lea_load8_at(row + cb * CBS + k, PS, q.P, t + cb * 8);
 #pragma unroll
         for (int c = 0; c < 9; ++c)
 #pragma unroll
