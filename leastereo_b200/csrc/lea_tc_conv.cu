@@ -761,6 +761,20 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // two accumulator sets let the epilogue of item i overlap the MMAs of item i+1; when that would leave fewer than
     // 4 depth slices per item (wide N), one set with twice the depth wastes fewer halo slabs
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
+    if (p.nsets == 1 && 512 / (2 * accw) >= 2) {
+        // measured cost model (cycles): a slab costs M = groups * taps * terms * max(64, N/2) of tensor pipe, the
+        // epilogue E ~ 650 per 16 output channels and depth.  One set runs them back to back, two sets overlap them
+        // at the price of half the depth per item (more halo slabs).
+        const int taps2d = s.taps2d, halo = (p.ks == 3) ? 2 : 0;
+        const int nmax = (p.ks == 3 ? 3 : 1) * s.NP;
+        const double M = (double)s.ncg * taps2d * p.nterm * (nmax / 2 > 64 ? nmax / 2 : 64);
+        const double E = 650.0 * ((c->c_out + 15) / 16);
+        const int d1 = 512 / accw, d2 = 512 / (2 * accw);
+        const double t1 = ((d1 + halo) * M + d1 * E) / d1;
+        const double me = (d2 + halo) * M, ee = d2 * E;
+        const double t2 = (me > ee ? me : ee) / d2;
+        if (t2 < t1) p.nsets = 2;
+    }
     if (opts && (opts->acc_sets == 1 || opts->acc_sets == 2)) p.nsets = opts->acc_sets;
     // tile shape: 8 x 16 for k = 3 (the tap windows need the 8-row core-matrix groups to be rows of the slab); a
     // 1x1x1 conv has no halo, its slab is 128 consecutive rows whatever the shape, so it takes the widest tile the
