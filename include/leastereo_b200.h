@@ -95,7 +95,9 @@ typedef struct lea_tc_opts {
     int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
     const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
     int32_t resident_weights;  /* 0 = auto (all channel groups' weights stay in shared memory when they fit), 2 = never */
-    int32_t depth_chunk;       /* 1x1x1 convs only: 0 = auto, n = depth slices per work item (development knob) */
+    int32_t debug;             /* development switches of the rolling kernel's epilogue; 0 in production */
+    int32_t rolling;           /* k = 3: 1 = rolling accumulator ring (needs <= 85 TMEM columns per depth), 0 = chunked kernel (default) */
+    int32_t depth_chunk;       /* 0 = auto, n = depth slices per work item, clamped to what the schedule allows (test knob) */
     int32_t tile_w_log2;       /* 1x1x1 convs only: 0 = auto, 3..7 = tile of 2^n voxels along w by 128/2^n along h */
 } lea_tc_opts;
 int lea_conv3d_tc(const lea_conv* p, const void* wimg, const lea_tc_opts* opts, void* stream);

@@ -43,9 +43,14 @@ constexpr int kThreads = 192;
 constexpr int kMaxTerms = 6;
 constexpr int kMaxStages = 24;   // deep enough that 8 KB 1x1x1 stages keep ~1.5 us of HBM latency covered
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kHeaderBytes = 1024;
-static_assert(8 * (2 * kMaxStages + 8) + 4 <= 512, "barriers + TMEM slot must fit below the BN vectors at byte 512");
-constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;    // ~2 s: a stuck pipeline traps instead of hanging
+constexpr int kMaxRing = 32;       // rolling schedule: depth accumulators in flight (TMEM ring entries)
+constexpr int kHeaderBytes = 2048;
+static_assert(8 * (2 * kMaxStages + 8 + 2 * kMaxRing) <= 1024, "barriers must fit below the BN vectors at byte 1024");
+#ifdef LEA_TC_SOFT_TIMEOUT
+constexpr unsigned long long kWaitTimeoutCycles = 100000000ull;
+#else
+constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;
+#endif    // ~2 s: a stuck pipeline traps instead of hanging
 
 struct TcParams {
     int B, D, H, W;
@@ -63,6 +68,8 @@ struct TcParams {
     int slab_vox, pitch_vox, blk_bytes, stage_bytes, stage_stride;   // stride = bytes rounded up to 128 (TMA alignment)
     int nstages, nwbuf;
     int tw_log2;              // tile = (1 << tw_log2) voxels along w x (128 >> tw_log2) along h  (3 for k = 3)
+    int dbg;                  // development switches (bit 0: epilogue skips its stores, bit 1: skips the TMEM loads)
+    int roll, R;              // rolling schedule (see lea_conv_tc_roll_kernel): R home accumulator blocks + 2 alias blocks
     int wres;                 // 1 = the weight parts of ALL channel groups stay resident in shared memory (loaded once per CTA)
     int fused_cv, ncg_half;   // fused cost volume: channel groups [0,ncg_half) come from x, the rest from y(w-d)
     const CUtensorMap* cvmaps; // [2*D]: x maps for d = 0..D-1, then y maps
@@ -98,13 +105,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (mbarrier.test_wait never suspends the thread)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > kWaitTimeoutCycles) {
+#ifdef LEA_TC_SOFT_TIMEOUT
+            atomicCAS(&g_lea_tc_status, 0, code * 1000 + (int)(threadIdx.x));   // debug build: record the first stuck wait, go on
+            return;
+#else
             atomicExch(&g_lea_tc_status, code);
             __trap();
+#endif
         }
     }
 }
@@ -312,8 +334,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint64_t* wempty = wfull + 2;                   // [2]
     uint64_t* accfull = wempty + 2;                 // [2]
     uint64_t* accempty = accfull + 2;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty + 2);
-    float* s_scale = reinterpret_cast<float*>(smem + 512);      // [64]  (barriers occupy the first 8*(2*kMaxStages+8) B)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1536);
+    float* s_scale = reinterpret_cast<float*>(smem + 1024);     // [64]  (barriers occupy the first KB)
     float* s_shift = s_scale + 64;                              // [64]
     uint8_t* wbuf = smem + kHeaderBytes;
     const int wbuf_stride = (p.wpart_bytes + 127) & ~127;
@@ -408,6 +430,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per (kh,kw) / 16
         const uint32_t set_cols = (uint32_t)(p.ngroups * p.Dc * p.NP);
         int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
+        uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
+                                 // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
         if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const ItemGeom g = decode_item(p, item);
@@ -419,7 +443,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 if (!p.wres) mbar_wait(smem_u32(wfull + wb), wphase, 202);
                 const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
-                    mbar_wait(smem_u32(full + stage), sphase, 203);
+                    if (!probed) mbar_wait(smem_u32(full + stage), sphase, 203);
                     tc_fence_after();
                     const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
                     // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi)
@@ -465,6 +489,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 } else {
                                     tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_all, 1u);
                                 }
+                            }
+                            if (kh == 0 && kw == 0) {
+                                const bool wrap = (stage + 1 == p.nstages);
+                                probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
                             }
                         }
                     }
@@ -570,6 +598,317 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Rolling schedule (k = 3).  The chunked kernel above keeps the accumulators of a whole depth chunk in TMEM, so a
+// chunk is at most 512 / (columns per depth) slices long and pays two halo slabs - full-price MMAs that feed one
+// or two output depths instead of three - per chunk (x1.25 .. x1.5 tensor time), and its epilogue only overlaps
+// the next item with half of TMEM.  Here a work item is a depth range of ANY length.  The loops are slab-major
+// (for d_in: for channel group: 27 taps), so output depth d is complete as soon as slab d+1 has been issued, is
+// drained by the epilogue while the issuer continues with the next slabs, and its accumulator is reused R slabs
+// later: TMEM is a ring of R "home" blocks.  One tcgen05.mma still spans the three kd taps, i.e. three
+// ADJACENT blocks (depths d_in+1, d_in, d_in-1 in that order); at the ring's wrap this is kept contiguous by two
+// alias blocks: block 0 takes the part that belongs to home block R, block R+1 the part of home block 1, and the
+// epilogue adds an alias to its home.  With h(s) = home of slab s's centre depth (R, R-1, .., 1, R, ..):
+//     blocks h-1, h, h+1  <-  depths s+1, s, s-1;   h == 1: block 0 is the alias of depth s+1 (home R),
+//                                                    h == R: block R+1 is the alias of depth s-1 (home 1).
+// First writes (accumulate = 0): the kd=0 part always; all three parts when h == R (depth s's earlier part went to
+// alias 0, depth s-1's part goes to alias R+1); depth 0 at slab 0.  No extra MMAs, no halo except 2 slabs per ITEM.
+// ---------------------------------------------------------------------------------------------------------
+template <int NTERM, int PL>
+__global__ void __launch_bounds__(kThreads, 1)
+lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* full = bars;                          // [kMaxStages]
+    uint64_t* empty = bars + kMaxStages;            // [kMaxStages]
+    uint64_t* wfull = bars + 2 * kMaxStages;        // [2]
+    uint64_t* wempty = wfull + 2;                   // [2]
+    uint64_t* dfull = wempty + 6;                   // [kMaxRing]  depth complete (tcgen05.commit)
+    uint64_t* dempty = dfull + kMaxRing;            // [kMaxRing]  depth drained by the 128 epilogue threads
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1536);
+    float* s_scale = reinterpret_cast<float*>(smem + 1024);
+    float* s_shift = s_scale + 64;
+    uint8_t* wbuf = smem + kHeaderBytes;
+    const int wbuf_stride = (p.wpart_bytes + 127) & ~127;
+    uint8_t* stages = wbuf + (size_t)p.nwbuf * wbuf_stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int R = p.R;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1); }
+        for (int i = 0; i < R; ++i) { mbar_init(smem_u32(dfull + i), 1); mbar_init(smem_u32(dempty + i), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int n = threadIdx.x - 64;
+        s_scale[n] = (p.bn_scale && n < p.c_out) ? __ldg(p.bn_scale + n) : 1.0f;
+        s_shift[n] = (p.bn_shift && n < p.c_out) ? __ldg(p.bn_shift + n) : 0.0f;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    constexpr int kHalo = 1;
+    constexpr int kPitch = LEA_TC_TW + 2;
+
+    if (warp == 0) {
+        // ================= TMA producer: slab-major order =================
+        if (lane == 0) {
+            int stage = 0, sphase = 0, wb = 0, wphase = 0;
+            if (p.wres) {
+                mbar_arrive_expect_tx(smem_u32(wfull), (uint32_t)(p.ncg * p.wpart_bytes));
+                for (int cg = 0; cg < p.ncg; ++cg)
+                    bulk_load(smem_u32(wbuf + (size_t)cg * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
+                              (uint32_t)p.wpart_bytes, smem_u32(wfull));
+            }
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const ItemGeom g = decode_item(p, item);
+                const int gbase = g.b * p.g0_stride_b + p.g0_first;
+                for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
+                    for (int cg = 0; cg < p.ncg; ++cg) {
+                        if (!p.wres) {
+                            mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101);
+                            mbar_arrive_expect_tx(smem_u32(wfull + wb), (uint32_t)p.wpart_bytes);
+                            bulk_load(smem_u32(wbuf + (size_t)wb * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
+                                      (uint32_t)p.wpart_bytes, smem_u32(wfull + wb));
+                            if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                        }
+                        mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102);
+                        mbar_arrive_expect_tx(smem_u32(full + stage), (uint32_t)p.stage_bytes);
+                        if (p.fused_cv) {
+                            const bool left = cg < p.ncg_half;
+                            const CUtensorMap* m = p.cvmaps + (left ? 0 : p.D) + d_in;
+                            tma_load_3d(smem_u32(stages + (size_t)stage * p.stage_stride), m, smem_u32(full + stage),
+                                        (g.w0 - kHalo - d_in) * 8, g.h0 - kHalo,
+                                        gbase + (left ? cg : cg - p.ncg_half) * p.blocks_per_cg);
+                        } else {
+                            tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_stride), &tmap, smem_u32(full + stage),
+                                        (g.w0 - kHalo) * 8, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
+                        }
+                        if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t elected = elect_one();
+        const int nblk = R + 2;
+        uint32_t a_term16[NTERM], a_lbo_field[NTERM], b_term16[NTERM], reg_col[NTERM];
+        bool t_first[NTERM];
+#pragma unroll
+        for (int t = 0; t < NTERM; ++t) {
+            a_term16[t] = (uint32_t)(p.term_aoff[t] * p.blk_bytes) >> 4;
+            a_lbo_field[t] = ((uint32_t)(p.term_lbo_blocks[t] * p.blk_bytes) >> 4) << 16;
+            b_term16[t] = (uint32_t)(p.term_btile[t] * p.btile_bytes) >> 4;
+            reg_col[t] = (uint32_t)(p.term_region[t] * nblk * p.NP);
+            t_first[t] = p.term_first[t] != 0;
+        }
+        const uint32_t idesc1 = make_idesc(p.NP), idesc2 = make_idesc(2 * p.NP), idesc3 = make_idesc(3 * p.NP);
+        const uint32_t a_hi = (uint32_t)kPitch | (1u << 14);
+        const uint32_t b_hi = 8u | (1u << 14);
+        const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;
+        const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;
+        int stage = 0, sphase = 0, wb = 0, wphase = 0;
+        // Ring bookkeeping without divisions (this warp's instruction stream is what feeds the tensor pipe): depth
+        // number q = R + (depths of earlier items) + (d - d0) lives in entry q % R, generation q / R - 1; (e0, par0)
+        // = (q % R, (q / R) & 1) of the item's first depth, advanced per slab.
+        int e0 = 0, par0 = 1;
+        uint32_t probed = 0;
+        if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const ItemGeom g = decode_item(p, item);
+            int e = e0, par = par0;                    // entry / parity of slab d_in's centre depth
+            if (g.dlo < g.d0) { if (e == 0) { e = R - 1; par ^= 1; } else --e; }
+            for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
+                const int kd_a = (d_in + 1 <= g.d_hi - 1) ? 0 : ((d_in <= g.d_hi - 1) ? 1 : 2);
+                const int kd_b = (d_in - 1 >= g.d0) ? 2 : ((d_in >= g.d0) ? 1 : 0);
+                const int nkd = kd_b - kd_a + 1;
+                const int h = R - e;
+                const int e_up = (e + 1 == R) ? 0 : e + 1, par_up = (e + 1 == R) ? par ^ 1 : par;   // depth d_in+1
+                const int e_dn = (e == 0) ? R - 1 : e - 1;                                           // depth d_in-1
+                // acquire the ring entries of the depths this slab opens (drained one generation ago)
+                if (!(p.dbg & 4)) {
+                if (kd_a == 0) mbar_wait(smem_u32(dempty + e_up), par_up, 204);
+                if (d_in == 0 && kd_a <= 1 && kd_b >= 1) mbar_wait(smem_u32(dempty + e), par, 205);   // slab 0 opens depth 0
+                tc_fence_after();
+                }
+                int nfresh = 0;
+                for (int kd = kd_a; kd <= kd_b; ++kd) {
+                    const bool fr = (kd == 0) || (h == R) || (kd == 1 && d_in == 0);
+                    if (!fr) break;
+                    ++nfresh;
+                }
+                const uint32_t col0 = (uint32_t)((h - 1 + kd_a) * p.NP);
+                const uint32_t brow16 = (uint32_t)(kd_a * p.NP);
+                const uint32_t idesc_all = nkd == 3 ? idesc3 : (nkd == 2 ? idesc2 : idesc1);
+                for (int cg = 0; cg < p.ncg; ++cg) {
+                    if (!p.wres) mbar_wait(smem_u32(wfull + wb), wphase, 202);
+                    const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
+                    if (!probed) mbar_wait(smem_u32(full + stage), sphase, 203);
+                    tc_fence_after();
+                    const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
+                    const int nf = (cg == 0) ? nfresh : 0;
+                    const uint32_t idesc_fresh = nf == 3 ? idesc3 : (nf == 2 ? idesc2 : idesc1);
+                    const int nrest = nkd - nf;
+                    const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
+                            const uint32_t b_tap = w16 + (uint32_t)(kh * 3 + kw) * tap16 + brow16;
+#pragma unroll
+                            for (int t = 0; t < NTERM; ++t) {
+                                const uint32_t a_lo = (a_tap + a_term16[t]) | a_lbo_field[t];
+                                const uint32_t b_lo = b_tap + b_term16[t];
+                                const uint32_t dcol = tmem_base + reg_col[t] + col0;
+                                if (kh == 0 && kw == 0 && t_first[t] && nf > 0) {
+                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
+                                    if (nrest > 0)
+                                        tc_mma_issue(elected, dcol + (uint32_t)(nf * p.NP), a_lo, a_hi,
+                                                     b_lo + (uint32_t)(nf * p.NP), b_hi, idesc_rest, 1u);
+                                } else {
+                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_all, 1u);
+                                }
+                            }
+                            if (kh == 0 && kw == 0) {
+                                const bool wrap = (stage + 1 == p.nstages);
+                                probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
+                            }
+                        }
+                    }
+                    tc_commit_if(elected, smem_u32(empty + stage));
+                    if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                    if (!p.wres) {
+                        tc_commit_if(elected, smem_u32(wempty + wb));
+                        if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
+                    }
+                }
+                // depths completed by this slab
+                if (!(p.dbg & 8)) {
+                if (d_in - 1 >= g.d0) tc_commit_if(elected, smem_u32(dfull + e_dn));
+                if (d_in == p.D - 1 && d_in < g.d_hi) tc_commit_if(elected, smem_u32(dfull + e));
+                }
+                e = e_up; par = par_up;
+            }
+            e0 += g.d_hi - g.d0;
+            while (e0 >= R) { e0 -= R; par0 ^= 1; }
+        }
+    } else {
+        // ================= epilogue warps 2..5: one depth at a time, as they complete =================
+        const int qd = warp & 3;
+        const int m = qd * 32 + lane;
+        const int lh = m >> 3, lw = m & 7;
+        const int64_t sp = (int64_t)p.D * p.H * p.W;
+        const int nblk = R + 2;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
+        const uint32_t region1 = (uint32_t)(nblk * p.NP);
+        int e = 0, par = 1;                            // entry / parity of the next depth (see the issuer)
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const ItemGeom g = decode_item(p, item);
+            const int h_out = g.h0 + lh, w_out = g.w0 + lw;
+            const bool valid = (h_out < p.H) && (w_out < p.W);
+            for (int d = g.d0; d < g.d_hi; ++d) {
+                const int hb = R - e;
+                // residual operands do not depend on the MMAs: fetch them before waiting for the depth
+                uint4 rq[4][2][PL];
+                if (p.has_res && valid) {
+#pragma unroll
+                    for (int ci = 0; ci < 4; ++ci) {
+                        const int c16 = ci * 16;
+                        if (c16 < p.c_out) {
+                            ep_load_raw8<PL>(p.res, g.b, (p.res_c0 + c16) >> 3, d, h_out, w_out, rq[ci][0]);
+                            if (c16 + 8 < p.c_out)
+                                ep_load_raw8<PL>(p.res, g.b, ((p.res_c0 + c16) >> 3) + 1, d, h_out, w_out, rq[ci][1]);
+                        }
+                    }
+                }
+                if (!(p.dbg & 8)) mbar_wait(smem_u32(dfull + e), par ^ 1, 301);
+                tc_fence_after();
+                const bool alias_lo = (hb == R) && (d >= 1);           // part written into block 0 by slab d-1
+                const bool alias_hi = (hb == 1) && (d <= p.D - 2);     // part written into block R+1 by slab d+1
+                const uint32_t home = lane_base + (uint32_t)(hb * p.NP);
+                const uint32_t alias = lane_base + (uint32_t)((alias_lo ? 0 : R + 1) * p.NP);
+                const bool has_alias = alias_lo || alias_hi;
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int c16 = ci * 16;
+                    if (c16 >= p.c_out) break;
+                    const bool two = (c16 + 8 < p.c_out);
+                    float acc[16];
+                    {
+                        uint32_t ra[16], rb[16], rc[16], rd[16];
+                        if (p.dbg & 2) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) { ra[i] = 0; rb[i] = 0; rc[i] = 0; rd[i] = 0; }
+                        } else {
+                        tc_ld16_nowait(home + (uint32_t)c16, ra);
+                        if (p.ngroups == 2) tc_ld16_nowait(home + region1 + (uint32_t)c16, rb);
+                        }
+                        if (has_alias && !(p.dbg & 2)) {
+                            tc_ld16_nowait(alias + (uint32_t)c16, rc);
+                            if (p.ngroups == 2) tc_ld16_nowait(alias + region1 + (uint32_t)c16, rd);
+                        }
+                        tc_wait_ld();
+                        tc_touch16(ra);
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
+                        if (has_alias) {
+                            tc_touch16(rc);
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(rc[i]);
+                        }
+                        if (p.ngroups == 2) {
+                            tc_touch16(rb);
+                            if (has_alias) {
+                                tc_touch16(rd);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(rb[i]) + __uint_as_float(rd[i]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(rb[i]);
+                            }
+                        }
+                    }
+                    if (!valid || (p.dbg & 1)) continue;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
+                        if (p.relu) v = fmaxf(v, 0.0f);
+                        acc[i] = v;
+                    }
+                    if (p.dst_f32) {
+                        float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h_out) * p.W + w_out;
+                        for (int n = 0; n < 16 && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
+                    } else {
+                        if (p.has_res) {
+                            ep_add_raw8<PL>(rq[ci][0], acc);
+                            if (two) ep_add_raw8<PL>(rq[ci][1], acc + 8);
+                        }
+                        ep_store8<PL>(p.dst, g.b, (p.dst_c0 + c16) >> 3, d, h_out, w_out, acc);
+                        if (two) ep_store8<PL>(p.dst, g.b, ((p.dst_c0 + c16) >> 3) + 1, d, h_out, w_out, acc + 8);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(smem_u32(dempty + e));
+                if (++e == R) { e = 0; par ^= 1; }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 typedef void (*TcKernelFn)(const CUtensorMap, const TcParams);
 template <int KS>
 static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
@@ -582,6 +921,17 @@ static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
     if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 3>;
     if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3>;          // 8-channel layout, 3 planes
     return lea_conv_tc_kernel<KS, 6, 3>;                           // bf16x6
+}
+static TcKernelFn tc_roll_kernel_for(int nterm, int planes) {
+    if (planes == 1) return lea_conv_tc_roll_kernel<1, 1>;
+    if (planes == 2) {
+        if (nterm == 1) return lea_conv_tc_roll_kernel<1, 2>;
+        if (nterm == 2) return lea_conv_tc_roll_kernel<2, 2>;
+        return lea_conv_tc_roll_kernel<3, 2>;
+    }
+    if (nterm == 1) return lea_conv_tc_roll_kernel<1, 3>;
+    if (nterm == 3) return lea_conv_tc_roll_kernel<3, 3>;
+    return lea_conv_tc_roll_kernel<6, 3>;
 }
 static TcKernelFn tc_kernel_for(int ks, int nterm, int planes) {
     return ks == 3 ? tc_kernel_for_ks<3>(nterm, planes) : tc_kernel_for_ks<1>(nterm, planes);
@@ -797,8 +1147,19 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.stage_stride = (p.stage_bytes + 127) & ~127;
     p.tiles_w = (p.W + tile_w - 1) / tile_w;
     p.tiles_h = (p.H + tile_h - 1) / tile_h;
-    int dc_max = 512 / (p.nsets * accw);
-    if (dc_max > 16) dc_max = 16;
+    // rolling schedule (k = 3): ring of R home blocks + 2 alias blocks; needs some slack between the issuer and the
+    // epilogue (R >= 4), i.e. at most 85 accumulator columns per depth
+    p.R = 512 / accw - 2;
+    if (p.R > kMaxRing) p.R = kMaxRing;
+    // Opt-in (opts->rolling == 1).  Measured on B200 (tools/roll_perf.py, KITTI shapes, 4 pairs): the rolling kernel
+    // issues 28 % fewer MMAs for stem1 but its per-slab time is ~25 % longer (tcgen05.mma issue is synchronous with
+    // the tensor pipe - queue depth ~1 - so the ring's extra barrier traffic and the continuously running epilogue
+    // show up as pipe bubbles): stem1 498 vs 505 us, 16-ch ops 36 vs 33 us, 8-ch ops 204 vs 153 us.  Kept for the
+    // next round (needs an epilogue that does not disturb the issuer); the chunked kernel is the default.
+    p.roll = (p.ks == 3 && p.R >= 4 && opts && opts->rolling == 1) ? 1 : 0;
+    p.dbg = opts ? opts->debug : 0;
+    int dc_max = p.roll ? p.D : 512 / (p.nsets * accw);
+    if (!p.roll && dc_max > 16) dc_max = 16;
     if (dc_max > p.D) dc_max = p.D;
     const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
     // Depth slices per work item: an item of Dc slices streams Dc + 2*halo slabs at a fixed MMA cost per slab, and the
@@ -810,7 +1171,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         const int64_t cost = ((items + num_sms - 1) / num_sms) * (cand + (p.ks == 3 ? 2 : 0));
         if (best < 0 || cost < best || (cost == best && cand > Dc)) { best = cost; Dc = cand; }
     }
-    if (opts && opts->depth_chunk > 0 && p.ks == 1) Dc = opts->depth_chunk < dc_max ? opts->depth_chunk : dc_max;
+    if (opts && opts->depth_chunk > 0) Dc = opts->depth_chunk < dc_max ? opts->depth_chunk : dc_max;
     p.Dc = Dc;
     p.dchunks = (p.D + Dc - 1) / Dc;
     const int64_t total = (int64_t)p.B * p.dchunks * p.tiles_h * p.tiles_w;
@@ -854,7 +1215,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm, P);
+    TcKernelFn kernel = p.roll ? tc_roll_kernel_for(p.nterm, P) : tc_kernel_for(p.ks, p.nterm, P);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;

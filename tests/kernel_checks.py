@@ -223,10 +223,25 @@ TC_CASES = [
 ]
 
 
+# rolling schedule (k = 3): long work items so that the TMEM ring wraps and both alias blocks are used; the last
+# field forces the depth-chunk length (ring sizes: 32 -> 32 ch: 6 blocks, 16 -> 16: 14, 8 -> 8: 30)
+TC_ROLL_CASES = [
+    (1, 32, 0, 32, 32, 3, (19, 20, 12), True, True, False, 19),
+    (1, 32, 0, 32, 32, 3, (19, 20, 12), True, True, True, 7),       # chunks 7+7+5: sequence numbers carry across items
+    (2, 16, 0, 16, 16, 3, (40, 16, 8), True, True, True, 40),
+    (1, 16, 0, 16, 16, 3, (33, 16, 8), False, False, False, 15),
+    (1, 8, 0, 8, 8, 3, (70, 16, 8), True, True, True, 70),
+    (1, 64, 0, 64, 32, 3, (13, 16, 8), True, True, False, 13),      # weights streamed per slab and channel group
+    (1, 32, 0, 32, 1, 3, (21, 16, 8), False, False, False, 21),     # fp32 output
+    (1, 16, 0, 16, 48, 3, (6, 16, 8), True, True, False, 6),        # 96 columns per depth: chunked kernel, two sets
+]
+
+
 def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False):
     from leastereo_b200.kernels import lea_tc_opts
     worst = 0.0
-    for i, (B, ct, c0, ci, co, k, sp, bn, relu, res) in enumerate(cases or TC_CASES):
+    for i, case in enumerate(cases or TC_CASES):
+        (B, ct, c0, ci, co, k, sp, bn, relu, res), chunk = case[:10], (case[10] if len(case) > 10 else 0)
         if ops.tc_weight_image_bytes(ci, co, k, planes) <= 0:
             continue
 
@@ -234,6 +249,8 @@ def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False)
             img = ops.pack_weights_tc(w.contiguous(), planes)
             opts = lea_tc_opts()
             opts.mma_terms = mma_terms
+            opts.depth_chunk = chunk
+            opts.rolling = 1 if chunk else 0          # the TC_ROLL_CASES exercise the rolling-schedule kernel
             ops.conv3d_tc(p, img, opts, x)
 
         got, ref = _conv_case(ops, device, B, ct, c0, ci, co, k, sp, bn, relu, res, planes, 300 + 10 * i, fn)

@@ -82,6 +82,12 @@ def test_conv_tc(ops, planes):
     K.check_conv_tc(ops, DEV, planes=planes, verbose=True)
 
 
+@pytest.mark.parametrize("planes", [2, 3])
+def test_conv_tc_rolling_schedule(ops, planes):
+    worst = K.check_conv_tc(ops, DEV, planes=planes, cases=K.TC_ROLL_CASES, verbose=True)
+    print("worst relative error (rolling), planes", planes, worst)
+
+
 def test_conv_tc_single_pass(ops):
     K.check_conv_tc(ops, DEV, planes=2, mma_terms=1, verbose=True)
 
