@@ -11,7 +11,7 @@ from leastereo_b200.kernels import get_ops, PlanesVol, lea_tc_opts  # noqa: E402
 
 
 def main():
-    which = sys.argv[1:] or ["stem0", "l1res", "l1batched", "conv1", "l0res", "cv", "disp", "resample"]
+    which = sys.argv[1:] or ["stem0", "l1res", "l1batched", "conv1", "l0res", "cv", "disp", "resample", "headtaps", "pp64"]
     ops = get_ops()
     dev = torch.device("cuda:0")
     B, C, H3, W3, D3, maxdisp = 1, 32, 128, 416, 64, 192
@@ -50,7 +50,18 @@ def main():
         mat = torch.randn(B, D3, H3, W3, device=dev) * 3
         for _ in range(2):
             ops.disp_head(mat, maxdisp)
+    if "headtaps" in which:
+        q = PlanesVol.empty(B, 32, 2, 32, 64, 208, dev); q.t.copy_(torch.randn(q.t.shape, device=dev).bfloat16())
+        mat = torch.empty((B, 1, D3, H3, W3), device=dev)
+        ws = ops.head_taps_workspace(q, (D3, H3, W3))
+        for _ in range(2):
+            ops.head_taps(q, 0, mat, ws)
     if "resample" in which:
+        src = PlanesVol.empty(B, 32, 2, 64, 128, 416, dev); src.t.zero_()
+        dst = PlanesVol.empty(B, 32, 2, 32, 64, 208, dev)
+        for _ in range(2):
+            ops.trilinear_ac(src, 0, 32, dst, 0)          # down-sample (cells 0, 11)
+        del src, dst
         src = PlanesVol.empty(B, 32, 2, 32, 64, 208, dev); src.t.zero_()
         dst = PlanesVol.empty(B, 32, 2, 64, 128, 416, dev)
         for _ in range(2):
