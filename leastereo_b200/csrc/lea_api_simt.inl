@@ -139,9 +139,9 @@ extern "C" int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D
                              int32_t maxdisp, void* stream) {
     LEA_CHECK(mat && disp, "disp_head: null pointer");
     LEA_CHECK(B > 0 && D3 > 0 && H3 > 0 && W3 > 0 && maxdisp > 0 && B <= 65535, "disp_head: bad shape");
-    LEA_CHECK((H3 + LEA_DH_BY - 1) / LEA_DH_BY <= 65535, "disp_head: grid too large");
-    LEA_LAUNCH(lea_disp_head_kernel, dim3((W3 + LEA_DH_BX - 1) / LEA_DH_BX, (H3 + LEA_DH_BY - 1) / LEA_DH_BY, B),
-               dim3(LEA_DH_BX * LEA_DH_BY), 0, stream, mat, disp, D3, H3, W3, maxdisp);
+    LEA_CHECK(H3 <= 65535, "disp_head: grid too large");
+    LEA_LAUNCH(lea_disp_head_kernel, dim3((W3 + LEA_DH_CELLS - 1) / LEA_DH_CELLS, H3, B),
+               dim3(LEA_DH_CELLS * LEA_DH_PARTS), 0, stream, mat, disp, D3, H3, W3, maxdisp);
     return LEA_POST_LAUNCH();
 }
 
@@ -165,8 +165,15 @@ extern "C" int lea_head_taps(const lea_vol* q, int32_t q_c0, float* mat, int32_t
     float* S = workspace + (int64_t)q->B * 9 * q->D * q->H * W;
     const int gx = (W + 127) / 128;
     LEA_LAUNCH(lea_head_taps_w_kernel, dim3(gx, q->D * q->H, q->B), dim3(128), 0, stream, *q, q_c0, R, W);
-    LEA_LAUNCH(lea_head_taps_h_kernel, dim3(gx, q->D * H, q->B), dim3(128), 0, stream, R, S, q->D, q->H, H, W);
-    LEA_LAUNCH(lea_head_taps_d_kernel, dim3(gx, D * H, q->B), dim3(128), 0, stream, S, mat, q->D, D, H, W);
+    const bool vec = (W % 4 == 0) && ((((uintptr_t)workspace) & 15) == 0) && ((((uintptr_t)mat) & 15) == 0);
+    if (vec) {
+        const int gx4 = (W / 4 + 127) / 128;
+        LEA_LAUNCH(lea_head_taps_h_kernel<4>, dim3(gx4, q->D * H, q->B), dim3(128), 0, stream, R, S, q->D, q->H, H, W);
+        LEA_LAUNCH(lea_head_taps_d_kernel<4>, dim3(gx4, D * H, q->B), dim3(128), 0, stream, S, mat, q->D, D, H, W);
+    } else {
+        LEA_LAUNCH(lea_head_taps_h_kernel<1>, dim3(gx, q->D * H, q->B), dim3(128), 0, stream, R, S, q->D, q->H, H, W);
+        LEA_LAUNCH(lea_head_taps_d_kernel<1>, dim3(gx, D * H, q->B), dim3(128), 0, stream, S, mat, q->D, D, H, W);
+    }
     return LEA_POST_LAUNCH();
 }
 

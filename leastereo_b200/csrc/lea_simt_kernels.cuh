@@ -471,8 +471,10 @@ LEA_HD bool lea_three_tap(int c, int r, int in_n, float* t /*[3]*/) {
     return !(j0 < 0 || j0 > 2 || j1 < 0 || j1 > 2);
 }
 
-#define LEA_DH_BX 32
+#define LEA_DH_BX 32             // backward kernel (lea_train_kernels.cuh): one thread per cell, 32 x 4 cells per block
 #define LEA_DH_BY 4
+#define LEA_DH_CELLS 32          // low-res cells per 128-thread block (along w3)
+#define LEA_DH_PARTS 4           // lanes per cell: each owns a quarter of the disparity range
 
 // raw 3x3 neighbourhood of a cell at disparity sample k, and the 9 blended logits
 //   u[r*3+c] = sum_{i,j} th[r][i] * tw[c][j] * s[k][i][j]
@@ -493,13 +495,20 @@ LEA_HD bool lea_three_tap(int c, int r, int in_n, float* t /*[3]*/) {
                 u[r * 3 + c] = th[r][0] * row[0][c] + th[r][1] * row[1][c] + th[r][2] * row[2][c];    \
     }
 
-__global__ void __launch_bounds__(LEA_DH_BX * LEA_DH_BY)
+// Four adjacent lanes share one low-res cell (its 3x3 output pixels): each takes a quarter of the disparity range in
+// both passes, and the softmin is completed with warp shuffles (min of the stabiliser, sums of numerator/denominator).
+// 4x the threads of the one-thread-per-cell formulation: the kernel is latency-bound on its FMA/MUFU chains, so the
+// extra warps in flight are what buys time (measured 105 -> see DESIGN.md).  No early exit: every lane takes part in
+// the shuffles; lanes past the right edge work on the last column and do not store.
+__global__ void __launch_bounds__(LEA_DH_CELLS * LEA_DH_PARTS)
 lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
                      int D3, int H3, int W3, int maxdisp) {
-    const int w3 = blockIdx.x * LEA_DH_BX + threadIdx.x % LEA_DH_BX;
-    const int h3 = blockIdx.y * LEA_DH_BY + threadIdx.x / LEA_DH_BX;
+    const int part = threadIdx.x & (LEA_DH_PARTS - 1);
+    const int w3r = blockIdx.x * LEA_DH_CELLS + (threadIdx.x >> 2);
+    const int h3 = blockIdx.y;
     const int b = blockIdx.z;
-    if (w3 >= W3 || h3 >= H3) return;
+    const bool live = w3r < W3;
+    const int w3 = live ? w3r : W3 - 1;
     const float* __restrict__ mb = mat + (int64_t)b * D3 * H3 * W3;
     float th[3][3], tw[3][3];
 #pragma unroll
@@ -513,28 +522,37 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
         ww = ww < 0 ? 0 : (ww > W3 - 1 ? W3 - 1 : ww);
         ro[i] = hh * W3; wo[i] = ww;
     }
-    // pass 1: per-pixel minimum of the blended column (next sample prefetched while this one is reduced)
+    // pass 1: per-pixel minimum of the blended column; this lane's quarter of the samples, then min over the 4 lanes
     float m[9];
-    {
-        float u[9], cur[9], nxt[9];
-        LEA_DH_LOAD(cur, 0);
-        LEA_DH_COMBINE(u, cur);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) m[q] = u[q];
-        if (D3 > 1) LEA_DH_LOAD(cur, 1);
-        for (int k = 1; k < D3; ++k) {
-            if (k + 1 < D3) LEA_DH_LOAD(nxt, k + 1);
+    for (int q = 0; q < 9; ++q) m[q] = 3.0e38f;
+    {
+        const int kchunk = (D3 + LEA_DH_PARTS - 1) / LEA_DH_PARTS;
+        const int ka = min(D3, part * kchunk), kb = min(D3, ka + kchunk);
+        float u[9], cur[9], nxt[9];
+        if (ka < kb) LEA_DH_LOAD(cur, ka);
+        for (int k = ka; k < kb; ++k) {
+            if (k + 1 < kb) LEA_DH_LOAD(nxt, k + 1);
             LEA_DH_COMBINE(u, cur);
 #pragma unroll
             for (int q = 0; q < 9; ++q) { m[q] = u[q] < m[q] ? u[q] : m[q]; cur[q] = nxt[q]; }
         }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            float o = __shfl_xor_sync(0xffffffffu, m[q], 1);
+            m[q] = o < m[q] ? o : m[q];
+            o = __shfl_xor_sync(0xffffffffu, m[q], 2);
+            m[q] = o < m[q] ? o : m[q];
+        }
     }
-    // pass 2: stream the maxdisp samples; (k0, k1) window along disparity
+    // pass 2: this lane's quarter of the maxdisp output samples; (k0, k1) window along disparity
     float den[9], num[9], u0[9], u1[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) { den[q] = 0.0f; num[q] = 0.0f; u0[q] = 0.0f; u1[q] = 0.0f; }
     int kc = -1, k1c = -1;
-    for (int i = 0; i < maxdisp; ++i) {
+    const int ichunk = (maxdisp + LEA_DH_PARTS - 1) / LEA_DH_PARTS;
+    const int ia = min(maxdisp, part * ichunk), ib = min(maxdisp, ia + ichunk);
+    for (int i = ia; i < ib; ++i) {
         const lea_axis_lerp ad = lea_axis_half_pixel(i, D3, maxdisp);
         if (ad.i0 != kc) {
             if (ad.i0 == k1c) {
@@ -567,11 +585,23 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
             num[q] += e * fi;
         }
     }
-    float* __restrict__ o = disp + ((int64_t)b * 3 * H3 + 3 * h3) * (3 * W3) + 3 * w3;
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
+    for (int q = 0; q < 9; ++q) {
+        den[q] += __shfl_xor_sync(0xffffffffu, den[q], 1);
+        num[q] += __shfl_xor_sync(0xffffffffu, num[q], 1);
+        den[q] += __shfl_xor_sync(0xffffffffu, den[q], 2);
+        num[q] += __shfl_xor_sync(0xffffffffu, num[q], 2);
+    }
+    // lanes 0..2 of the cell write output rows 0..2
+    if (live && part < 3) {
+        float* __restrict__ o = disp + ((int64_t)b * 3 * H3 + 3 * h3 + part) * (3 * W3) + 3 * w3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) o[(int64_t)r * 3 * W3 + c] = num[r * 3 + c] / den[r * 3 + c];
+        for (int c = 0; c < 3; ++c) {
+            const float nn = part == 0 ? num[c] : (part == 1 ? num[3 + c] : num[6 + c]);
+            const float dd = part == 0 ? den[c] : (part == 1 ? den[3 + c] : den[6 + c]);
+            o[c] = nn / dd;
+        }
+    }
 }
 #undef LEA_DH_LOAD
 #undef LEA_DH_COMBINE
@@ -640,45 +670,80 @@ lea_head_taps_w_kernel(lea_vol q, int q_c0, float* __restrict__ R, int W) {
     for (int c = 0; c < 9; ++c) o[c * plane] = acc[c];
 }
 
+// stages h and d work on plain fp32 rows; VEC = 4 processes four consecutive w per thread with 128-bit accesses
+// (W % 4 == 0), VEC = 1 is the ragged-width variant.  Both were instruction-bound on address arithmetic, hence the
+// single base pointer + compile-time multiples of the plane stride.
+template <int VEC> struct lea_fvec;
+template <> struct lea_fvec<1> { float v[1]; };
+template <> struct __attribute__((aligned(16))) lea_fvec<4> { float v[4]; };
+
 // stage h: R (B, 9, D1, H1, W) -> S (B, 3, D1, H, W)
+template <int VEC>
 __global__ void __launch_bounds__(128)
 lea_head_taps_h_kernel(const float* __restrict__ R, float* __restrict__ S, int D1, int H1, int H, int W) {
-    const int w = blockIdx.x * 128 + threadIdx.x;
+    const int w = (blockIdx.x * 128 + threadIdx.x) * VEC;
     if (w >= W) return;
     const int h = blockIdx.y % H, i = blockIdx.y / H, b = blockIdx.z;
     const lea_up3 u = lea_up3_weights(h, H1, H);
-    float acc[3] = {0.0f, 0.0f, 0.0f};
+    const int64_t plane = (int64_t)D1 * H1 * W;                         // one (kd, kh) channel of R
+    const float* __restrict__ rb = R + (int64_t)b * 9 * plane + (int64_t)i * H1 * W + w;
+    float acc[3][VEC];
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd)
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[kd][e] = 0.0f;
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
         if (u.c[0][m] == 0.0f && u.c[1][m] == 0.0f && u.c[2][m] == 0.0f) continue;
-        const int jj = min(u.base + m, H1 - 1);
+        const float* __restrict__ rr = rb + (int64_t)min(u.base + m, H1 - 1) * W;
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-                acc[kd] += u.c[kh][m] * __ldg(R + ((((int64_t)b * 9 + kd * 3 + kh) * D1 + i) * H1 + jj) * W + w);
-    }
+            for (int kh = 0; kh < 3; ++kh) {
+                const lea_fvec<VEC> x = *reinterpret_cast<const lea_fvec<VEC>*>(rr + (kd * 3 + kh) * plane);
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd) S[((((int64_t)b * 3 + kd) * D1 + i) * H + h) * W + w] = acc[kd];
+                for (int e = 0; e < VEC; ++e) acc[kd][e] += u.c[kh][m] * x.v[e];
+            }
+    }
+    const int64_t splane = (int64_t)D1 * H * W;
+    float* __restrict__ so = S + (int64_t)b * 3 * splane + ((int64_t)i * H + h) * W + w;
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+        lea_fvec<VEC> o;
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o.v[e] = acc[kd][e];
+        *reinterpret_cast<lea_fvec<VEC>*>(so + kd * splane) = o;
+    }
 }
 
 // stage d: S (B, 3, D1, H, W) -> mat (B, 1, D, H, W)
+template <int VEC>
 __global__ void __launch_bounds__(128)
 lea_head_taps_d_kernel(const float* __restrict__ S, float* __restrict__ mat, int D1, int D, int H, int W) {
-    const int w = blockIdx.x * 128 + threadIdx.x;
+    const int w = (blockIdx.x * 128 + threadIdx.x) * VEC;
     if (w >= W) return;
     const int h = blockIdx.y % H, d = blockIdx.y / H, b = blockIdx.z;
     const lea_up3 u = lea_up3_weights(d, D1, D);
-    float acc = 0.0f;
+    const int64_t HW = (int64_t)H * W, splane = HW * D1;
+    const float* __restrict__ sb = S + (int64_t)b * 3 * splane + (int64_t)h * W + w;
+    float acc[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) acc[e] = 0.0f;
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
         if (u.c[0][m] == 0.0f && u.c[1][m] == 0.0f && u.c[2][m] == 0.0f) continue;
-        const int ii = min(u.base + m, D1 - 1);
+        const float* __restrict__ sr = sb + (int64_t)min(u.base + m, D1 - 1) * HW;
 #pragma unroll
-        for (int kd = 0; kd < 3; ++kd)
-            acc += u.c[kd][m] * __ldg(S + ((((int64_t)b * 3 + kd) * D1 + ii) * H + h) * W + w);
+        for (int kd = 0; kd < 3; ++kd) {
+            const lea_fvec<VEC> x = *reinterpret_cast<const lea_fvec<VEC>*>(sr + kd * splane);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[e] += u.c[kd][m] * x.v[e];
+        }
     }
-    mat[(((int64_t)b * D + d) * H + h) * W + w] = acc;
+    lea_fvec<VEC> o;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) o.v[e] = acc[e];
+    *reinterpret_cast<lea_fvec<VEC>*>(mat + (((int64_t)b * D + d) * H + h) * W + w) = o;
 }
 
 // DisparityRegression alone (models/build_model_2d.py:36-41)

@@ -33,6 +33,17 @@ extern unsigned char* emu_dyn_smem;
 static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
 #include <atomic>
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
+// warp shuffle for the emulator: every thread of the block must call it (the kernels that use it have no early exit);
+// values are exchanged through a per-block scratch array between two block-wide barriers
+extern float emu_shfl_scratch[1024];
+static inline float __shfl_xor_sync(unsigned, float v, int lane_mask) {
+    const unsigned t = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    emu_shfl_scratch[t] = v;
+    emu_barrier->arrive_and_wait();
+    const float r = emu_shfl_scratch[t ^ (unsigned)lane_mask];
+    emu_barrier->arrive_and_wait();
+    return r;
+}
 using std::min;
 using std::max;
 

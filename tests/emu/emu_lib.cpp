@@ -6,6 +6,7 @@
 thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 thread_local std::barrier<>* emu_barrier = nullptr;
 unsigned char* emu_dyn_smem = nullptr;
+float emu_shfl_scratch[1024];
 
 void emu_launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
     const unsigned nthreads = block.x * block.y * block.z;
