@@ -165,6 +165,30 @@ int lea_cost_volume_bwd(const lea_vol* dcost, int32_t C, float* dx, float* dy, v
 int lea_disp_head_bwd(const float* mat, const float* gout, float* dmat, int32_t B, int32_t D3, int32_t H3, int32_t W3,
                       int32_t maxdisp, void* stream);
 
+/* ---- callers on either side of the path -------------------------------------------------- */
+/* Input side, predict.py:144-184 / dataloaders/datasets/common.py:119-131: per-channel z-normalisation of an 8-bit RGB
+ * image in HWC order (PIL's layout) and test_transform's pad (image bottom-right on zeros) or centre crop to
+ * crop_h x crop_w.  Two launches: exact 64-bit sums (sums[0..2] = sum x, sums[3..5] = sum x^2 per channel; zero them
+ * first), then out (3, crop_h, crop_w) fp32 = ((double)x - mean) / std with the population std, like np.std.
+ * The 8-bit image is what crosses PCIe (4x fewer bytes than the fp32 tensor the reference uploads). */
+int lea_image_stats_u8(const uint8_t* img_hwc, int32_t H, int32_t W, uint64_t* sums6, void* stream);
+int lea_normalize_pad_u8(const uint8_t* img_hwc, int32_t H, int32_t W, const uint64_t* sums6, float* out,
+                         int32_t crop_h, int32_t crop_w, void* stream);
+/* Training loss, train.py:116-118,157,162: F.smooth_l1_loss(disp[mask], target[mask], 'mean') with
+ * mask = 0.001 < target < maxdisp.  acc3 (zeroed by the caller) += {sum loss, sum |disp - target|, #valid};
+ * the backward writes grad = mask * clamp(disp - target, -1, 1) * upstream / #valid reading #valid from acc3 on the
+ * device (no host synchronisation between forward and backward). */
+int lea_masked_smooth_l1(const float* disp, const float* target, int64_t n, float maxdisp, double* acc3, void* stream);
+int lea_masked_smooth_l1_bwd(const float* disp, const float* target, int64_t n, float maxdisp, const double* acc3,
+                             float upstream, float* grad, void* stream);
+/* optim.Adam(lr, betas=(0.9, 0.999)) of train.py:76 as one launch over a flat fp32 parameter buffer; step >= 1. */
+int lea_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, int32_t step, void* stream);
+/* utils/metrics.py:6-46 in one pass: acc7 (zeroed by the caller) += {#valid, sum |d| (EPE), #3-px-correct
+ * (|d| < 3 or |d| < 0.05 target), #(|d| <= thresholds4[0..3])}; bad-N fraction = 1 - acc[3+k] / acc[0]. */
+int lea_disparity_metrics(const float* pred, const float* target, int64_t n, float maxdisp, const float* thresholds4,
+                          double* acc7, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

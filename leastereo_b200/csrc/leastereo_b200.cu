@@ -21,5 +21,7 @@ static int lea_post_launch(const char* what) {
 
 #include "lea_simt_kernels.cuh"
 #include "lea_train_kernels.cuh"
+#include "lea_io_kernels.cuh"
 #include "lea_api_simt.inl"
 #include "lea_api_train.inl"
+#include "lea_api_io.inl"

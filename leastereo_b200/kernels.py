@@ -68,6 +68,12 @@ SYMBOLS = {
     "lea_trilinear_ac_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp]),
     "lea_cost_volume_bwd": (C.c_int, [_VOLP, _i32, _vp, _vp, _vp]),
     "lea_disp_head_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "lea_image_stats_u8": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
+    "lea_normalize_pad_u8": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp]),
+    "lea_masked_smooth_l1": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, _vp]),
+    "lea_masked_smooth_l1_bwd": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, C.c_float, _vp, _vp]),
+    "lea_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, _i32, _vp]),
+    "lea_disparity_metrics": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, _vp, _vp]),
 }
 # symbols only the CUDA build has (tcgen05 path); the CPU emulation used by the no-GPU tests lacks them
 DEVICE_ONLY = {"lea_tc_weight_image_bytes", "lea_pack_weights_tc", "lea_conv3d_tc", "lea_tc_selftest",
@@ -404,6 +410,73 @@ class Ops:
             self._check(self.lib.lea_disp_head_bwd(mat.data_ptr(), gout.data_ptr(), dmat.data_ptr(), B, D3, H3, W3,
                                                    int(maxdisp), self._stream(mat)))
         return dmat
+
+    # ---- callers on either side of the path ----------------------------------------------
+    def normalize_pad_u8(self, img_hwc: torch.Tensor, crop_h: int, crop_w: int, out: Optional[torch.Tensor] = None,
+                         sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 (H, W, 3) image -> z-normalised, padded / centre-cropped fp32 (3, crop_h, crop_w)
+        (predict.py:144-184)."""
+        self._dev(img_hwc)
+        assert img_hwc.dtype == torch.uint8 and img_hwc.dim() == 3 and img_hwc.shape[2] == 3 and img_hwc.is_contiguous()
+        H, W = int(img_hwc.shape[0]), int(img_hwc.shape[1])
+        if sums is None:
+            sums = torch.zeros(6, dtype=torch.int64, device=img_hwc.device)
+        else:
+            sums.zero_()
+        if out is None:
+            out = torch.empty((3, crop_h, crop_w), dtype=torch.float32, device=img_hwc.device)
+        assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (3, crop_h, crop_w)
+        with self._dev_ctx(img_hwc):
+            st = self._stream(img_hwc)
+            self._check(self.lib.lea_image_stats_u8(img_hwc.data_ptr(), H, W, sums.data_ptr(), st))
+            self._check(self.lib.lea_normalize_pad_u8(img_hwc.data_ptr(), H, W, sums.data_ptr(), out.data_ptr(),
+                                                      crop_h, crop_w, st))
+        return out
+
+    def masked_smooth_l1(self, disp: torch.Tensor, target: torch.Tensor, maxdisp: float) -> torch.Tensor:
+        """float64 [sum loss, sum |d|, #valid] over mask = 0.001 < target < maxdisp (train.py:116-118,157,162)."""
+        disp, target = self._f32(disp), self._f32(target)
+        self._dev(disp, target)
+        assert disp.shape == target.shape
+        acc = torch.zeros(3, dtype=torch.float64, device=disp.device)
+        with self._dev_ctx(disp):
+            self._check(self.lib.lea_masked_smooth_l1(disp.data_ptr(), target.data_ptr(), disp.numel(), float(maxdisp),
+                                                      acc.data_ptr(), self._stream(disp)))
+        return acc
+
+    def masked_smooth_l1_bwd(self, disp: torch.Tensor, target: torch.Tensor, maxdisp: float, acc: torch.Tensor,
+                             upstream: float = 1.0) -> torch.Tensor:
+        disp, target = self._f32(disp), self._f32(target)
+        self._dev(disp, target, acc)
+        grad = torch.empty_like(disp)
+        with self._dev_ctx(disp):
+            self._check(self.lib.lea_masked_smooth_l1_bwd(disp.data_ptr(), target.data_ptr(), disp.numel(),
+                                                          float(maxdisp), acc.data_ptr(), float(upstream),
+                                                          grad.data_ptr(), self._stream(disp)))
+        return grad
+
+    def adam_step(self, param: torch.Tensor, grad: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor,
+                  lr: float, beta1: float, beta2: float, eps: float, step: int):
+        self._dev(param, grad, exp_avg, exp_avg_sq)
+        for t in (param, grad, exp_avg, exp_avg_sq):
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == param.numel()
+        with self._dev_ctx(param):
+            self._check(self.lib.lea_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(),
+                                               exp_avg_sq.data_ptr(), param.numel(), float(lr), float(beta1),
+                                               float(beta2), float(eps), int(step), self._stream(param)))
+
+    def disparity_metrics(self, pred: torch.Tensor, target: torch.Tensor, maxdisp: float,
+                          thresholds=(1.0, 2.0, 3.0, 5.0)) -> torch.Tensor:
+        """float64 [#valid, sum |d|, #3-px-correct, #(|d| <= thr_k) x4] (utils/metrics.py:6-46); device tensor."""
+        pred, target = self._f32(pred), self._f32(target)
+        self._dev(pred, target)
+        assert pred.shape == target.shape and len(thresholds) == 4
+        acc = torch.zeros(7, dtype=torch.float64, device=pred.device)
+        thr = (C.c_float * 4)(*[float(t) for t in thresholds])
+        with self._dev_ctx(pred):
+            self._check(self.lib.lea_disparity_metrics(pred.data_ptr(), target.data_ptr(), pred.numel(), float(maxdisp),
+                                                       thr, acc.data_ptr(), self._stream(pred)))
+        return acc
 
     def disparity_regression(self, p: torch.Tensor, maxdisp: int) -> torch.Tensor:
         p = self._f32(p)

@@ -33,6 +33,10 @@ extern unsigned char* emu_dyn_smem;
 static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
 #include <atomic>
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
+static inline double atomicAdd(double* p, double v) { return std::atomic_ref<double>(*p).fetch_add(v, std::memory_order_relaxed); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+    return std::atomic_ref<unsigned long long>(*p).fetch_add(v, std::memory_order_relaxed);
+}
 // warp shuffle for the emulator: every thread of the block must call it (the kernels that use it have no early exit);
 // values are exchanged through a per-block scratch array between two block-wide barriers
 extern float emu_shfl_scratch[1024];

@@ -42,5 +42,7 @@ extern "C" int lea_is_device_build(void) { return 0; }
 #define LEA_POST_LAUNCH() 0
 #include "../../leastereo_b200/csrc/lea_simt_kernels.cuh"
 #include "../../leastereo_b200/csrc/lea_train_kernels.cuh"
+#include "../../leastereo_b200/csrc/lea_io_kernels.cuh"
 #include "../../leastereo_b200/csrc/lea_api_simt.inl"
 #include "../../leastereo_b200/csrc/lea_api_train.inl"
+#include "../../leastereo_b200/csrc/lea_api_io.inl"

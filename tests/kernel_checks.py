@@ -289,3 +289,90 @@ def check_feature_plan(ops, device, name="cal_46x94_d50", planes=3, conv="simt",
     assert got.shape == want.shape
     assert err <= tol, err
     return err
+
+
+# ---------------------------------------------------------------------------------------------------------
+# callers on either side of the path: input normalisation, loss, Adam, metrics
+# ---------------------------------------------------------------------------------------------------------
+def check_normalize_pad(ops, device):
+    """lea_image_stats_u8 + lea_normalize_pad_u8 against predict.py:144-184 restated in oracle/io_oracle.py."""
+    from oracle import io_oracle as IO
+    g = np.random.RandomState(7)
+    for (h, w, ch, cw) in [(20, 30, 24, 36), (20, 30, 20, 30), (20, 30, 16, 24), (37, 53, 24, 48), (5, 300, 8, 512)]:
+        left = g.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        right = g.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        left[:, :, 1] //= 4                                  # a low-contrast channel
+        want_l, want_r = IO.test_transform(IO.normalize_pair(left, right), ch, cw)
+        got_l = ops.normalize_pad_u8(torch.from_numpy(left).to(device), ch, cw).cpu().numpy()
+        got_r = ops.normalize_pad_u8(torch.from_numpy(right).to(device), ch, cw).cpu().numpy()
+        assert got_l.shape == want_l.shape[1:]
+        assert float(np.abs(got_l - want_l[0]).max()) <= 2e-6, (h, w, ch, cw)
+        assert float(np.abs(got_r - want_r[0]).max()) <= 2e-6, (h, w, ch, cw)
+
+
+def _loss_case(device, seed=3, shape=(2, 17, 23), maxdisp=48.0):
+    g = torch.Generator().manual_seed(seed)
+    target = torch.rand(shape, generator=g) * maxdisp * 1.2            # some beyond maxdisp
+    target[torch.rand(shape, generator=g) < 0.2] = 0.0                 # occlusions
+    disp = target + torch.randn(shape, generator=g) * 1.5              # both smooth-L1 branches
+    return disp.to(device), target.to(device), maxdisp
+
+
+def check_masked_smooth_l1(ops, device):
+    from oracle import io_oracle as IO
+    disp, target, maxdisp = _loss_case(device)
+    acc = ops.masked_smooth_l1(disp, target, maxdisp).cpu()
+    d_ref = disp.detach().cpu().clone().requires_grad_(True)
+    want = IO.masked_smooth_l1(d_ref, target.cpu(), maxdisp)
+    want.backward()
+    mask = (target.cpu() < maxdisp) & (target.cpu() > 0.001)
+    assert int(acc[2]) == int(mask.sum())
+    wv = float(want.detach())
+    assert abs(float(acc[0] / acc[2]) - wv) <= 1e-6 * max(1.0, abs(wv))
+    assert abs(float(acc[1] / acc[2]) - float((disp.cpu() - target.cpu())[mask].abs().mean())) <= 1e-5
+    grad = ops.masked_smooth_l1_bwd(disp, target, maxdisp, acc.to(device), 1.0).cpu()
+    assert float((grad - d_ref.grad).abs().max()) <= 1e-8
+    # no valid pixel: zero gradient, no NaN
+    z = torch.zeros_like(target)
+    acc0 = ops.masked_smooth_l1(disp, z, maxdisp)
+    assert float(acc0[2]) == 0.0
+    assert float(ops.masked_smooth_l1_bwd(disp, z, maxdisp, acc0, 1.0).abs().max()) == 0.0
+
+
+def check_adam(ops, device):
+    """FlatAdam (one lea_adam_step launch over the flat buffer) against torch.optim.Adam (train.py:76)."""
+    from leastereo_b200.pipeline import FlatAdam, multistep_lr
+    g = torch.Generator().manual_seed(11)
+    shapes = [(4, 3, 3, 3, 3), (7,), (5, 6)]
+    ours = [torch.nn.Parameter(torch.randn(s, generator=g).to(device)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().cpu().clone()) for p in ours]
+    opt = FlatAdam(ours, lr=1e-3, betas=(0.9, 0.999), ops=ops)
+    ropt = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999))
+    for step in range(6):
+        opt.zero_grad(); ropt.zero_grad()
+        for p, r in zip(ours, ref):
+            gr = torch.randn(p.shape, generator=g) * (10.0 ** (step - 3))
+            r.grad = gr.clone()
+            if step % 2 == 0:
+                p.grad.copy_(gr.to(device))                  # accumulate into the flat bucket (what autograd does)
+            else:
+                p.grad = gr.to(device)                       # a foreign .grad tensor: gathered by step()
+        opt.step(); ropt.step()
+        for p, r in zip(ours, ref):
+            assert float((p.detach().cpu() - r.detach()).abs().max()) <= 2e-6 * max(1.0, float(r.abs().max())), step
+    assert multistep_lr(1e-3, 0, [30, 50]) == 1e-3 and multistep_lr(1e-3, 30, [30, 50]) == 5e-4
+    assert multistep_lr(1e-3, 70, [30, 50]) == 2.5e-4
+
+
+def check_disparity_metrics(ops, device):
+    from oracle import io_oracle as IO
+    from leastereo_b200.pipeline import disparity_metrics
+    disp, target, maxdisp = _loss_case(device, seed=5, shape=(3, 31, 29), maxdisp=96.0)
+    disp = disp + (torch.rand(disp.shape) < 0.1).to(device) * 7.0          # some gross errors
+    got = disparity_metrics(disp, target, maxdisp, (1.0, 2.0, 3.0, 5.0), ops=ops)
+    p, t = disp.cpu().numpy(), target.cpu().numpy()
+    assert got["valid"] == int(IO.validity_mask(t, maxdisp).sum())
+    assert abs(got["epe"] - IO.epe(p, t, maxdisp)) <= 1e-5
+    assert abs(got["three_px_error"] - IO.three_px_error(p, t, maxdisp)) <= 1e-12
+    for thr in (1.0, 2.0, 3.0, 5.0):
+        assert abs(got["bad_%g" % thr] - IO.bad_pixel_frac(p, t, maxdisp, thr)) <= 1e-12

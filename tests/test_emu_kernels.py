@@ -23,7 +23,8 @@ def emu_ops():
         pytest.skip("g++ not available")
     srcs = [os.path.join(EMU_DIR, "emu_lib.cpp"), os.path.join(EMU_DIR, "cuda_emu.h")] + \
         [os.path.join(ROOT, "leastereo_b200", "csrc", f) for f in
-         ("lea_common.h", "lea_simt_kernels.cuh", "lea_api_simt.inl")]
+         ("lea_common.h", "lea_simt_kernels.cuh", "lea_api_simt.inl", "lea_train_kernels.cuh", "lea_api_train.inl",
+          "lea_io_kernels.cuh", "lea_api_io.inl")]
     if not os.path.exists(EMU_LIB) or any(os.path.getmtime(s) > os.path.getmtime(EMU_LIB) for s in srcs):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-DLEA_CPU_EMU", "-Wno-unknown-pragmas",
                                "-I" + EMU_DIR, "-o", EMU_LIB, srcs[0], "-lpthread"])
@@ -90,3 +91,20 @@ def test_native_feature_net(emu_ops):
     # ragged image size (46x94): partial tiles, stride-3 stem with H, W not multiples of 3
     err = K.check_feature_plan(emu_ops, DEV, "cal_46x94_d50", planes=3, conv="simt")
     print("native feature net vs reference feature maps: rel err", err)
+
+
+# ---- callers on either side of the path ------------------------------------------------
+def test_normalize_pad(emu_ops):
+    K.check_normalize_pad(emu_ops, DEV)
+
+
+def test_masked_smooth_l1(emu_ops):
+    K.check_masked_smooth_l1(emu_ops, DEV)
+
+
+def test_flat_adam(emu_ops):
+    K.check_adam(emu_ops, DEV)
+
+
+def test_disparity_metrics(emu_ops):
+    K.check_disparity_metrics(emu_ops, DEV)

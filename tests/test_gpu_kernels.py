@@ -241,3 +241,49 @@ def test_full_forward_native_vs_golden(ops, name):
     rep = O.tolerance_report(d.cpu(), torch.from_numpy(g["disp"]))
     print(name, rep)
     assert rep["ok"], rep
+
+
+# ---- callers on either side of the path ------------------------------------------------
+def test_normalize_pad(ops):
+    K.check_normalize_pad(ops, DEV)
+
+
+def test_masked_smooth_l1(ops):
+    K.check_masked_smooth_l1(ops, DEV)
+    # the autograd wrapper used by a training script
+    from leastereo_b200.pipeline import masked_smooth_l1_loss
+    from oracle import io_oracle as IO
+    disp, target, maxdisp = K._loss_case(DEV, seed=9)
+    d = disp.clone().requires_grad_(True)
+    loss = masked_smooth_l1_loss(d, target, maxdisp)
+    (loss * 3.0).backward()
+    r = disp.detach().cpu().clone().requires_grad_(True)
+    want = IO.masked_smooth_l1(r, target.cpu(), maxdisp)
+    (want * 3.0).backward()
+    assert abs(float(loss) - float(want)) <= 1e-6 and float((d.grad.cpu() - r.grad).abs().max()) <= 1e-7
+
+
+def test_flat_adam(ops):
+    K.check_adam(ops, DEV)
+
+
+def test_disparity_metrics(ops):
+    K.check_disparity_metrics(ops, DEV)
+
+
+def test_input_pipeline_double_buffer(ops):
+    """InputPipeline: pinned uint8 uploads on a side stream, normalised on the compute stream; KITTI-sized pairs."""
+    import numpy as np
+    from oracle import io_oracle as IO
+    from leastereo_b200.pipeline import InputPipeline
+    g = np.random.RandomState(1)
+    H, W, ch, cw = 75, 124, 96, 144
+    pairs = [(g.randint(0, 256, (H, W, 3)).astype(np.uint8), g.randint(0, 256, (H, W, 3)).astype(np.uint8)) for _ in range(5)]
+    pipe = InputPipeline(H, W, ch, cw, DEV, depth=2)
+    pipe.submit(*pairs[0])
+    for k in range(5):
+        if k + 1 < 5:
+            pipe.submit(*pairs[k + 1])
+        left, right = pipe.next()
+        wl, wr = IO.test_transform(IO.normalize_pair(*pairs[k]), ch, cw)
+        assert float(np.abs(left.cpu().numpy() - wl).max()) <= 2e-6 and float(np.abs(right.cpu().numpy() - wr).max()) <= 2e-6
