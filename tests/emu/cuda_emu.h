@@ -12,6 +12,7 @@
 #include <cmath>
 
 struct dim3 { unsigned x, y, z; dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {} };
+struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r{a, b, c, d}; return r; }
 
