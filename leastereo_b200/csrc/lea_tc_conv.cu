@@ -39,7 +39,12 @@
 
 namespace {
 
-constexpr int kThreads = 192;
+// Epilogue warps: one per TMEM lane quarter.  Measured: two per quarter (alternate depth batches) speed up only the
+// 8-channel layers (155 -> 139 us) and lose overall (174 -> 170 pairs/s): 10 warps put three warps on one SM
+// sub-partition (16 K registers), capping the kernel at 168 registers per thread.
+__host__ __device__ constexpr int epi_warps(int planes) { return planes == 3 ? 4 : 4; }
+__host__ __device__ constexpr int tc_threads(int planes) { return 64 + 32 * epi_warps(planes); }
+constexpr int kThreads = 192;       // rolling kernel: 4 epilogue warps
 constexpr int kMaxTerms = 6;
 constexpr int kMaxStages = 24;   // deep enough that 8 KB 1x1x1 stages keep ~1.5 us of HBM latency covered
 constexpr int kSmemBudget = 227 * 1024;
@@ -323,7 +328,7 @@ __device__ __forceinline__ void tc_touch16(uint32_t* r) {
 }
 
 template <int KS, int NTERM, int PL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(tc_threads(PL), 1)
 lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // header: barriers, TMEM base, BN scale/shift
@@ -347,7 +352,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1);
-            mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 128);
+            mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 32 * epi_warps(PL));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -523,7 +528,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const bool valid = (h < p.H) && (w < p.W);
             const int nd = g.d_hi - g.d0;
             bool waited = false;
-            for (int j0 = 0; j0 < nd; j0 += kJB) {
+            for (int j0 = ((warp - 2) >> 2) * kJB; j0 < nd; j0 += (epi_warps(PL) / 4) * kJB) {
                 for (int c16 = 0; c16 < p.c_out; c16 += 16) {
                     const bool two = (c16 + 8 < p.c_out);
                     uint4 rq[kJB][2][PL];
@@ -586,6 +591,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         }
                     }
                 }
+            }
+            if (!waited) {        // a warp group without a depth batch in this item still paces itself on the item
+                mbar_wait(smem_u32(accfull + set), aphase, 302);
+                tc_fence_after();
             }
             tc_fence_before();
             mbar_arrive(smem_u32(accempty + set));
@@ -801,7 +810,7 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
             e0 += g.d_hi - g.d0;
             while (e0 >= R) { e0 -= R; par0 ^= 1; }
         }
-    } else {
+    } else if (warp < 6) {
         // ================= epilogue warps 2..5: one depth at a time, as they complete =================
         const int qd = warp & 3;
         const int m = qd * 32 + lane;
@@ -1110,14 +1119,15 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // short reductions: keep two accumulator sets so that the epilogue overlaps the next item's MMAs
     // two accumulator sets let the epilogue of item i overlap the MMAs of item i+1; when that would leave fewer than
     // 4 depth slices per item (wide N), one set with twice the depth wastes fewer halo slabs
+    // One or two TMEM accumulator sets.  Two sets let the epilogue of item i overlap the MMAs of item i+1 at half the
+    // depth per item (more halo slabs); when that leaves fewer than 4 depths a measured cycle model decides: a slab
+    // costs M = groups * taps * terms * max(64, N/2) cycles of tensor pipe, the epilogue E ~ 650 cycles per 16 output
+    // channels and depth.
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
     if (p.nsets == 1 && 512 / (2 * accw) >= 2) {
-        // measured cost model (cycles): a slab costs M = groups * taps * terms * max(64, N/2) of tensor pipe, the
-        // epilogue E ~ 650 per 16 output channels and depth.  One set runs them back to back, two sets overlap them
-        // at the price of half the depth per item (more halo slabs).
-        const int taps2d = s.taps2d, halo = (p.ks == 3) ? 2 : 0;
+        const int halo = (p.ks == 3) ? 2 : 0;
         const int nmax = (p.ks == 3 ? 3 : 1) * s.NP;
-        const double M = (double)s.ncg * taps2d * p.nterm * (nmax / 2 > 64 ? nmax / 2 : 64);
+        const double M = (double)s.ncg * s.taps2d * p.nterm * (nmax / 2 > 64 ? nmax / 2 : 64);
         const double E = 650.0 * ((c->c_out + 15) / 16);
         const int d1 = 512 / accw, d2 = 512 / (2 * accw);
         const double t1 = ((d1 + halo) * M + d1 * E) / d1;
@@ -1220,7 +1230,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
     // always request the full budget so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
-    kernel<<<grid, kThreads, kSmemBudget, (cudaStream_t)stream>>>(tmap, p);
+    kernel<<<grid, p.roll ? kThreads : tc_threads(P), kSmemBudget, (cudaStream_t)stream>>>(tmap, p);
     (void)smem;
     e = cudaGetLastError();
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: launch failed: %s", cudaGetErrorString(e));
