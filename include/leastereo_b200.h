@@ -95,6 +95,7 @@ typedef struct lea_tc_opts {
     int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
     const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
     int32_t resident_weights;  /* 0 = auto (all channel groups' weights stay in shared memory when they fit), 2 = never */
+    int32_t cv_skip;           /* fused_cv only: 1 = leave the voxels lea_stem0_assemble writes (collapsed stem0) untouched */
     int32_t debug;             /* development switches of the rolling kernel's epilogue; 0 in production */
     int32_t rolling;           /* k = 3: 1 = rolling accumulator ring (needs <= 85 TMEM columns per depth), 0 = chunked kernel (default) */
     int32_t depth_chunk;       /* 0 = auto, n = depth slices per work item, clamped to what the schedule allows (test knob) */
@@ -111,6 +112,16 @@ int64_t lea_fused_cv_maps_bytes(int32_t d3);
 int lea_build_fused_cv_maps(const lea_vol* fx, const lea_vol* fy, int32_t d3, void* maps_dev, void* stream);
 /* self-test of the tcgen05 path on a synthetic GEMM-shaped conv; returns 0 when it matches the SIMT kernel. */
 int lea_tc_selftest(int32_t verbose, void* stream);
+
+/* ---- collapsed stem0: retrain/LEAStereo.py:34-48 + matching.stem0 (skip_model_3d.py:141) --------------------------- */
+/* Where the 3x3x3 window of an output voxel lies entirely in the un-masked part of the cost volume (first/last depth,
+ * the band w <= d+1 and the last 8-column tile excluded), stem0's convolution separates exactly into 2-D convolutions
+ * of the two feature maps: out = L[h,w] + A[h,w-d-1] + B[h,w-d+1] (L: x with sum_kd W; A/B: y with the taps kw-kd in
+ * {-2,-1,0} / {1,2}).  The maps are computed once per pair by any ConvBR kernel above on depth-1 volumes; this entry
+ * point adds them, applies BN+ReLU and writes those voxels of dst.  The excluded voxels are written by lea_conv3d_tc
+ * with fused_cv and cv_skip = 1 (it skips exactly the voxels written here). */
+int lea_stem0_assemble(const lea_vol* lmap, const lea_vol* abmap, const lea_vol* dst, int32_t dst_c0, int32_t c_out,
+                       const float* bn_scale, const float* bn_shift, int32_t relu, void* stream);
 
 /* ---- matching-net head without the up-sampled volume: retrain/skip_model_3d.py:162-169 (upsample_6 -> last_3) ---- */
 /* last_3 (Conv3d C->1, 3x3x3, no BN/ReLU, skip_model_3d.py:132) and the trilinear align_corners=True up-sample are both

@@ -177,6 +177,23 @@ extern "C" int lea_head_taps(const lea_vol* q, int32_t q_c0, float* mat, int32_t
     return LEA_POST_LAUNCH();
 }
 
+extern "C" int lea_stem0_assemble(const lea_vol* lmap, const lea_vol* abmap, const lea_vol* dst, int32_t dst_c0,
+                                  int32_t c_out, const float* bn_scale, const float* bn_shift, int32_t relu,
+                                  void* stream) {
+    if (lea_check_vol(lmap, "stem0_assemble lmap") || lea_check_vol(abmap, "stem0_assemble abmap") ||
+        lea_check_vol(dst, "stem0_assemble dst") || lea_check_slice(dst, dst_c0, c_out, "stem0_assemble dst"))
+        return 1;
+    LEA_CHECK((bn_scale == nullptr) == (bn_shift == nullptr), "stem0_assemble: bn_scale/bn_shift must come together");
+    LEA_CHECK(lmap->D == 1 && abmap->D == 1 && lmap->C == c_out && abmap->C == 2 * c_out && lmap->B == dst->B &&
+              abmap->B == dst->B && lmap->H == dst->H && abmap->H == dst->H && lmap->W == dst->W && abmap->W == dst->W,
+              "stem0_assemble: maps must be (B, c_out | 2*c_out, 1, H, W) volumes matching dst");
+    LEA_CHECK((int64_t)dst->B * (c_out >> 3) <= 65535, "stem0_assemble: grid too large");
+    const int nchunk = (dst->D + LEA_AS_DCH - 1) / LEA_AS_DCH;
+    LEA_LAUNCH(lea_stem0_assemble_kernel, dim3((dst->W + 127) / 128, nchunk * dst->H, dst->B * (c_out >> 3)), dim3(128),
+               0, stream, *lmap, *abmap, *dst, dst_c0, c_out, bn_scale, bn_shift, relu);
+    return LEA_POST_LAUNCH();
+}
+
 extern "C" int lea_disparity_regression(const float* p, float* out, int32_t B, int32_t maxdisp, int32_t H, int32_t W,
                                         void* stream) {
     LEA_CHECK(p && out, "disparity_regression: null pointer");

@@ -142,6 +142,13 @@ LEA_HD void lea_load8_at(const lea_u4* g0, int64_t ps, int P, float* f) {
         if (p < P) lea_unpack8(g0[p * ps], f, true);
 }
 
+// Collapsed stem0 (see lea_stem0_assemble): output voxels (d, w in the 8-wide tile tw) whose 3x3x3 window lies entirely
+// inside the un-masked part of the cost volume (w' >= d' for every tap), off the first/last depth slice and off the
+// first/last column.  Tile-granular along w so that the two kernels that share the volume write disjoint regions.
+LEA_HD bool lea_cv_interior(int d, int tw, int D, int W) {
+    return d >= 1 && d <= D - 2 && 8 * tw >= d + 2 && 8 * tw + 7 <= W - 2;
+}
+
 // error reporting shared by every API translation unit
 void lea_set_error(const char* fmt, ...);
 #define LEA_CHECK(cond, ...) do { if (!(cond)) { lea_set_error(__VA_ARGS__); return 1; } } while (0)

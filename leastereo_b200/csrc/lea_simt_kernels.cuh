@@ -746,6 +746,69 @@ lea_head_taps_d_kernel(const float* __restrict__ S, float* __restrict__ mat, int
     *reinterpret_cast<lea_fvec<VEC>*>(mat + (((int64_t)b * D + d) * H + h) * W + w) = o;
 }
 
+// =========================================================================================================
+// K8  collapsed stem0 (retrain/LEAStereo.py:34-48 + matching.stem0, skip_model_3d.py:92,141).  The cost volume is
+//     cost[c] = x[c,h,w], cost[C+c] = y[c,h,w-d] wherever w >= d.  For an output voxel whose whole 3x3x3 window is
+//     un-masked (lea_cv_interior) the conv separates exactly:
+//         sum_{c,kd,kh,kw} W[co,c,kd,kh,kw] x[c,h+kh-1,w+kw-1]            = L[co,h,w]      (3x3 kernel  sum_kd W)
+//         sum_{c,kd,kh,kw} W[co,C+c,kd,kh,kw] y[c,h+kh-1,(w-d)+(kw-kd)]   = R[co,h,w-d]    (3x5 kernel over kw-kd)
+//     and R(u) = A(u-1) + B(u+1) with two ordinary 3x3 kernels (taps kw-kd in {-2,-1,0} and {1,2}).  L, A, B are 2-D
+//     convs of the feature maps, computed ONCE per pair instead of once per disparity (377 GFLOP -> 3 GFLOP); this
+//     kernel adds them, applies BN+ReLU and writes stem0's output.  The remaining voxels (first/last depth, the band
+//     w <= d+1, the last column tile) come from the tensor-core kernel with the fused loader (lea_tc_opts.cv_skip).
+//     lmap (B, C_out, 1, H, W), abmap (B, 2*C_out, 1, H, W): planes volumes (3 planes = fp32 exact).
+// =========================================================================================================
+#define LEA_AS_DCH 16        // depths per CTA: the A/B rows it needs (128 + 16 positions) are staged once in shared memory
+__global__ void __launch_bounds__(128)
+lea_stem0_assemble_kernel(lea_vol lmap, lea_vol abmap, lea_vol dst, int dst_c0, int c_out,
+                          const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int relu) {
+    __shared__ float sA[(128 + LEA_AS_DCH) * 8];
+    __shared__ float sB[(128 + LEA_AS_DCH) * 8];
+    const int tid = threadIdx.x;
+    const int w0 = blockIdx.x * 128, w = w0 + tid;
+    const int h = blockIdx.y % dst.H, dch = blockIdx.y / dst.H;
+    const int d0 = dch * LEA_AS_DCH, d1 = min(dst.D, d0 + LEA_AS_DCH);
+    const int cbn = c_out >> 3;
+    const int b = blockIdx.z / cbn, cb = blockIdx.z - b * cbn;
+    const int64_t hw = (int64_t)lmap.H * lmap.W;
+    const lea_u4* lb = (const lea_u4*)lmap.data + ((int64_t)b * (lmap.C >> 3) + cb) * lmap.P * hw + (int64_t)h * lmap.W;
+    const lea_u4* ab = (const lea_u4*)abmap.data + ((int64_t)b * (abmap.C >> 3) + cb) * abmap.P * hw + (int64_t)h * lmap.W;
+    const lea_u4* bb = ab + (int64_t)cbn * abmap.P * hw;                   // B = channels [c_out, 2*c_out)
+    // A is read at w-d-1, B at w-d+1 = that + 2: position k of both staging rows belongs to A index ia0 + k
+    const int ia0 = w0 - d1;
+    const int nstage = 127 + (d1 - d0);
+    for (int k = tid; k < nstage; k += 128) {
+        // clamped positions are only ever used by voxels outside the interior (which this kernel does not write)
+        const int ia = min(max(ia0 + k, 0), lmap.W - 1), ib = min(max(ia0 + k + 2, 0), lmap.W - 1);
+        lea_load8_at(ab + ia, hw, abmap.P, sA + k * 8);
+        lea_load8_at(bb + ib, hw, abmap.P, sB + k * 8);
+    }
+    __syncthreads();
+    if (w >= dst.W) return;
+    float l[8], sc[8], sh[8];
+    lea_load8_at(lb + w, hw, lmap.P, l);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = bn_scale ? __ldg(bn_scale + cb * 8 + j) : 1.0f;
+        sh[j] = bn_scale ? __ldg(bn_shift + cb * 8 + j) : 0.0f;
+    }
+    const int64_t dHW = (int64_t)dst.H * dst.W, dPS = dHW * dst.D;
+    lea_u4* ob = (lea_u4*)dst.data + ((int64_t)b * (dst.C >> 3) + (dst_c0 >> 3) + cb) * dst.P * dPS + (int64_t)h * dst.W + w;
+    for (int d = d0; d < d1; ++d) {
+        if (!lea_cv_interior(d, w >> 3, dst.D, dst.W)) continue;
+        const int k = (w - d - 1) - ia0;                                   // = tid + d1 - d - 1
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = l[j] + (sA[k * 8 + j] + sB[k * 8 + j]);
+            v = v * sc[j] + sh[j];
+            if (relu) v = v > 0.0f ? v : 0.0f;
+            out[j] = v;
+        }
+        lea_store8_at(ob + (int64_t)d * dHW, dPS, dst.P, out);
+    }
+}
+
 // DisparityRegression alone (models/build_model_2d.py:36-41)
 __global__ void __launch_bounds__(256)
 lea_disparity_regression_kernel(const float* __restrict__ p, float* __restrict__ out, int maxdisp, int HW) {

@@ -73,6 +73,7 @@ struct TcParams {
     int slab_vox, pitch_vox, blk_bytes, stage_bytes, stage_stride;   // stride = bytes rounded up to 128 (TMA alignment)
     int nstages, nwbuf;
     int tw_log2;              // tile = (1 << tw_log2) voxels along w x (128 >> tw_log2) along h  (3 for k = 3)
+    int cv_skip;              // collapsed stem0: skip the voxels lea_stem0_assemble writes (lea_cv_interior)
     int dbg;                  // development switches (bit 0: epilogue skips its stores, bit 1: skips the TMEM loads)
     int roll, R;              // rolling schedule (see lea_conv_tc_roll_kernel): R home accumulator blocks + 2 alias blocks
     int wres;                 // 1 = the weight parts of ALL channel groups stay resident in shared memory (loaded once per CTA)
@@ -214,6 +215,13 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
     if (p.ks == 3) { g.dlo = max(g.d0 - 1, 0); g.dhi = min(g.d_hi, p.D - 1); }
     else           { g.dlo = g.d0;             g.dhi = g.d_hi - 1; }
     return g;
+}
+
+// collapsed stem0: true when every voxel of the item is written by lea_stem0_assemble (the item is skipped by all roles)
+__device__ __forceinline__ bool item_skipped(const TcParams& p, const ItemGeom& g) {
+    if (!p.cv_skip) return false;
+    const int tw = g.w0 >> 3;
+    return lea_cv_interior(g.d0, tw, p.D, p.W) && lea_cv_interior(g.d_hi - 1, tw, p.D, p.W);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -385,6 +393,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             }
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const ItemGeom g = decode_item(p, item);
+                if (item_skipped(p, g)) continue;
                 const int gbase = g.b * p.g0_stride_b + p.g0_first;
                 for (int cg = 0; cg < p.ncg; ++cg) {
                     if (!p.wres) {
@@ -438,9 +447,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
                                  // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
         if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const ItemGeom g = decode_item(p, item);
+            if (item_skipped(p, g)) continue;
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
+            ++it;
             mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201);
             tc_fence_after();
             const uint32_t set_base = tmem_base + (uint32_t)set * set_cols;
@@ -521,9 +532,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int lh = m >> p.tw_log2, lw = m & ((1 << p.tw_log2) - 1);
         const int64_t sp = (int64_t)p.D * p.H * p.W;
         int it = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const ItemGeom g = decode_item(p, item);
+            if (item_skipped(p, g)) continue;
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
+            ++it;
             const int h = g.h0 + lh, w = g.w0 + lw;
             const bool valid = (h < p.H) && (w < p.W);
             const int nd = g.d_hi - g.d0;
@@ -571,7 +584,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
                             }
                         }
-                        if (!valid) continue;
+                        if (!valid || (p.cv_skip && lea_cv_interior(d, g.w0 >> 3, p.D, p.W))) continue;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
@@ -1168,6 +1181,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // next round (needs an epilogue that does not disturb the issuer); the chunked kernel is the default.
     p.roll = (p.ks == 3 && p.R >= 4 && opts && opts->rolling == 1) ? 1 : 0;
     p.dbg = opts ? opts->debug : 0;
+    p.cv_skip = (fused && opts->cv_skip == 1 && !p.roll) ? 1 : 0;
     int dc_max = p.roll ? p.D : 512 / (p.nsets * accw);
     if (!p.roll && dc_max > 16) dc_max = 16;
     if (dc_max > p.D) dc_max = p.D;

@@ -57,6 +57,7 @@ class Step:
     image: Optional[torch.Tensor] = None      # packed tcgen05 weight image
     ref: Optional[torch.Tensor] = None
     wfn: object = None             # callable(step): fills step.wcat with weights DERIVED from the modules' parameters
+    planes: int = 0                # plane count of the packed weight image (0 = the plan's)
     # resample
     rs: tuple = ()
 
@@ -78,6 +79,7 @@ class MatchingPlan:
         self.fuse = fuse               # graph-level rewrites: batched sibling convs, conv-before-upsample
         self.fuse_cv = bool(tc_knobs.get("fuse_cv", True))
         self.fuse_head = bool(tc_knobs.get("fuse_head", True))
+        self.collapse_stem0 = bool(tc_knobs.get("collapse_stem0", True))
         self.accum_split = int(tc_knobs.get("accum_split", 0))
         self.acc_sets = int(tc_knobs.get("acc_sets", 0))
         self.tile_w_log2 = int(tc_knobs.get("tile_w_log2", 0))
@@ -236,6 +238,62 @@ class MatchingPlan:
                                2.0 * self.P * m_vox * (c_in + dst.c), p=p, mods=(mod,), weight=wcat, wcat=wcat, opts=opts,
                                ref=src.vol.t, wfn=fill))
 
+    # ---- collapsed stem0 ------------------------------------------------------------------------------------
+    def _can_collapse_stem0(self, fm: int, L0) -> bool:
+        st = self.m.stem0
+        w = st.conv.weight
+        return (self.fuse and self.collapse_stem0 and self.conv_mode == "tc" and tuple(w.shape[2:]) == (3, 3, 3)
+                and w.shape[1] == 2 * fm and w.shape[0] % 8 == 0 and w.shape[0] <= 32 and L0[0] >= 3 and L0[2] >= 24
+                and self.ops.tc_weight_image_bytes(fm, 2 * w.shape[0], 3, 3) > 0)
+
+    def _emit_collapsed_stem0(self, fm: int, L0, v0: PlanesVol):
+        """stem0 on the cost volume (LEAStereo.py:34-48 + skip_model_3d.py:141) without the per-disparity work where
+        the volume is un-masked: out = L[h,w] + A[h,w-d-1] + B[h,w-d+1] with three 2-D convs of the feature maps
+        (see ``lea_stem0_assemble``); the tensor-core kernel with the fused loader does the remaining voxels."""
+        m, B = self.m, self.B
+        st = m.stem0
+        c_out = st.conv.out_channels
+        D, H, W = L0
+        P3 = 3                                               # the maps are summed afterwards: keep them exact
+        self.fxy3 = PlanesVol.empty(2 * B, fm, P3, 1, H, W, self.device)
+        fx3, fy3 = PlanesVol(self.fxy3.t[:B]), PlanesVol(self.fxy3.t[B:])
+        lmap = PlanesVol.empty(B, c_out, P3, 1, H, W, self.device)
+        abmap = PlanesVol.empty(B, 2 * c_out, P3, 1, H, W, self.device)
+        self.volumes += [self.fxy3, lmap, abmap]
+
+        def fill_l(step, st=st, fm=fm):
+            step.wcat.copy_(collapsed_stem0_weights(st.conv.weight.detach(), fm)[0])
+
+        def fill_ab(step, st=st, fm=fm):
+            step.wcat.copy_(collapsed_stem0_weights(st.conv.weight.detach(), fm)[1])
+
+        def emit_map(name, src_vol, dst_vol, co, fill):
+            wcat = torch.zeros((co, fm, 3, 3, 3), dtype=torch.float32, device=self.device)
+            p = self.ops.make_conv(src_vol, 0, fm, co, 3, None, None, False, dst=dst_vol, dst_c0=0)
+            opts = lea_tc_opts()
+            opts.accum_split = self.accum_split
+            self.steps.append(Step("conv_tc", name, 2.0 * B * H * W * co * fm * 9,
+                                   2.0 * P3 * B * H * W * (fm + co), p=p, mods=(st,), weight=wcat, wcat=wcat, opts=opts,
+                                   ref=src_vol.t, wfn=fill, planes=P3))
+
+        emit_map("stem0.collapsed.L(2-D)", fx3, lmap, c_out, fill_l)
+        emit_map("stem0.collapsed.A|B(2-D)", fy3, abmap, 2 * c_out, fill_ab)
+        # the voxels the maps do not cover: tensor-core kernel with the fused cost-volume loader
+        n_before = len(self.steps)
+        self._emit_conv("stem0(fused cost volume; band + edges)", st, Slice(self.fxp, 0, 2 * fm), Slice(v0, 0, fm),
+                        fused_cv=True)
+        tc_step = self.steps[n_before]
+        tc_step.opts.cv_skip = 1
+        tiles_w = (W + 7) // 8
+        interior = sum(1 for d in range(D) for tw in range(tiles_w)
+                       if d >= 1 and d <= D - 2 and 8 * tw >= d + 2 and 8 * tw + 7 <= W - 2)
+        frac = 1.0 - interior * 8.0 / (D * W)
+        tc_step.flops *= frac
+        scale, shift = self._bn_slices([st]) if st.use_bn else (None, None)
+        nbytes = 2.0 * self.P * B * D * H * W * c_out * (1.0 - frac) + 2.0 * P3 * B * H * W * 3 * c_out
+        self.steps.append(Step("stem0_assemble", "stem0.collapsed.assemble", 0.0, nbytes,
+                               rs=(lmap, abmap, v0, 0, c_out, scale, shift, st.relu)))
+
     def _identity_weight(self, c: int) -> torch.Tensor:
         if c not in self._eye:
             self._eye[c] = torch.eye(c, dtype=torch.float32, device=self.device).reshape(c, c, 1, 1, 1).contiguous()
@@ -358,7 +416,7 @@ class MatchingPlan:
         fm = m.initial_fm
         L0 = self.spatial
         v0, v1 = self._vol(fm, L0), self._vol(fm, L0)
-        self.cost = self.fxp = self.fyp = self.fxy = self.cv_maps = None
+        self.cost = self.fxp = self.fyp = self.fxy = self.cv_maps = self.fxy3 = None
         can_fuse_cv = (self.fuse_cv and self.conv_mode == "tc" and fm % 16 == 0 and L0[0] <= L0[2] and
                        self.ops.tc_weight_image_bytes(2 * fm, fm, 3, self.P) > 0)
         if can_fuse_cv:
@@ -369,8 +427,11 @@ class MatchingPlan:
             self.fxp = PlanesVol(self.fxy.t[: self.B])
             self.fyp = PlanesVol(self.fxy.t[self.B:])
             self.cv_maps = self.ops.build_fused_cv_maps(self.fxp, self.fyp, L0[0])
-            self._emit_conv("stem0(fused cost volume)", m.stem0, Slice(self.fxp, 0, 2 * fm), Slice(v0, 0, fm),
-                            fused_cv=True)
+            if self._can_collapse_stem0(fm, L0):
+                self._emit_collapsed_stem0(fm, L0, v0)
+            else:
+                self._emit_conv("stem0(fused cost volume)", m.stem0, Slice(self.fxp, 0, 2 * fm), Slice(v0, 0, fm),
+                                fused_cv=True)
         else:
             self.cost = self._vol(2 * fm, L0)
             self._emit_conv("stem0", m.stem0, Slice(self.cost, 0, 2 * fm), Slice(v0, 0, fm))
@@ -492,7 +553,7 @@ class MatchingPlan:
                     else:
                         s.weight = s.mods[0].conv.weight.detach()
                 if s.kind == "conv_tc":
-                    s.image = self.ops.pack_weights_tc(s.weight, self.P, out=s.image)
+                    s.image = self.ops.pack_weights_tc(s.weight, s.planes or self.P, out=s.image)
         self._param_key = key
 
     # ---- execution ------------------------------------------------------------------------------------
@@ -504,6 +565,9 @@ class MatchingPlan:
             self.ops.conv3d_simt(s.p, s.weight, s.ref)
         elif s.kind == "conv_tc":
             self.ops.conv3d_tc(s.p, s.image, s.opts, s.ref)
+        elif s.kind == "stem0_assemble":
+            lmap, abmap, dst, dst_c0, c_out, scale, shift, relu = s.rs
+            self.ops.stem0_assemble(lmap, abmap, dst, dst_c0, c_out, scale, shift, relu)
         elif s.kind == "head_taps":
             q, q_c0, mat, ws = s.rs
             self.ops.head_taps(q, q_c0, mat, ws)
@@ -538,9 +602,11 @@ class FeaturePlan(MatchingPlan):
     operand buffer of the fused cost-volume loader (left block | right block)."""
 
     def __init__(self, feature: newFeature, ops: Ops, B2: int, H: int, W: int, planes: int, device, out: PlanesVol,
-                 mma_terms: int = 0, fuse: bool = True, tc_knobs: Optional[dict] = None, conv_mode: str = "tc"):
+                 mma_terms: int = 0, fuse: bool = True, tc_knobs: Optional[dict] = None, conv_mode: str = "tc",
+                 out3: Optional[PlanesVol] = None):
         self.img_hw = (int(H), int(W))
         self.out = out
+        self.out3 = out3               # optional second destination holding the features in this plan's own planes
         h3, w3 = (H - 1) // 3 + 1, (W - 1) // 3 + 1
         super().__init__(feature, ops, B2, (1, h3, w3), planes, device, conv_mode, mma_terms, fuse, tc_knobs)
 
@@ -582,15 +648,23 @@ class FeaturePlan(MatchingPlan):
             feat = self._resample("feature.upsample_6", conv_to("feature.last_6", f.last_6, t), L0)
         else:
             raise LeaError("feature net ends on a level the native path does not handle")
+        used3 = False
         if self.out.P == self.P:
             self._emit_conv("feature.last_3", f.last_3, feat, Slice(self.out, 0, fm))
         else:
             # the feature net runs with its own plane count (3 = exact storage / bf16x6: it is tiny, and its rounding
             # errors are amplified by the whole matching net); convert to the matching net's operand format at the end
-            tmp = Slice(self._vol(fm, L0), 0, fm)
+            if self.out3 is not None and self.out3.P == self.P and self.out3.spatial == L0 and self.out3.C == fm:
+                tmp = Slice(self.out3, 0, fm)          # the collapsed stem0 reads the features at full precision
+                used3 = True
+            else:
+                tmp = Slice(self._vol(fm, L0), 0, fm)
             self._emit_conv("feature.last_3", f.last_3, feat, tmp)
             self.steps.append(Step("repack", "feature.to_operand_planes", 0.0,
                                    2.0 * self.B * _prod(L0) * fm * (self.P + self.out.P), rs=(tmp.vol, self.out, fm)))
+        if self.out3 is not None and not used3:
+            self.steps.append(Step("repack", "feature.to_map_planes", 0.0,
+                                   2.0 * self.B * _prod(L0) * fm * (self.out.P + self.out3.P), rs=(self.out, self.out3, fm)))
 
     def refresh_params(self, force: bool = False):
         key = self._current_param_key()
@@ -602,6 +676,25 @@ class FeaturePlan(MatchingPlan):
                 img, _, sc0, sh0, _, sc1, sh1, dst = s.rs
                 s.rs = (img, s.mods[0].conv.weight.detach().contiguous(), sc0, sh0,
                         s.mods[1].conv.weight.detach().contiguous(), sc1, sh1, dst)
+
+
+def collapsed_stem0_weights(w: torch.Tensor, fm: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """2-D kernels of the collapsed stem0 from its (c_out, 2*fm, 3, 3, 3) weight, as k^3 kernels whose kd != 1 taps
+    are zero (they run on depth-1 volumes):  L (c_out, fm, 3,3,3) = sum over kd of the x half;  A|B (2*c_out, fm, 3,3,3)
+    from the y half, taps delta = kw - kd in {-2,-1,0} for A (read at u-1) and {1,2} for B (read at u+1)."""
+    c_out = w.shape[0]
+    wd = w.double()
+    wl = torch.zeros((c_out, fm, 3, 3, 3), dtype=torch.float32, device=w.device)
+    wl[:, :, 1].copy_(wd[:, :fm].sum(dim=2).float())
+    wy = wd[:, fm:]
+    r = torch.zeros((c_out, fm, 3, 5), dtype=torch.float64, device=w.device)          # index = delta + 2
+    for kd in range(3):
+        for kw in range(3):
+            r[:, :, :, kw - kd + 2] += wy[:, :, kd, :, kw]
+    wab = torch.zeros((2 * c_out, fm, 3, 3, 3), dtype=torch.float32, device=w.device)
+    wab[:c_out, :, 1].copy_(r[:, :, :, 0:3].float())
+    wab[c_out:, :, 1, :, 1:3].copy_(r[:, :, :, 3:5].float())
+    return wl, wab
 
 
 def _prod(t):
@@ -620,7 +713,7 @@ DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fus
 
 
 # tensor-core kernel / plan-rewrite knobs an ``engine_options`` dict may carry (defaults = what the product runs)
-_TC_KNOBS = {"accum_split": 0, "acc_sets": 0, "fuse_cv": True, "fuse_head": True, "tile_w_log2": 0,
+_TC_KNOBS = {"accum_split": 0, "acc_sets": 0, "fuse_cv": True, "fuse_head": True, "collapse_stem0": True, "tile_w_log2": 0,
              "resident_weights": 0, "depth_chunk": 0, "rolling": 0}
 
 
@@ -682,6 +775,9 @@ def hot_path_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optional[Op
     if plan.fxp is not None:                 # fused: stem0's loader builds the volume from the packed feature maps
         ops.pack(fx, opt["planes"], out=plan.fxp)
         ops.pack(fy, opt["planes"], out=plan.fyp)
+        if plan.fxy3 is not None:            # exact copies for the 2-D maps of the collapsed stem0
+            ops.pack(fx, 3, out=PlanesVol(plan.fxy3.t[:B]))
+            ops.pack(fy, 3, out=PlanesVol(plan.fxy3.t[B:]))
     else:
         ops.cost_volume_planes(fx, fy, model.maxdisp, opt["planes"], out=plan.cost)
     mat = plan.run(check_params=not opt["assume_frozen"])
@@ -711,7 +807,7 @@ def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[O
             try:
                 fplan = FeaturePlan(model.feature, ops, 2 * B, H, W, int(opt.get("feature_planes", 3)), left.device, plan.fxy,
                                     opt["mma_terms"], bool(opt.get("fuse", True)),
-                                    {k: opt.get(k, d) for k, d in _TC_KNOBS.items()})
+                                    {k: opt.get(k, d) for k, d in _TC_KNOBS.items()}, out3=plan.fxy3)
             except LeaError:
                 fplan = False
             plans[key] = fplan

@@ -33,7 +33,7 @@ class lea_conv(C.Structure):
 class lea_tc_opts(C.Structure):
     _fields_ = [("mma_terms", C.c_int32), ("fused_cv", C.c_int32), ("fx", lea_vol), ("fy", lea_vol),
                 ("d3", C.c_int32), ("num_sms", C.c_int32), ("accum_split", C.c_int32), ("acc_sets", C.c_int32), ("cv_maps", C.c_void_p),
-                ("resident_weights", C.c_int32), ("debug", C.c_int32), ("rolling", C.c_int32), ("depth_chunk", C.c_int32),
+                ("resident_weights", C.c_int32), ("cv_skip", C.c_int32), ("debug", C.c_int32), ("rolling", C.c_int32), ("depth_chunk", C.c_int32),
                 ("tile_w_log2", C.c_int32)]
 
 
@@ -56,6 +56,7 @@ SYMBOLS = {
     "lea_tc_selftest": (C.c_int, [_i32, _vp]),
     "lea_fused_cv_maps_bytes": (_i64, [_i32]),
     "lea_build_fused_cv_maps": (C.c_int, [_VOLP, _VOLP, _i32, _vp, _vp]),
+    "lea_stem0_assemble": (C.c_int, [_VOLP, _VOLP, _VOLP, _i32, _i32, _vp, _vp, _i32, _vp]),
     "lea_head_taps_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "lea_head_taps": (C.c_int, [_VOLP, _i32, _vp, _i32, _i32, _i32, _vp, _vp]),
     "lea_disp_head": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -288,6 +289,16 @@ class Ops:
 
     def tc_selftest(self, verbose: int = 1) -> int:
         return int(self.lib.lea_tc_selftest(verbose, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    # ---- collapsed stem0 ---------------------------------------------------------------------------------------
+    def stem0_assemble(self, lmap: PlanesVol, abmap: PlanesVol, dst: PlanesVol, dst_c0: int, c_out: int,
+                       bn_scale: Optional[torch.Tensor], bn_shift: Optional[torch.Tensor], relu: bool):
+        self._dev(lmap.t, abmap.t, dst.t)
+        a, b, d = lmap.struct(), abmap.struct(), dst.struct()
+        with self._dev_ctx(dst.t):
+            self._check(self.lib.lea_stem0_assemble(C.byref(a), C.byref(b), C.byref(d), dst_c0, c_out,
+                                                    self._ptr(bn_scale), self._ptr(bn_shift), int(bool(relu)),
+                                                    self._stream(dst.t)))
 
     # ---- matching-net head (upsample_6 -> last_3 without the up-sampled volume) ----------------------------
     def head_taps_workspace(self, q: PlanesVol, spatial) -> torch.Tensor:

@@ -24,6 +24,7 @@ extern unsigned char* emu_dyn_smem;
 #define __device__
 #define __host__
 #define __shared__ static
+#define __align__(n) alignas(n)
 #define __restrict__
 #define __forceinline__ inline
 #define __launch_bounds__(...)

@@ -167,6 +167,41 @@ def check_head_taps(ops, device):
         assert err <= 5e-6, (src_sp, dst_sp, err)
 
 
+def check_stem0_collapse(ops, device):
+    """Collapsed stem0: L/A/B 2-D maps (derived weights, ordinary conv kernel on depth-1 volumes) + lea_stem0_assemble
+    against conv3d over the materialised cost volume (LEAStereo.py:34-48 + skip_model_3d.py:141) on every voxel the
+    assemble kernel claims; the other voxels must stay untouched."""
+    B, fm, co, maxdisp, H, W = 2, 8, 8, 21, 5, 40
+    D = maxdisp // 3
+    fx, fy = _rand((B, fm, H, W), 71, device), _rand((B, fm, H, W), 72, device)
+    w = _rand((co, 2 * fm, 3, 3, 3), 73, device, scale=0.2)
+    scale = (_rand((co,), 74, device).abs() + 0.5).contiguous()
+    shift = _rand((co,), 75, device).contiguous()
+    wl, wab = engine.collapsed_stem0_weights(w, fm)
+    fx3, fy3 = ops.pack(fx, 3), ops.pack(fy, 3)
+    lmap = PlanesVol.empty(B, co, 3, 1, H, W, device)
+    abmap = PlanesVol.empty(B, 2 * co, 3, 1, H, W, device)
+    ops.conv3d_simt(ops.make_conv(fx3, 0, fm, co, 3, None, None, False, dst=lmap), wl.contiguous(), fx)
+    ops.conv3d_simt(ops.make_conv(fy3, 0, fm, 2 * co, 3, None, None, False, dst=abmap), wab.contiguous(), fy)
+    dst = PlanesVol.empty(B, co + 8, 3, D, H, W, device)
+    dst.t.zero_()
+    ops.stem0_assemble(lmap, abmap, dst, 8, co, scale, shift, True)
+    got = ops.unpack(dst, 8, co).cpu()
+    cost = torch.from_numpy(O.cost_volume_numpy(fx.cpu().numpy(), fy.cpu().numpy(), maxdisp))
+    ref = F.relu(F.conv3d(cost, w.cpu(), None, 1, 1) * scale.cpu().view(1, -1, 1, 1, 1) + shift.cpu().view(1, -1, 1, 1, 1))
+    claimed = torch.zeros((D, W), dtype=torch.bool)
+    for d in range(D):
+        for x in range(W):
+            claimed[d, x] = (1 <= d <= D - 2) and (8 * (x // 8) >= d + 2) and (8 * (x // 8) + 7 <= W - 2)
+    assert int(claimed.sum()) > 0
+    m = claimed.view(1, 1, D, 1, W).expand_as(got)
+    err = float((got - ref)[m].abs().max()) / float(ref.abs().max())
+    assert err <= 2e-6, err
+    assert float(got[~m].abs().max()) == 0.0, "wrote outside the claimed voxels"
+    assert float(ops.unpack(dst, 0, 8).abs().max()) == 0.0
+    return err
+
+
 def check_disparity_regression(ops, device):
     p = torch.softmax(_rand((2, 24, 5, 7), 5, device), dim=1).contiguous()
     got = ops.disparity_regression(p, 24).cpu()

@@ -71,6 +71,10 @@ def test_head_taps(emu_ops):
     K.check_head_taps(emu_ops, DEV)
 
 
+def test_stem0_collapse(emu_ops):
+    print("collapsed stem0 vs conv3d(cost volume): rel err", K.check_stem0_collapse(emu_ops, DEV))
+
+
 def test_disparity_regression(emu_ops):
     K.check_disparity_regression(emu_ops, DEV)
 

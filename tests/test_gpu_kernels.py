@@ -60,6 +60,10 @@ def test_head_taps(ops):
     K.check_head_taps(ops, DEV)
 
 
+def test_stem0_collapse(ops):
+    print("collapsed stem0 vs conv3d(cost volume): rel err", K.check_stem0_collapse(ops, DEV))
+
+
 def test_disparity_regression(ops):
     K.check_disparity_regression(ops, DEV)
 
@@ -108,7 +112,7 @@ def test_fused_cost_volume_equals_materialised(ops):
         model = K.seeded_model(int(g["maxdisp"]))
         model.load_state_dict(K.golden_state_dict(g, model))
         model = model.to(DEV).eval()
-        model.engine_options = {"planes": 2, "conv": "tc", "fuse_cv": fuse_cv}
+        model.engine_options = {"planes": 2, "conv": "tc", "fuse_cv": fuse_cv, "collapse_stem0": False}
         fx, fy = torch.from_numpy(g["fx"]).to(DEV), torch.from_numpy(g["fy"]).to(DEV)
         from leastereo_b200 import engine
         disp = engine.hot_path_forward(model, fx, fy, ops=ops)
@@ -124,6 +128,28 @@ def _random_model(maxdisp, options):
     model = K.seeded_model(maxdisp).to(DEV).eval()
     model.engine_options = dict(options)
     return model
+
+
+def test_collapsed_stem0_matches_plain(ops):
+    """stem0 through the 2-D maps + assemble + band/edge tensor-core launch must agree with the plain fused-loader run
+    on every voxel (different summation order: compare the stem0 output volume to fp32 rounding of 2 planes)."""
+    from leastereo_b200 import engine
+    g = load_golden("cal_48x96_d48")
+    vols, disps = {}, {}
+    for collapse in (False, True):
+        model = K.seeded_model(int(g["maxdisp"]))
+        model.load_state_dict(K.golden_state_dict(g, model))
+        model = model.to(DEV).eval()
+        model.engine_options = {"planes": 2, "conv": "tc", "collapse_stem0": collapse}
+        fx, fy = torch.from_numpy(g["fx"]).to(DEV), torch.from_numpy(g["fy"]).to(DEV)
+        disps[collapse] = engine.hot_path_forward(model, fx, fy, ops=ops).cpu()
+        plan = engine.get_plan(model.matching, 1, (16, 16, 32), fx.device, engine._options(model), ops)
+        assert (plan.fxy3 is not None) == collapse
+        vols[collapse] = ops.unpack(plan.volumes[0]).cpu()            # v0 = stem0's output
+    err = float((vols[True] - vols[False]).abs().max()) / float(vols[False].abs().max())
+    print("collapsed vs plain stem0: rel err", err)
+    assert err <= 1e-4
+    assert O.tolerance_report(disps[True], disps[False])["ok"]
 
 
 def test_cost_volume_full_kitti_bit_exact(ops):
