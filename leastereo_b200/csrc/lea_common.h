@@ -148,6 +148,10 @@ LEA_HD void lea_load8_at(const lea_u4* g0, int64_t ps, int P, float* f) {
 LEA_HD bool lea_cv_interior(int d, int tw, int D, int W) {
     return d >= 1 && d <= D - 2 && 8 * tw >= d + 2 && 8 * tw + 7 <= W - 2;
 }
+// ... and the voxels whose whole window is masked (every tap has w' < d'): the conv output is exactly 0 there, so
+// stem0's output is relu(bn(0)).  Also written by lea_stem0_assemble, also skipped by the tensor-core launch.
+LEA_HD bool lea_cv_masked(int d, int tw) { return 8 * tw + 7 <= d - 3; }
+LEA_HD bool lea_cv_collapsed(int d, int tw, int D, int W) { return lea_cv_interior(d, tw, D, W) || lea_cv_masked(d, tw); }
 
 // error reporting shared by every API translation unit
 void lea_set_error(const char* fmt, ...);

@@ -794,8 +794,16 @@ lea_stem0_assemble_kernel(lea_vol lmap, lea_vol abmap, lea_vol dst, int dst_c0, 
     }
     const int64_t dHW = (int64_t)dst.H * dst.W, dPS = dHW * dst.D;
     lea_u4* ob = (lea_u4*)dst.data + ((int64_t)b * (dst.C >> 3) + (dst_c0 >> 3) + cb) * dst.P * dPS + (int64_t)h * dst.W + w;
+    float cst[8];                                                          // relu(bn(0)): the fully masked voxels
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cst[j] = (relu && sh[j] < 0.0f) ? 0.0f : sh[j];
+    const int tw = w >> 3;
     for (int d = d0; d < d1; ++d) {
-        if (!lea_cv_interior(d, w >> 3, dst.D, dst.W)) continue;
+        if (lea_cv_masked(d, tw)) {
+            lea_store8_at(ob + (int64_t)d * dHW, dPS, dst.P, cst);
+            continue;
+        }
+        if (!lea_cv_interior(d, tw, dst.D, dst.W)) continue;
         const int k = (w - d - 1) - ia0;                                   // = tid + d1 - d - 1
         float out[8];
 #pragma unroll

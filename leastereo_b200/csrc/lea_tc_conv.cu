@@ -221,7 +221,9 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
 __device__ __forceinline__ bool item_skipped(const TcParams& p, const ItemGeom& g) {
     if (!p.cv_skip) return false;
     const int tw = g.w0 >> 3;
-    return lea_cv_interior(g.d0, tw, p.D, p.W) && lea_cv_interior(g.d_hi - 1, tw, p.D, p.W);
+    // both predicates are monotone in d over a chunk (interior: a range test; masked: d >= 8 tw + 10)
+    return (lea_cv_interior(g.d0, tw, p.D, p.W) && lea_cv_interior(g.d_hi - 1, tw, p.D, p.W)) ||
+           (lea_cv_masked(g.d0, tw) && lea_cv_masked(g.d_hi - 1, tw));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -584,7 +586,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
                             }
                         }
-                        if (!valid || (p.cv_skip && lea_cv_interior(d, g.w0 >> 3, p.D, p.W))) continue;
+                        if (!valid || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];

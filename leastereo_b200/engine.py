@@ -286,7 +286,7 @@ class MatchingPlan:
         tc_step.opts.cv_skip = 1
         tiles_w = (W + 7) // 8
         interior = sum(1 for d in range(D) for tw in range(tiles_w)
-                       if d >= 1 and d <= D - 2 and 8 * tw >= d + 2 and 8 * tw + 7 <= W - 2)
+                       if (d >= 1 and d <= D - 2 and 8 * tw >= d + 2 and 8 * tw + 7 <= W - 2) or 8 * tw + 7 <= d - 3)
         frac = 1.0 - interior * 8.0 / (D * W)
         tc_step.flops *= frac
         scale, shift = self._bn_slices([st]) if st.use_bn else (None, None)

@@ -171,7 +171,7 @@ def check_stem0_collapse(ops, device):
     """Collapsed stem0: L/A/B 2-D maps (derived weights, ordinary conv kernel on depth-1 volumes) + lea_stem0_assemble
     against conv3d over the materialised cost volume (LEAStereo.py:34-48 + skip_model_3d.py:141) on every voxel the
     assemble kernel claims; the other voxels must stay untouched."""
-    B, fm, co, maxdisp, H, W = 2, 8, 8, 21, 5, 40
+    B, fm, co, maxdisp, H, W = 2, 8, 8, 39, 5, 40            # D = 13: one fully masked tile (d >= 10, w < 8)
     D = maxdisp // 3
     fx, fy = _rand((B, fm, H, W), 71, device), _rand((B, fm, H, W), 72, device)
     w = _rand((co, 2 * fm, 3, 3, 3), 73, device, scale=0.2)
@@ -192,7 +192,8 @@ def check_stem0_collapse(ops, device):
     claimed = torch.zeros((D, W), dtype=torch.bool)
     for d in range(D):
         for x in range(W):
-            claimed[d, x] = (1 <= d <= D - 2) and (8 * (x // 8) >= d + 2) and (8 * (x // 8) + 7 <= W - 2)
+            claimed[d, x] = ((1 <= d <= D - 2) and (8 * (x // 8) >= d + 2) and (8 * (x // 8) + 7 <= W - 2)) or \
+                (8 * (x // 8) + 7 <= d - 3)
     assert int(claimed.sum()) > 0
     m = claimed.view(1, 1, D, 1, W).expand_as(got)
     err = float((got - ref)[m].abs().max()) / float(ref.abs().max())
