@@ -46,7 +46,7 @@ class Slice:
 class Step:
     kind: str                      # "conv_simt" | "conv_tc" | "resample"
     name: str                      # module path(s), for per-kernel timing reports
-    flops: float = 0.0             # 2*M*N*K for convs
+    flops: float = 0.0             # 2*M*N*K for convs, as launched
     bytes: float = 0.0             # algorithmic bytes read+written
     # conv
     p: object = None               # lea_conv
@@ -58,6 +58,7 @@ class Step:
     ref: Optional[torch.Tensor] = None
     wfn: object = None             # callable(step): fills step.wcat with weights DERIVED from the modules' parameters
     planes: int = 0                # plane count of the packed weight image (0 = the plan's)
+    ref_flops: float = -1.0        # 2*M*N*K of the reference conv(s) this launch stands for (-1: same as flops)
     # resample
     rs: tuple = ()
 
@@ -288,7 +289,10 @@ class MatchingPlan:
         interior = sum(1 for d in range(D) for tw in range(tiles_w)
                        if (d >= 1 and d <= D - 2 and 8 * tw >= d + 2 and 8 * tw + 7 <= W - 2) or 8 * tw + 7 <= d - 3)
         frac = 1.0 - interior * 8.0 / (D * W)
+        tc_step.ref_flops = tc_step.flops             # the reference's stem0: the whole volume
         tc_step.flops *= frac
+        for ms in self.steps[n_before - 2: n_before]:
+            ms.ref_flops = 0.0                         # the 2-D maps have no counterpart of their own
         scale, shift = self._bn_slices([st]) if st.use_bn else (None, None)
         nbytes = 2.0 * self.P * B * D * H * W * c_out * (1.0 - frac) + 2.0 * P3 * B * H * W * 3 * c_out
         self.steps.append(Step("stem0_assemble", "stem0.collapsed.assemble", 0.0, nbytes,
@@ -312,6 +316,7 @@ class MatchingPlan:
         elif self.fuse and _prod(src.spatial) < _prod(spatial):
             small = Slice(self._vol(dst.c, src.spatial), 0, dst.c)
             self._emit_conv(name + "(raw,low-res)", mod, src, small, raw=True)
+            self.steps[-1].ref_flops = self.steps[-1].flops * _prod(spatial) / _prod(src.spatial)   # reference: after the up-sample
             self._resample(name + ".upsample+bn+relu", small, spatial, dst=dst, bn_of=mod, relu=mod.relu)
         else:
             r = self._resample(name + ".resample", src, spatial)
@@ -495,6 +500,7 @@ class MatchingPlan:
             # volume (27 tap channels), the separable interpolation + tap shifts are summed by lea_head_taps
             q = Slice(self._vol(32, pre.spatial), 0, 32)
             self._emit_tap_projection("last_3.taps(low-res)", l3, pre, q)
+            self.steps[-1].ref_flops = 2.0 * self.B * _prod(L0) * l3.conv.in_channels * 27      # last_3 on the up-sampled volume
             ws = self.ops.head_taps_workspace(q.vol, L0)
             nbytes = 2.0 * self.P * self.B * _prod(pre.spatial) * 32 + 4.0 * self.B * _prod(L0)
             self.steps.append(Step("head_taps", "head.upsample_6+last_3", 0.0, nbytes, rs=(q.vol, 0, self.mat, ws)))
@@ -590,6 +596,10 @@ class MatchingPlan:
 
     def conv_flops(self) -> float:
         return sum(s.flops for s in self.steps)
+
+    def reference_conv_flops(self) -> float:
+        """2*M*N*K summed over the reference's own conv list (1344.17 GFLOP per KITTI pair)."""
+        return sum((s.ref_flops if s.ref_flops >= 0.0 else s.flops) for s in self.steps)
 
 
 class FeaturePlan(MatchingPlan):

@@ -210,13 +210,14 @@ def check_disparity_regression(ops, device):
     assert float((got - want).abs().max()) <= 1e-4
 
 
-def run_hot_path(ops, device, g, planes, conv="simt", mma_terms=0):
+def run_hot_path(ops, device, g, planes, conv="simt", mma_terms=0, extra=None):
     """Product engine on a golden case's feature maps; returns (mat, disp) on CPU."""
     maxdisp = int(g["maxdisp"])
     model = seeded_model(maxdisp)
     model.load_state_dict(golden_state_dict(g, model))
     model = model.to(device).eval()
     model.engine_options = {"planes": planes, "conv": conv, "mma_terms": mma_terms}
+    model.engine_options.update(extra or {})
     fx, fy = torch.from_numpy(g["fx"]).to(device), torch.from_numpy(g["fy"]).to(device)
     disp = engine.hot_path_forward(model, fx, fy, ops=ops)
     B, _, H3, W3 = fx.shape
@@ -224,9 +225,10 @@ def run_hot_path(ops, device, g, planes, conv="simt", mma_terms=0):
     return plan.mat.cpu().clone(), disp.cpu(), model, plan
 
 
-def check_hot_path_golden(ops, device, name, planes, conv="simt", mma_terms=0, mat_rtol=2e-4, require_tolerance=True):
+def check_hot_path_golden(ops, device, name, planes, conv="simt", mma_terms=0, mat_rtol=2e-4, require_tolerance=True,
+                          extra=None):
     g = load_golden(name)
-    mat, disp, _, _ = run_hot_path(ops, device, g, planes, conv, mma_terms)
+    mat, disp, _, _ = run_hot_path(ops, device, g, planes, conv, mma_terms, extra)
     ref_mat, ref_disp = torch.from_numpy(g["mat"]), torch.from_numpy(g["disp"])
     assert mat.shape == ref_mat.shape and disp.shape == ref_disp.shape
     rel = float((mat - ref_mat).abs().max()) / float(ref_mat.abs().max())

@@ -18,14 +18,20 @@ def main():
     ops = get_ops()
     dev = torch.device("cuda:0")
     modes = [("simt", 3, 0), ("simt", 2, 0), ("tc", 3, 0), ("tc", 2, 0), ("tc", 2, 1)]
-    if len(sys.argv) > 1:
-        modes = [m for m in modes if m[0] in sys.argv[1:]]
+    extra = None
+    args = sys.argv[1:]
+    if "--extra" in args:                       # engine-option overrides as JSON, e.g. --extra '{"accum_split": 2}'
+        i = args.index("--extra")
+        extra = json.loads(args[i + 1])
+        args = args[:i] + args[i + 2:]
+    if args:
+        modes = [m for m in modes if m[0] in args]
     out = []
     print("%-20s %-6s %-2s %-5s | %-9s %-9s %-8s %-9s %s" % ("case", "conv", "P", "terms", "frac<=0.1", "mean", "max", "mat_rel", "ok"))
     for name in GOLDEN_CASES:
         for conv, planes, terms in modes:
             rep = K.check_hot_path_golden(ops, dev, name, planes=planes, conv=conv, mma_terms=terms, mat_rtol=None,
-                                          require_tolerance=False)
+                                          require_tolerance=False, extra=extra)
             print("%-20s %-6s %-2d %-5d | %-9.5f %-9.5f %-8.4f %-9.2e %s" % (
                 name, conv, planes, terms, rep["frac_within_0p1"], rep["mean_abs"], rep["max_abs"], rep["mat_rel_err"],
                 "PASS" if rep["ok"] else "FAIL"))
