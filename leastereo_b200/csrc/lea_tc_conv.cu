@@ -212,6 +212,13 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
     g.d0 = dc * p.Dc;
     g.d_hi = min(g.d0 + p.Dc, p.D);
     g.h0 = th * (128 >> p.tw_log2); g.w0 = tw << p.tw_log2;
+    if (p.cv_skip) {
+        // collapsed stem0: keep only the depths of the chunk that lea_stem0_assemble does not write.  For one w tile
+        // they are contiguous (depth 0 | the band 8 tw - 1 .. 8 tw + 9 | depth D-1), so trimming both ends is exact;
+        // an edge chunk then streams 2 slabs instead of Dc + 2.  Empty range = the item is skipped by every role.
+        while (g.d0 < g.d_hi && lea_cv_collapsed(g.d0, tw, p.D, p.W)) ++g.d0;
+        while (g.d_hi > g.d0 && lea_cv_collapsed(g.d_hi - 1, tw, p.D, p.W)) --g.d_hi;
+    }
     if (p.ks == 3) { g.dlo = max(g.d0 - 1, 0); g.dhi = min(g.d_hi, p.D - 1); }
     else           { g.dlo = g.d0;             g.dhi = g.d_hi - 1; }
     return g;
@@ -219,11 +226,7 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
 
 // collapsed stem0: true when every voxel of the item is written by lea_stem0_assemble (the item is skipped by all roles)
 __device__ __forceinline__ bool item_skipped(const TcParams& p, const ItemGeom& g) {
-    if (!p.cv_skip) return false;
-    const int tw = g.w0 >> 3;
-    // both predicates are monotone in d over a chunk (interior: a range test; masked: d >= 8 tw + 10)
-    return (lea_cv_interior(g.d0, tw, p.D, p.W) && lea_cv_interior(g.d_hi - 1, tw, p.D, p.W)) ||
-           (lea_cv_masked(g.d0, tw) && lea_cv_masked(g.d_hi - 1, tw));
+    return p.cv_skip && g.d0 >= g.d_hi;
 }
 
 // ---------------------------------------------------------------------------------------------------------
