@@ -545,10 +545,51 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
             m[q] = o < m[q] ? o : m[q];
         }
     }
-    // pass 2: this lane's quarter of the maxdisp output samples; (k0, k1) window along disparity
     float den[9], num[9], u0[9], u1[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) { den[q] = 0.0f; num[q] = 0.0f; u0[q] = 0.0f; u1[q] = 0.0f; }
+    if (maxdisp == 3 * D3) {
+        // pass 2, exact x3 scale (every BASELINE config): output 0 is sample 0, 3k+1 is sample k, 3k+2 and 3k+3 blend
+        // samples k and k+1 with weights (2/3, 1/3) and (1/3, 2/3) (sample D3 := sample D3-1).  With
+        // T_k = exp((m - u_k) / 3) the three softmin terms are T_k^3, T_k^2 T_{k+1}, T_k T_{k+1}^2: ONE exp per sample
+        // instead of three and no per-output blends.  This lane owns samples [ka, kb).
+        const int kchunk = (D3 + LEA_DH_PARTS - 1) / LEA_DH_PARTS;
+        const int ka = min(D3, part * kchunk), kb = min(D3, ka + kchunk);
+        const float c3 = 1.4426950408889634f / 3.0f;                   // log2(e) / 3
+        float T[9], raw[9], u[9];
+        if (ka < kb) {
+            LEA_DH_LOAD(raw, ka);
+            LEA_DH_COMBINE(u, raw);
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                T[q] = exp2f((m[q] - u[q]) * c3);              // subtract first: logits can be ~1e8
+                if (ka == 0) den[q] += T[q] * T[q] * T[q];             // output 0 (weight 0 in the numerator)
+            }
+        }
+        for (int k = ka; k < kb; ++k) {
+            float Tn[9];
+            if (k + 1 < D3) {
+                LEA_DH_LOAD(raw, k + 1);
+                LEA_DH_COMBINE(u, raw);
+#pragma unroll
+                for (int q = 0; q < 9; ++q) Tn[q] = exp2f((m[q] - u[q]) * c3);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) Tn[q] = T[q];
+            }
+            const float i1 = (float)(3 * k + 1), i2 = (float)(3 * k + 2), i3 = (float)(3 * k + 3);
+            const bool has3 = (k + 1 < D3);                             // output 3k+3 exists up to k = D3-2
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const float t2 = T[q] * T[q];
+                const float e1 = t2 * T[q], e2 = t2 * Tn[q], e3 = has3 ? T[q] * Tn[q] * Tn[q] : 0.0f;
+                den[q] += e1 + e2 + e3;
+                num[q] += e1 * i1 + e2 * i2 + e3 * i3;
+                T[q] = Tn[q];
+            }
+        }
+    } else {
+    // pass 2, general scale: this lane's quarter of the maxdisp output samples; (k0, k1) window along disparity
     int kc = -1, k1c = -1;
     const int ichunk = (maxdisp + LEA_DH_PARTS - 1) / LEA_DH_PARTS;
     const int ia = min(maxdisp, part * ichunk), ib = min(maxdisp, ia + ichunk);
@@ -584,6 +625,7 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
             den[q] += e;
             num[q] += e * fi;
         }
+    }
     }
 #pragma unroll
     for (int q = 0; q < 9; ++q) {

@@ -32,6 +32,7 @@ extern unsigned char* emu_dyn_smem;
 #define LEA_D inline
 #define __ldg(p) (*(p))
 #define __expf(x) expf(x)
+using std::exp2f;
 static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
 #include <atomic>
 static inline float atomicAdd(float* p, float v) { return std::atomic_ref<float>(*p).fetch_add(v, std::memory_order_relaxed); }
