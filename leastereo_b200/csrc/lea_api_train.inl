@@ -63,6 +63,17 @@ extern "C" int lea_conv3d_wgrad(const lea_vol* in, int32_t in_c0, int32_t c_in, 
             cudaFuncSetAttribute(lea_conv_wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
         LEA_LAUNCH(lea_conv_wgrad_kernel<3>, grid, dim3(128), smem, stream, *in, in_c0, c_in, *dout, dout_c0, c_out, dw);
+    } else if ((c_in >> 2) * (cpad >> 2) <= 512 && (size_t)LEA_W1_VOX * (c_in + cpad) * sizeof(float) <= 96 * 1024) {
+        // skinny-GEMM kernel: (c_out/4) x (c_in/4) register blocks fit 256 threads x 2
+        const size_t smem = (size_t)LEA_W1_VOX * (c_in + cpad) * sizeof(float);
+        const int64_t sp = (int64_t)in->D * in->H * in->W;
+        const int chunks = (int)((sp + (int64_t)LEA_W1_VOX * LEA_W1_TILES - 1) / ((int64_t)LEA_W1_VOX * LEA_W1_TILES));
+#ifndef LEA_CPU_EMU
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(lea_conv1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+        LEA_LAUNCH(lea_conv1_wgrad_kernel, dim3(chunks, in->B), dim3(256), smem, stream, *in, in_c0, c_in, *dout, dout_c0,
+                   c_out, cpad, dw);
     } else {
         const size_t smem = (size_t)(8 * LEA_TH * LEA_TW + cpad * 128) * sizeof(float);
         LEA_LAUNCH(lea_conv_wgrad_kernel<1>, grid, dim3(128), smem, stream, *in, in_c0, c_in, *dout, dout_c0, c_out, dw);

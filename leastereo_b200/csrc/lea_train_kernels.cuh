@@ -26,27 +26,29 @@ lea_channel_reduce_kernel(lea_vol x, int x_c0, lea_vol dy, int dy_c0, int c, int
     float s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s0[j] = 0.0f; s1[j] = 0.0f; }
-    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < vox; v += (int64_t)gridDim.x * 256) {
-        const int b = (int)(v / sp);
-        const int64_t r = v - (int64_t)b * sp;
-        const int d = (int)(r / ((int64_t)x.H * x.W));
-        const int hw = (int)(r - (int64_t)d * x.H * x.W);
-        const int h = hw / x.W, w = hw - h * x.W;
-        float f[8];
-        lea_vol_load8(x, b, (x_c0 >> 3) + cb, d, h, w, f);
-        if (mode == 0) {
+    // a channel block of one batch element is contiguous over (d, h, w): walk it linearly (no per-voxel divisions;
+    // the kernel was instruction-bound on index arithmetic)
+    (void)vox;
+    for (int b = 0; b < x.B; ++b) {
+        const lea_u4* xb = (const lea_u4*)x.data + ((int64_t)b * (x.C >> 3) + (x_c0 >> 3) + cb) * x.P * sp;
+        const lea_u4* gb = (const lea_u4*)dy.data + ((int64_t)b * (dy.C >> 3) + (dy_c0 >> 3) + cb) * dy.P * sp;
+        for (int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; r < sp; r += (int64_t)gridDim.x * 256) {
+            float f[8];
+            lea_load8_at(xb + r, sp, x.P, f);
+            if (mode == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] += f[j] * f[j]; }
-        } else {
-            float g[8];
-            lea_vol_load8(dy, b, (dy_c0 >> 3) + cb, d, h, w, g);
+                for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] += f[j] * f[j]; }
+            } else {
+                float g[8];
+                lea_load8_at(gb + r, sp, dy.P, g);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int ch = cb * 8 + j;
-                const float y = scale ? f[j] * scale[ch] + shift[ch] : f[j];
-                const float gg = (relu && !(y > 0.0f)) ? 0.0f : g[j];
-                const float xh = mean ? (f[j] - mean[ch]) * invstd[ch] : f[j];
-                s0[j] += gg; s1[j] += gg * xh;
+                for (int j = 0; j < 8; ++j) {
+                    const int ch = cb * 8 + j;
+                    const float y = scale ? f[j] * scale[ch] + shift[ch] : f[j];
+                    const float gg = (relu && !(y > 0.0f)) ? 0.0f : g[j];
+                    const float xh = mean ? (f[j] - mean[ch]) * invstd[ch] : f[j];
+                    s0[j] += gg; s1[j] += gg * xh;
+                }
             }
         }
     }
@@ -237,6 +239,92 @@ lea_conv_wgrad_kernel(lea_vol in, int in_c0, int c_in, lea_vol dout, int dout_c0
                     for (int t = 0; t < TAPS; ++t) atomicAdd(dw + ((int64_t)co * c_in + ci) * TAPS + t, acc[q][t]);
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 1x1x1 weight gradient: dW[co][ci] += sum_v dO[v][co] * In[v][ci] - a skinny GEMM (K = voxels), HBM-bound on reading
+// In and dO once.  One CTA walks LEA_W1_TILES tiles of 64 consecutive voxels of one batch element; a tile is staged in
+// shared memory as fp32 [voxel][channel] and every thread accumulates a 4 x 4 block of (co, ci) pairs in registers
+// (2 vector loads per 16 FMAs); one atomic flush per CTA.  grid (voxel chunks, B), block 256.
+// ---------------------------------------------------------------------------------------------------------
+#define LEA_W1_VOX 64
+#define LEA_W1_TILES 64
+__global__ void __launch_bounds__(256)
+lea_conv1_wgrad_kernel(lea_vol in, int in_c0, int c_in, lea_vol dout, int dout_c0, int c_out, int cpad,
+                       float* __restrict__ dw /* [c_out][c_in] */) {
+    LEA_DYN_SMEM(float, smem);
+    float* in_s = smem;                                  // [LEA_W1_VOX][c_in]
+    float* do_s = smem + LEA_W1_VOX * c_in;              // [LEA_W1_VOX][cpad]
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int64_t sp = (int64_t)in.D * in.H * in.W;
+    const int64_t v_begin = (int64_t)blockIdx.x * LEA_W1_VOX * LEA_W1_TILES;
+    const int64_t v_end = v_begin + LEA_W1_VOX * LEA_W1_TILES < sp ? v_begin + LEA_W1_VOX * LEA_W1_TILES : sp;
+    const lea_u4* ib = (const lea_u4*)in.data + ((int64_t)b * (in.C >> 3) + (in_c0 >> 3)) * in.P * sp;
+    const lea_u4* gb = (const lea_u4*)dout.data + ((int64_t)b * (dout.C >> 3) + (dout_c0 >> 3)) * dout.P * sp;
+    const int nci4 = c_in >> 2, nco4 = cpad >> 2;
+    const int nblk = nci4 * nco4;                        // 4 x 4 blocks of (co, ci); each thread owns blocks tid, tid+256
+    float acc[2][16];
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[q][t] = 0.0f;
+    for (int64_t v0 = v_begin; v0 < v_end; v0 += LEA_W1_VOX) {
+        __syncthreads();
+        // stage: one (voxel, channel block) group per thread iteration
+        for (int e = tid; e < LEA_W1_VOX * (c_in >> 3); e += 256) {
+            const int vx = e % LEA_W1_VOX, cb = e / LEA_W1_VOX;
+            float f[8];
+            if (v0 + vx < v_end) lea_load8_at(ib + (int64_t)cb * in.P * sp + v0 + vx, sp, in.P, f);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) in_s[vx * c_in + cb * 8 + j] = f[j];
+        }
+        for (int e = tid; e < LEA_W1_VOX * (cpad >> 3); e += 256) {
+            const int vx = e % LEA_W1_VOX, cb = e / LEA_W1_VOX;
+            float f[8];
+            if (v0 + vx < v_end && cb * 8 < c_out) lea_load8_at(gb + (int64_t)cb * dout.P * sp + v0 + vx, sp, dout.P, f);
+            else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) do_s[vx * cpad + cb * 8 + j] = f[j];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int blk = tid + q * 256;
+            if (blk < nblk) {
+                const int co4 = blk / nci4, ci4 = blk - co4 * nci4;
+                for (int vx = 0; vx < LEA_W1_VOX; ++vx) {
+                    const float4 a = *reinterpret_cast<const float4*>(do_s + vx * cpad + co4 * 4);
+                    const float4 x = *reinterpret_cast<const float4*>(in_s + vx * c_in + ci4 * 4);
+                    acc[q][0] += a.x * x.x; acc[q][1] += a.x * x.y; acc[q][2] += a.x * x.z; acc[q][3] += a.x * x.w;
+                    acc[q][4] += a.y * x.x; acc[q][5] += a.y * x.y; acc[q][6] += a.y * x.z; acc[q][7] += a.y * x.w;
+                    acc[q][8] += a.z * x.x; acc[q][9] += a.z * x.y; acc[q][10] += a.z * x.z; acc[q][11] += a.z * x.w;
+                    acc[q][12] += a.w * x.x; acc[q][13] += a.w * x.y; acc[q][14] += a.w * x.z; acc[q][15] += a.w * x.w;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int blk = tid + q * 256;
+        if (blk < nblk) {
+            const int co4 = blk / nci4, ci4 = blk - co4 * nci4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int co = co4 * 4 + i, ci = ci4 * 4 + j;
+                    if (co < c_out) atomicAdd(dw + (int64_t)co * c_in + ci, acc[q][i * 4 + j]);
+                }
         }
     }
 }

@@ -352,11 +352,13 @@ class Ops:
 
     def channel_reduce(self, x: PlanesVol, x_c0: int, c: int, mode: int = 0, dy: Optional[PlanesVol] = None,
                        dy_c0: int = 0, relu: bool = False, scale=None, shift=None, mean=None, invstd=None,
-                       chunks: int = 64) -> torch.Tensor:
+                       chunks: int = 0) -> torch.Tensor:
         """Per-channel (sum, sum of squares) [mode 0] or BN-backward sums [mode 1]; returns float64 (2, c)."""
         self._dev(x.t)
         vox = x.B * x.D * x.H * x.W
-        chunks = max(1, min(chunks, (vox + 255) // 256))
+        if chunks <= 0:
+            chunks = max(64, 1184 // max(1, c >> 3))          # ~8 CTAs per SM over all channel blocks
+        chunks = max(1, min(chunks, (vox // max(1, x.B) + 255) // 256))
         partial = torch.empty((chunks, 2, c), dtype=torch.float32, device=x.t.device)
         xs = x.struct()
         ds = dy.struct() if dy is not None else xs
