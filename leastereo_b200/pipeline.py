@@ -152,6 +152,16 @@ class FlatAdam:
                 self.grad[off:off + k].copy_(p.grad.reshape(-1))
             off += k
 
+    def allreduce(self, world_size: int, group=None):
+        """Average the gradients over the ranks: ONE all-reduce of the flat bucket, no packing copies (the parameters'
+        ``.grad`` tensors are views of it).  Per-replica BatchNorm statistics, as under ``nn.DataParallel``."""
+        if world_size <= 1:
+            return
+        import torch.distributed as dist
+        self._gather_grads()
+        dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+        self.grad.div_(world_size)
+
     def step(self):
         self._gather_grads()
         self.t += 1

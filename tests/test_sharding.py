@@ -90,3 +90,46 @@ def test_gradient_allreduce_flat_bucket(tmp_path):
     assert torch.allclose(res["g0"], torch.full((3, 4), 1.5))
     assert torch.allclose(res["g1"], torch.arange(5.0) * 1.5)
     assert res["g2"] is None
+
+
+def _flat_adam_worker(rank, world, port, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import shutil
+    from test_emu_kernels import EMU_LIB
+    from leastereo_b200.kernels import Ops
+    from leastereo_b200.pipeline import FlatAdam
+    ops = Ops(EMU_LIB, require_device_build=False)           # CPU emulation of the Adam kernel (test infrastructure)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.ones(3, 4)), torch.nn.Parameter(torch.ones(5))]
+    opt = FlatAdam(params, lr=0.1, ops=ops)
+    opt.zero_grad()
+    params[0].grad.add_(float(rank + 1))                      # accumulates in the flat bucket, like autograd
+    params[1].grad = torch.arange(5.0) * (rank + 1)           # a foreign .grad tensor
+    opt.allreduce(world)
+    g = opt.grad.clone()
+    opt.step()
+    if rank == 0:
+        torch.save({"g": g, "p0": params[0].detach().clone(), "p1": params[1].detach().clone()}, out_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_adam_allreduce(tmp_path):
+    """FlatAdam.allreduce: the flat gradient bucket is the all-reduce buffer; both ranks then take the same step."""
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    from test_emu_kernels import EMU_LIB
+    if not os.path.exists(EMU_LIB):
+        import __graft_entry__ as ge
+        ge.build()
+    out_path = str(tmp_path / "fa.pt")
+    mp.spawn(_flat_adam_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    res = torch.load(out_path)
+    assert torch.allclose(res["g"][:12], torch.full((12,), 1.5))
+    assert torch.allclose(res["g"][12:], torch.arange(5.0) * 1.5)
+    # first Adam step moves every parameter with a non-zero gradient by lr against the gradient's sign
+    assert torch.allclose(res["p0"], torch.full((3, 4), 0.9), atol=1e-5)
+    assert torch.allclose(res["p1"][1:], torch.full((4,), 0.9), atol=1e-5) and float(res["p1"][0]) == 1.0

@@ -6,12 +6,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from leastereo_b200 import LEAStereo, default_args
 from leastereo_b200.sharding import allreduce_gradients
+from leastereo_b200.pipeline import FlatAdam, masked_smooth_l1_loss
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4); ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1); ap.add_argument("--h", type=int, default=288)
     ap.add_argument("--w", type=int, default=576); ap.add_argument("--conv", default="tc")
+    ap.add_argument("--torch-optim", action="store_true", help="torch smooth_l1 + torch.optim.Adam instead of our kernels")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     lr = int(os.environ.get("LOCAL_RANK", "0"))
@@ -25,7 +27,10 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         model = LEAStereo(default_args(192), dev).to(dev).train()
     model.engine_options = {"planes": 2, "conv": a.conv}
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))      # train.py:76
+    if a.torch_optim:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))      # train.py:76
+    else:
+        opt = FlatAdam(model.parameters(), lr=1e-3, betas=(0.9, 0.999))              # one launch over the flat buffer
     g = torch.Generator().manual_seed(1 + rank)
     left = torch.randn(a.batch, 3, a.h, a.w, generator=g).to(dev)
     right = torch.randn(a.batch, 3, a.h, a.w, generator=g).to(dev)
@@ -33,12 +38,21 @@ def main():
     params = [p for p in model.parameters()]
 
     def step():
-        opt.zero_grad(set_to_none=True)
+        if a.torch_optim:
+            opt.zero_grad(set_to_none=True)
+        else:
+            opt.zero_grad()
         disp = model(left, right)
-        mask = (target < 192) & (target > 0.001)
-        loss = torch.nn.functional.smooth_l1_loss(disp[mask], target[mask])
+        if a.torch_optim:
+            mask = (target < 192) & (target > 0.001)
+            loss = torch.nn.functional.smooth_l1_loss(disp[mask], target[mask])
+        else:
+            loss = masked_smooth_l1_loss(disp, target, 192)                             # train.py:116-118,157
         loss.backward()
-        allreduce_gradients(params, world)
+        if a.torch_optim:
+            allreduce_gradients(params, world)
+        else:
+            opt.allreduce(world)                                                        # the flat bucket itself
         opt.step()
         return loss
 
@@ -56,7 +70,7 @@ def main():
     if rank == 0:
         print(json.dumps({"metric": "training fwd+bwd+Adam, SceneFlow crop %dx%d D=192, batch %d/GPU" % (a.h, a.w, a.batch),
                           "n_gpus": world, "ms_per_step": float(ms), "pairs_per_s": a.batch * world / (float(ms) / 1e3),
-                          "loss": float(loss), "conv": a.conv, "max_mem_GB": torch.cuda.max_memory_allocated() / 2**30}))
+                          "loss": float(loss.detach()), "optimizer": "torch" if a.torch_optim else "FlatAdam + masked_smooth_l1 kernels", "conv": a.conv, "max_mem_GB": torch.cuda.max_memory_allocated() / 2**30}))
     if dist: dist.barrier(); dist.destroy_process_group()
 
 if __name__ == "__main__":
