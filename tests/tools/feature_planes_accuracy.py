@@ -1,7 +1,7 @@
 """Development aid: full-forward tolerance vs the golden vectors for feature-net plane counts."""
 import os, sys
 import torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import kernel_checks as K
 from conftest import GOLDEN_CASES, load_golden
