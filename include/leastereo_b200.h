@@ -91,7 +91,8 @@ typedef struct lea_tc_opts {
     int32_t num_sms;   /* 0 = query */
     int32_t accum_split;   /* 0 = default (1): hi*hi term in its own TMEM accumulator, correction terms in a second one
                               (the tensor core loses ~1 ulp per fp32 accumulation step; this cuts the steps of the
-                              dominant accumulator 3x); 2 = all terms share one accumulator (more depth per work item) */
+                              dominant accumulator 3x); 2 = all terms share one accumulator (more depth per work item);
+                              3 = two accumulators only when the reduction spans more than one 16-channel group */
     int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
     const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
     int32_t resident_weights;  /* 0 = auto (all channel groups' weights stay in shared memory when they fit), 2 = never */

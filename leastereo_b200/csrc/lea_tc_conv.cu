@@ -1071,7 +1071,12 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
             // accumulation step (measured: error grows linearly with the number of steps), so the dominant term
             // hi*hi gets an accumulator of its own (region 0) and all correction terms, 2^-8 smaller, share
             // region 1; the epilogue adds the two regions in fp32.
-            const bool split = !(opts && opts->accum_split == 2);
+            // accum_split 3: two regions only for long reductions (more than one 16-channel group at k = 3); a single
+            // 16-channel group accumulates 9 taps x 3 terms = 27 steps, where one region costs little accuracy and
+            // halves the TMEM columns per depth (twice the depth per item: fewer halo slabs)
+            bool split = !(opts && opts->accum_split == 2);
+            if (opts && opts->accum_split == 3) split = (s.ncg * s.taps2d > 9);
+            if (opts && opts->accum_split == 4) split = (s.ncg * s.taps2d > 18);      // ... more than two groups
             p.ngroups = (P > 1 && split) ? 2 : 1;
             for (int pw = 0; pw < P; ++pw)                     // weight plane pw = weight tile pw
                 for (int t = 0; t + pw < P; ++t) {             // activation plane t (plane t of cb 0; cb 1 is P blocks on)
