@@ -171,10 +171,19 @@ def check_stem0_collapse(ops, device):
     """Collapsed stem0: L/A/B 2-D maps (derived weights, ordinary conv kernel on depth-1 volumes) + lea_stem0_assemble
     against conv3d over the materialised cost volume (LEAStereo.py:34-48 + skip_model_3d.py:141) on every voxel the
     assemble kernel claims; the other voxels must stay untouched."""
-    B, fm, co, maxdisp, H, W = 2, 8, 8, 39, 5, 40            # D = 13: one fully masked tile (d >= 10, w < 8)
+    worst = 0.0
+    # (B, maxdisp, H, W): D = 13 with a fully masked tile; ragged width (last tile partial); minimum depth 3;
+    # D3 == W3 (every disparity column in play, deep masked triangle)
+    for (B, maxdisp, H, W) in [(2, 39, 5, 40), (1, 30, 3, 27), (1, 9, 4, 24), (1, 96, 2, 32)]:
+        worst = max(worst, _stem0_collapse_case(ops, device, B, maxdisp, H, W))
+    return worst
+
+
+def _stem0_collapse_case(ops, device, B, maxdisp, H, W):
+    fm, co = 8, 8
     D = maxdisp // 3
-    fx, fy = _rand((B, fm, H, W), 71, device), _rand((B, fm, H, W), 72, device)
-    w = _rand((co, 2 * fm, 3, 3, 3), 73, device, scale=0.2)
+    fx, fy = _rand((B, fm, H, W), 71 + W, device), _rand((B, fm, H, W), 72 + W, device)
+    w = _rand((co, 2 * fm, 3, 3, 3), 73 + W, device, scale=0.2)
     scale = (_rand((co,), 74, device).abs() + 0.5).contiguous()
     shift = _rand((co,), 75, device).contiguous()
     wl, wab = engine.collapsed_stem0_weights(w, fm)
@@ -194,13 +203,58 @@ def check_stem0_collapse(ops, device):
         for x in range(W):
             claimed[d, x] = ((1 <= d <= D - 2) and (8 * (x // 8) >= d + 2) and (8 * (x // 8) + 7 <= W - 2)) or \
                 (8 * (x // 8) + 7 <= d - 3)
-    assert int(claimed.sum()) > 0
+    assert int(claimed.sum()) > 0, (D, W)
     m = claimed.view(1, 1, D, 1, W).expand_as(got)
     err = float((got - ref)[m].abs().max()) / float(ref.abs().max())
     assert err <= 2e-6, err
     assert float(got[~m].abs().max()) == 0.0, "wrote outside the claimed voxels"
     assert float(ops.unpack(dst, 0, 8).abs().max()) == 0.0
     return err
+
+
+def check_stem0_collapse_tc(ops, device):
+    """GPU only: the two kernels that share stem0's output - lea_stem0_assemble and the tensor-core launch with the
+    fused cost-volume loader and cv_skip - must together write EVERY voxel exactly once and agree with conv3d over the
+    materialised cost volume; ragged width, a depth range with masked tiles, batch 2."""
+    from leastereo_b200.kernels import lea_tc_opts
+    worst = 0.0
+    for (B, maxdisp, H, W) in [(2, 39, 20, 43), (1, 75, 16, 32), (1, 9, 16, 24)]:
+        fm, co, P = 16, 16, 2
+        D = maxdisp // 3
+        fx, fy = _rand((B, fm, H, W), 81 + W, device), _rand((B, fm, H, W), 82 + W, device)
+        w = _rand((co, 2 * fm, 3, 3, 3), 83 + W, device, scale=0.2)
+        scale = (_rand((co,), 84, device).abs() + 0.5).contiguous()
+        shift = _rand((co,), 85, device).contiguous()
+        # 2-D maps (exact planes, fp32 FMA convs) + assemble
+        wl, wab = engine.collapsed_stem0_weights(w, fm)
+        fx3, fy3 = ops.pack(fx, 3), ops.pack(fy, 3)
+        lmap = PlanesVol.empty(B, co, 3, 1, H, W, device)
+        abmap = PlanesVol.empty(B, 2 * co, 3, 1, H, W, device)
+        ops.conv3d_simt(ops.make_conv(fx3, 0, fm, co, 3, None, None, False, dst=lmap), wl.contiguous(), fx)
+        ops.conv3d_simt(ops.make_conv(fy3, 0, fm, 2 * co, 3, None, None, False, dst=abmap), wab.contiguous(), fy)
+        dst = PlanesVol.empty(B, co, P, D, H, W, device)
+        dst.t.fill_(float("nan"))                              # every voxel must be overwritten
+        ops.stem0_assemble(lmap, abmap, dst, 0, co, scale, shift, True)
+        # band + edges: tensor-core kernel, cost volume built by its loader, skipping the assembled voxels
+        fxy = PlanesVol.empty(2 * B, fm, P, 1, H, W, device)
+        fxp, fyp = PlanesVol(fxy.t[:B]), PlanesVol(fxy.t[B:])
+        ops.pack(fx, P, out=fxp); ops.pack(fy, P, out=fyp)
+        maps = ops.build_fused_cv_maps(fxp, fyp, D)
+        p = ops.make_conv(fxp, 0, 2 * fm, co, 3, scale, shift, True, dst=dst, dst_c0=0)
+        opts = lea_tc_opts()
+        opts.fused_cv, opts.fx, opts.fy, opts.d3 = 1, fxp.struct(), fyp.struct(), D
+        opts.cv_maps = maps.data_ptr()
+        opts.cv_skip = 1
+        ops.conv3d_tc(p, ops.pack_weights_tc(w.contiguous(), P), opts, fx)
+        torch.cuda.synchronize()
+        got = ops.unpack(dst).cpu()
+        assert torch.isfinite(got).all(), "a voxel was written by neither kernel"
+        cost = torch.from_numpy(O.cost_volume_numpy(fx.cpu().numpy(), fy.cpu().numpy(), maxdisp))
+        ref = F.relu(F.conv3d(cost, w.cpu(), None, 1, 1) * scale.cpu().view(1, -1, 1, 1, 1) + shift.cpu().view(1, -1, 1, 1, 1))
+        err = float((got - ref).abs().max()) / float(ref.abs().max())
+        assert err <= 2e-4, (B, maxdisp, H, W, err)            # 2-plane operands / storage
+        worst = max(worst, err)
+    return worst
 
 
 def check_disparity_regression(ops, device):

@@ -130,6 +130,10 @@ def _random_model(maxdisp, options):
     return model
 
 
+def test_stem0_collapse_tc_covers_every_voxel(ops):
+    print("assemble + band/edge tensor-core launch vs conv3d(cost volume): rel err", K.check_stem0_collapse_tc(ops, DEV))
+
+
 def test_collapsed_stem0_matches_plain(ops):
     """stem0 through the 2-D maps + assemble + band/edge tensor-core launch must agree with the plain fused-loader run
     on every voxel (different summation order: compare the stem0 output volume to fp32 rounding of 2 planes)."""
