@@ -693,90 +693,139 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;
         const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;
         int stage = 0, sphase = 0, wb = 0, wphase = 0;
-        // Ring bookkeeping without divisions (this warp's instruction stream is what feeds the tensor pipe): depth
-        // number q = R + (depths of earlier items) + (d - d0) lives in entry q % R, generation q / R - 1; (e0, par0)
-        // = (q % R, (q / R) & 1) of the item's first depth, advanced per slab.
-        int e0 = 0, par0 = 1;
-        uint32_t probed = 0;
+        // tcgen05.mma issue is synchronous with the tensor pipe (DESIGN.md 4.1 law ii): every instruction this warp
+        // executes between the last MMA of a slab and the first MMA of the next one is a pipe bubble.  All per-slab
+        // bookkeeping - kd range, ring entry and block, first-write count, the barriers to acquire / commit, and at an
+        // item boundary the decode of the next item - is therefore computed for the NEXT slab in the shadow of the
+        // current slab's MMAs (the ~20 spare cycles between two MMA issues), and the barriers the next slab needs are
+        // probed there with mbarrier.test_wait.
+        // Ring: depth number q = R + (depths of earlier items) + (d - d0) lives in entry q % R, generation q / R - 1;
+        // (e, par) = (q % R, (q / R) & 1), advanced without divisions.
+        struct Slab {
+            int valid, item, d_in, e, par, e0, par0;
+            ItemGeom g;
+            int nkd, nfresh;
+            uint32_t col0, brow16, idesc_all, open1, open1_par, open2, open2_par, done1, done2;
+        };
+        const uint32_t dempty0 = smem_u32(dempty), dfull0 = smem_u32(dfull);
+        auto derive = [&](Slab& c) {
+            const ItemGeom& g = c.g;
+            const int d_in = c.d_in, e = c.e, par = c.par;
+            const int kd_a = (d_in + 1 <= g.d_hi - 1) ? 0 : ((d_in <= g.d_hi - 1) ? 1 : 2);
+            const int kd_b = (d_in - 1 >= g.d0) ? 2 : ((d_in >= g.d0) ? 1 : 0);
+            c.nkd = kd_b - kd_a + 1;
+            const int h = R - e;
+            const int e_up = (e + 1 == R) ? 0 : e + 1, par_up = (e + 1 == R) ? par ^ 1 : par;   // depth d_in+1
+            const int e_dn = (e == 0) ? R - 1 : e - 1;                                           // depth d_in-1
+            // first writes (accumulate = 0) are a prefix of [kd_a, kd_b]: kd 0 always; everything when h == R; depth 0
+            const bool fr1 = (h == R) || (d_in == 0), fr2 = (h == R);
+            int nf;
+            if (kd_a == 0)      nf = 1 + ((kd_b >= 1 && fr1) ? 1 + ((kd_b >= 2 && fr2) ? 1 : 0) : 0);
+            else if (kd_a == 1) nf = fr1 ? 1 + ((kd_b >= 2 && fr2) ? 1 : 0) : 0;
+            else                nf = fr2 ? 1 : 0;
+            c.nfresh = nf;
+            c.col0 = (uint32_t)((h - 1 + kd_a) * p.NP);
+            c.brow16 = (uint32_t)(kd_a * p.NP);
+            c.idesc_all = c.nkd == 3 ? idesc3 : (c.nkd == 2 ? idesc2 : idesc1);
+            c.open1 = (kd_a == 0) ? dempty0 + 8u * (uint32_t)e_up : 0u;            c.open1_par = (uint32_t)par_up;
+            c.open2 = (d_in == 0 && kd_a <= 1 && kd_b >= 1) ? dempty0 + 8u * (uint32_t)e : 0u;   c.open2_par = (uint32_t)par;
+            c.done1 = (d_in - 1 >= g.d0) ? dfull0 + 8u * (uint32_t)e_dn : 0u;
+            c.done2 = (d_in == p.D - 1 && d_in < g.d_hi) ? dfull0 + 8u * (uint32_t)e : 0u;
+        };
+        auto first_of_item = [&](Slab& c, int item, int e0, int par0) {
+            c.item = item; c.e0 = e0; c.par0 = par0;
+            c.valid = item < p.total_items;
+            if (!c.valid) return;
+            c.g = decode_item(p, item);
+            c.d_in = c.g.dlo;
+            c.e = e0; c.par = par0;
+            if (c.g.dlo < c.g.d0) { if (c.e == 0) { c.e = R - 1; c.par ^= 1; } else --c.e; }   // leading halo slab
+            derive(c);
+        };
+        auto next_slab = [&](const Slab& c, Slab& n) {
+            if (c.d_in < c.g.dhi) {
+                n = c;
+                n.d_in = c.d_in + 1;
+                if (c.e + 1 == R) { n.e = 0; n.par = c.par ^ 1; } else n.e = c.e + 1;
+                derive(n);
+            } else {
+                int e0 = c.e0 + (c.g.d_hi - c.g.d0), par0 = c.par0;
+                while (e0 >= R) { e0 -= R; par0 ^= 1; }
+                first_of_item(n, c.item + (int)gridDim.x, e0, par0);
+            }
+        };
+        uint32_t probed = 0, opened = 0;
         if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const ItemGeom g = decode_item(p, item);
-            int e = e0, par = par0;                    // entry / parity of slab d_in's centre depth
-            if (g.dlo < g.d0) { if (e == 0) { e = R - 1; par ^= 1; } else --e; }
-            for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
-                const int kd_a = (d_in + 1 <= g.d_hi - 1) ? 0 : ((d_in <= g.d_hi - 1) ? 1 : 2);
-                const int kd_b = (d_in - 1 >= g.d0) ? 2 : ((d_in >= g.d0) ? 1 : 0);
-                const int nkd = kd_b - kd_a + 1;
-                const int h = R - e;
-                const int e_up = (e + 1 == R) ? 0 : e + 1, par_up = (e + 1 == R) ? par ^ 1 : par;   // depth d_in+1
-                const int e_dn = (e == 0) ? R - 1 : e - 1;                                           // depth d_in-1
-                // acquire the ring entries of the depths this slab opens (drained one generation ago)
-                if (!(p.dbg & 4)) {
-                if (kd_a == 0) mbar_wait(smem_u32(dempty + e_up), par_up, 204);
-                if (d_in == 0 && kd_a <= 1 && kd_b >= 1) mbar_wait(smem_u32(dempty + e), par, 205);   // slab 0 opens depth 0
+        Slab cur, nxt;
+        first_of_item(cur, (int)blockIdx.x, 0, 1);
+        nxt.valid = 0;
+        while (cur.valid) {
+            // acquire the ring entries of the depths this slab opens (drained one generation ago)
+            if (!opened) {
+                if (cur.open1) mbar_wait(cur.open1, cur.open1_par, 204);
+                if (cur.open2) mbar_wait(cur.open2, cur.open2_par, 205);
+            }
+            const uint32_t col0 = cur.col0, brow16 = cur.brow16, idesc_all = cur.idesc_all;
+            const int nkd = cur.nkd;
+            for (int cg = 0; cg < p.ncg; ++cg) {
+                if (!p.wres) mbar_wait(smem_u32(wfull + wb), wphase, 202);
+                const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
+                if (!probed) mbar_wait(smem_u32(full + stage), sphase, 203);
                 tc_fence_after();
-                }
-                int nfresh = 0;
-                for (int kd = kd_a; kd <= kd_b; ++kd) {
-                    const bool fr = (kd == 0) || (h == R) || (kd == 1 && d_in == 0);
-                    if (!fr) break;
-                    ++nfresh;
-                }
-                const uint32_t col0 = (uint32_t)((h - 1 + kd_a) * p.NP);
-                const uint32_t brow16 = (uint32_t)(kd_a * p.NP);
-                const uint32_t idesc_all = nkd == 3 ? idesc3 : (nkd == 2 ? idesc2 : idesc1);
-                for (int cg = 0; cg < p.ncg; ++cg) {
-                    if (!p.wres) mbar_wait(smem_u32(wfull + wb), wphase, 202);
-                    const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
-                    if (!probed) mbar_wait(smem_u32(full + stage), sphase, 203);
-                    tc_fence_after();
-                    const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
-                    const int nf = (cg == 0) ? nfresh : 0;
-                    const uint32_t idesc_fresh = nf == 3 ? idesc3 : (nf == 2 ? idesc2 : idesc1);
-                    const int nrest = nkd - nf;
-                    const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
+                const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
+                const int nf = (cg == 0) ? cur.nfresh : 0;
+                const uint32_t idesc_fresh = nf == 3 ? idesc3 : (nf == 2 ? idesc2 : idesc1);
+                const int nrest = nkd - nf;
+                const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
+                const bool last_cg = (cg + 1 == p.ncg);
 #pragma unroll
-                    for (int kh = 0; kh < 3; ++kh) {
+                for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                        for (int kw = 0; kw < 3; ++kw) {
-                            const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
-                            const uint32_t b_tap = w16 + (uint32_t)(kh * 3 + kw) * tap16 + brow16;
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
+                        const uint32_t b_tap = w16 + (uint32_t)(kh * 3 + kw) * tap16 + brow16;
 #pragma unroll
-                            for (int t = 0; t < NTERM; ++t) {
-                                const uint32_t a_lo = (a_tap + a_term16[t]) | a_lbo_field[t];
-                                const uint32_t b_lo = b_tap + b_term16[t];
-                                const uint32_t dcol = tmem_base + reg_col[t] + col0;
-                                if (kh == 0 && kw == 0 && t_first[t] && nf > 0) {
-                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
-                                    if (nrest > 0)
-                                        tc_mma_issue(elected, dcol + (uint32_t)(nf * p.NP), a_lo, a_hi,
-                                                     b_lo + (uint32_t)(nf * p.NP), b_hi, idesc_rest, 1u);
-                                } else {
-                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_all, 1u);
-                                }
+                        for (int t = 0; t < NTERM; ++t) {
+                            const uint32_t a_lo = (a_tap + a_term16[t]) | a_lbo_field[t];
+                            const uint32_t b_lo = b_tap + b_term16[t];
+                            const uint32_t dcol = tmem_base + reg_col[t] + col0;
+                            if (kh == 0 && kw == 0 && t_first[t] && nf > 0) {
+                                tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
+                                if (nrest > 0)
+                                    tc_mma_issue(elected, dcol + (uint32_t)(nf * p.NP), a_lo, a_hi,
+                                                 b_lo + (uint32_t)(nf * p.NP), b_hi, idesc_rest, 1u);
+                            } else {
+                                tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_all, 1u);
                             }
-                            if (kh == 0 && kw == 0) {
-                                const bool wrap = (stage + 1 == p.nstages);
-                                probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
+                        }
+                        // ---- work done in the MMA shadow ----
+                        if (kh == 0 && kw == 0) {
+                            const bool wrap = (stage + 1 == p.nstages);
+                            probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
+                        }
+                        if (kh == 1 && kw == 0 && last_cg) next_slab(cur, nxt);
+                        if (kh == 2 && kw == 1 && last_cg) {
+                            opened = 0;
+                            if (nxt.valid) {
+                                uint32_t ok = 1;
+                                if (nxt.open1) ok &= mbar_test(nxt.open1, nxt.open1_par);
+                                if (nxt.open2) ok &= mbar_test(nxt.open2, nxt.open2_par);
+                                opened = ok;
                             }
                         }
                     }
-                    tc_commit_if(elected, smem_u32(empty + stage));
-                    if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
-                    if (!p.wres) {
-                        tc_commit_if(elected, smem_u32(wempty + wb));
-                        if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
-                    }
                 }
-                // depths completed by this slab
-                if (!(p.dbg & 8)) {
-                if (d_in - 1 >= g.d0) tc_commit_if(elected, smem_u32(dfull + e_dn));
-                if (d_in == p.D - 1 && d_in < g.d_hi) tc_commit_if(elected, smem_u32(dfull + e));
+                tc_commit_if(elected, smem_u32(empty + stage));
+                if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                if (!p.wres) {
+                    tc_commit_if(elected, smem_u32(wempty + wb));
+                    if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
                 }
-                e = e_up; par = par_up;
             }
-            e0 += g.d_hi - g.d0;
-            while (e0 >= R) { e0 -= R; par0 ^= 1; }
+            // depths completed by this slab
+            if (cur.done1) tc_commit_if(elected, cur.done1);
+            if (cur.done2) tc_commit_if(elected, cur.done2);
+            cur = nxt;
         }
     } else if (warp < 6) {
         // ================= epilogue warps 2..5: one depth at a time, as they complete =================
@@ -807,7 +856,7 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
                         }
                     }
                 }
-                if (!(p.dbg & 8)) mbar_wait(smem_u32(dfull + e), par ^ 1, 301);
+                mbar_wait(smem_u32(dfull + e), par ^ 1, 301);
                 tc_fence_after();
                 const bool alias_lo = (hb == R) && (d >= 1);           // part written into block 0 by slab d-1
                 const bool alias_hi = (hb == 1) && (d <= p.D - 2);     // part written into block R+1 by slab d+1
@@ -1135,10 +1184,11 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.R = 512 / accw - 2;
     if (p.R > kMaxRing) p.R = kMaxRing;
     // Opt-in (opts->rolling == 1).  Measured on B200 (tools/roll_perf.py, KITTI shapes, 4 pairs): the rolling kernel
-    // issues 28 % fewer MMAs for stem1 but its per-slab time is ~25 % longer (tcgen05.mma issue is synchronous with
-    // the tensor pipe - queue depth ~1 - so the ring's extra barrier traffic and the continuously running epilogue
-    // show up as pipe bubbles): stem1 498 vs 505 us, 16-ch ops 36 vs 33 us, 8-ch ops 204 vs 153 us.  Kept for the
-    // next round (needs an epilogue that does not disturb the issuer); the chunked kernel is the default.
+    // issues 28 % fewer MMAs for stem1 but its per-slab time is ~35 % longer: stem1 526 vs 516 us, 16-ch ops 38 vs 35,
+    // 8-ch ops 205 vs 158, 32-ch level-2 ops 14.5 vs 12.9.  Ablations: epilogue doing no work -12 %, no ring barriers
+    // a further -7 %; moving all per-slab bookkeeping into the MMA shadow (this version) changed nothing, so the loss
+    // is not issuer arithmetic - the suspects left are the per-slab tcgen05.commit and TMEM reads next to the columns
+    // being accumulated.  Kept for the next round; the chunked kernel is the default.
     p.roll = (p.ks == 3 && p.R >= 4 && opts && opts->rolling == 1) ? 1 : 0;
     p.dbg = opts ? opts->debug : 0;
     p.cv_skip = (fused && opts->cv_skip == 1 && !p.roll) ? 1 : 0;

@@ -9,7 +9,8 @@ from quick_perf import timeit  # noqa: E402
 ops = get_ops()
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", "4"))
-cases = [("stem1", 32, 32, (64, 128, 416), False), ("L1op", 16, 16, (32, 64, 208), True), ("L0op", 8, 8, (64, 128, 416), True)]
+cases = [("stem1", 32, 32, (64, 128, 416), False), ("L1op", 16, 16, (32, 64, 208), True), ("L0op", 8, 8, (64, 128, 416), True),
+         ("L2op", 32, 32, (16, 32, 104), True)]
 for name, ci, co, sp, res in cases:
     src = PlanesVol.empty(B, ci, 2, *sp, dev)
     src.t.copy_(torch.randn(src.t.shape, device=dev).bfloat16() * 0.1)
@@ -19,7 +20,7 @@ for name, ci, co, sp, res in cases:
     sc = torch.ones(co, device=dev); sh = torch.zeros(co, device=dev)
     p = ops.make_conv(src, 0, ci, co, 3, sc, sh, True, dst=dst, res=dst if res else None)
     img = ops.pack_weights_tc(w, 2)
-    for knobs in [{}, {"debug": 8 << 8}, {"debug": 16 << 8}, {"debug": 32 << 8}, {"debug": 64 << 8}]:
+    for knobs in [{}, {"rolling": 1}, {"rolling": 1, "debug": 3}]:
         opts = lea_tc_opts()
         for kk, v in knobs.items():
             setattr(opts, kk, v)
