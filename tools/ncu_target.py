@@ -11,7 +11,8 @@ from leastereo_b200.kernels import get_ops, PlanesVol, lea_tc_opts  # noqa: E402
 
 
 def main():
-    which = sys.argv[1:] or ["stem0", "l1res", "l1batched", "conv1", "l0res", "cv", "disp", "resample", "headtaps", "pp64"]
+    which = sys.argv[1:] or ["stem0", "l1res", "l1batched", "conv1", "l0res", "cv", "disp", "resample", "headtaps", "pp64",
+                             "assemble"]
     ops = get_ops()
     dev = torch.device("cuda:0")
     B, C, H3, W3, D3, maxdisp = 1, 32, 128, 416, 64, 192
@@ -50,6 +51,14 @@ def main():
         mat = torch.randn(B, D3, H3, W3, device=dev) * 3
         for _ in range(2):
             ops.disp_head(mat, maxdisp)
+    if "assemble" in which:
+        lmap = PlanesVol.empty(B, 32, 3, 1, H3, W3, dev); lmap.t.copy_(torch.randn(lmap.t.shape, device=dev).bfloat16())
+        abmap = PlanesVol.empty(B, 64, 3, 1, H3, W3, dev); abmap.t.copy_(torch.randn(abmap.t.shape, device=dev).bfloat16())
+        dst = PlanesVol.empty(B, 32, 2, D3, H3, W3, dev)
+        sc = torch.ones(32, device=dev); sh = torch.zeros(32, device=dev)
+        for _ in range(2):
+            ops.stem0_assemble(lmap, abmap, dst, 0, 32, sc, sh, True)
+        del lmap, abmap, dst
     if "headtaps" in which:
         q = PlanesVol.empty(B, 32, 2, 32, 64, 208, dev); q.t.copy_(torch.randn(q.t.shape, device=dev).bfloat16())
         mat = torch.empty((B, 1, D3, H3, W3), device=dev)
