@@ -96,6 +96,8 @@ typedef struct lea_tc_opts {
     int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
     const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
     int32_t resident_weights;  /* 0 = auto (all channel groups' weights stay in shared memory when they fit), 2 = never */
+    int32_t early_drain;       /* k = 3: 1 = one accumulator set, depths go to the epilogue one by one while the last channel
+                                  group accumulates; 0 = default schedule (measured faster, see lea_tc_conv.cu) */
     int32_t cv_skip;           /* fused_cv only: 1 = leave the voxels lea_stem0_assemble writes (collapsed stem0) untouched */
     int32_t debug;             /* development switches of the rolling kernel's epilogue; 0 in production */
     int32_t rolling;           /* k = 3: 1 = rolling accumulator ring (needs <= 85 TMEM columns per depth), 0 = chunked kernel (default) */

@@ -73,6 +73,7 @@ struct TcParams {
     int slab_vox, pitch_vox, blk_bytes, stage_bytes, stage_stride;   // stride = bytes rounded up to 128 (TMA alignment)
     int nstages, nwbuf;
     int tw_log2;              // tile = (1 << tw_log2) voxels along w x (128 >> tw_log2) along h  (3 for k = 3)
+    int early;                // one accumulator set, depths handed to the epilogue one by one while the last channel group runs
     int cv_skip;              // collapsed stem0: skip the voxels lea_stem0_assemble writes (lea_cv_interior)
     int dbg;                  // development switches (bit 0: epilogue skips its stores, bit 1: skips the TMEM loads)
     int roll, R;              // rolling schedule (see lea_conv_tc_roll_kernel): R home accumulator blocks + 2 alias blocks
@@ -302,6 +303,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint64_t* wempty = wfull + 2;                   // [2]
     uint64_t* accfull = wempty + 2;                 // [2]
     uint64_t* accempty = accfull + 2;               // [2]
+    uint64_t* dready = accempty + 2;                // [kMaxRing] early drain: depth slot j of the item is final
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1536);
     float* s_scale = reinterpret_cast<float*>(smem + 1024);     // [64]  (barriers occupy the first KB)
     float* s_shift = s_scale + 64;                              // [64]
@@ -317,6 +319,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1);
             mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 32 * epi_warps(PL));
         }
+        for (int i = 0; i < kMaxRing; ++i) mbar_init(smem_u32(dready + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x >= 64 && threadIdx.x < 128) {
@@ -469,13 +472,23 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     }
                     tc_commit_if(elected, smem_u32(empty + stage));
                     if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                    if (p.early && cg + 1 == p.ncg) {
+                        // last channel group: slab d_in was the last contribution to depth d_in-1 (and to its own depth
+                        // when it is the final slab of a chunk that ends with the volume) - hand them to the epilogue
+                        if (d_in - 1 >= g.d0) tc_commit_if(elected, smem_u32(dready + (d_in - 1 - g.d0)));
+                        if (d_in == g.dhi && g.dhi == g.d_hi - 1) tc_commit_if(elected, smem_u32(dready + (g.d_hi - 1 - g.d0)));
+                    }
                 }
                 if (!p.wres) {
                     tc_commit_if(elected, smem_u32(wempty + wb));
                     if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
                 }
             }
-            tc_commit_if(elected, smem_u32(accfull + set));
+            if (p.early) {          // unused depth slots of a short chunk: keep every slot's barrier in step with the items
+                for (int j = g.d_hi - g.d0; j < p.Dc; ++j) tc_commit_if(elected, smem_u32(dready + j));
+            } else {
+                tc_commit_if(elected, smem_u32(accfull + set));
+            }
         }
     } else {
         // ================= epilogue warps 2..5 =================
@@ -495,7 +508,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const int h = g.h0 + lh, w = g.w0 + lw;
             const bool valid = (h < p.H) && (w < p.W);
             const int nd = g.d_hi - g.d0;
-            bool waited = false;
+            bool waited = p.early != 0;
+            int ready_upto = 0;                      // early drain: depth slots [0, ready_upto) are known to be final
             for (int j0 = ((warp - 2) >> 2) * kJB; j0 < nd; j0 += (epi_warps(PL) / 4) * kJB) {
                 for (int c16 = 0; c16 < p.c_out; c16 += 16) {
                     const bool two = (c16 + 8 < p.c_out);
@@ -520,6 +534,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     for (int jj = 0; jj < kJB; ++jj) {
                         if (j0 + jj >= nd) break;
                         const int d = g.d0 + j0 + jj;
+                        if (p.early && j0 + jj >= ready_upto) {
+                            mbar_wait(smem_u32(dready + j0 + jj), aphase, 303);
+                            tc_fence_after();
+                            ready_upto = j0 + jj + 1;
+                        }
                         // depth d of region r: column set*ngroups*Dc*NP + r*Dc*NP + (d_hi-1-d)*NP
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
@@ -1145,6 +1164,13 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // depth per item (more halo slabs); when that leaves fewer than 4 depths a measured cycle model decides: a slab
     // costs M = groups * taps * terms * max(64, N/2) cycles of tensor pipe, the epilogue E ~ 650 cycles per 16 output
     // channels and depth.
+    // "Early drain" (opts->early_drain == 1, k = 3): one set with twice the depth, the depths handed to the epilogue one
+    // by one while the LAST channel group is still being accumulated (depth d is final once slab d+1 of that group is
+    // issued).  Measured: it saves 17 % of stem1's MMAs and gains nothing (521 vs 523 us; 8-ch, batched and 32-ch
+    // level-2 convs lose 3-12 %) - like the rolling kernel, an epilogue that reads the accumulator set the MMAs are
+    // writing slows the MMAs by about what the saved halo is worth; with two sets MMAs and tcgen05.ld work on
+    // different halves of TMEM and the kernel runs at exactly #MMAs x 64 cycles.
+    const bool want_early = (p.ks == 3) && opts && opts->early_drain == 1;
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
     if (p.nsets == 1 && 512 / (2 * accw) >= 2) {
         const int halo = (p.ks == 3) ? 2 : 0;
@@ -1157,6 +1183,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         const double t2 = (me > ee ? me : ee) / d2;
         if (t2 < t1) p.nsets = 2;
     }
+    if (want_early) p.nsets = 1;
     if (opts && (opts->acc_sets == 1 || opts->acc_sets == 2)) p.nsets = opts->acc_sets;
     // tile shape: 8 x 16 for k = 3 (the tap windows need the 8-row core-matrix groups to be rows of the slab); a
     // 1x1x1 conv has no halo, its slab is 128 consecutive rows whatever the shape, so it takes the widest tile the
@@ -1192,8 +1219,9 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.roll = (p.ks == 3 && p.R >= 4 && opts && opts->rolling == 1) ? 1 : 0;
     p.dbg = opts ? opts->debug : 0;
     p.cv_skip = (fused && opts->cv_skip == 1 && !p.roll) ? 1 : 0;
+    p.early = (want_early && p.nsets == 1 && !p.roll) ? 1 : 0;
     int dc_max = p.roll ? p.D : 512 / (p.nsets * accw);
-    if (!p.roll && dc_max > 16) dc_max = 16;
+    if (!p.roll && dc_max > (p.early ? kMaxRing : 16)) dc_max = p.early ? kMaxRing : 16;
     if (dc_max > p.D) dc_max = p.D;
     const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
     // Depth slices per work item: an item of Dc slices streams Dc + 2*halo slabs at a fixed MMA cost per slab, and the

@@ -87,6 +87,7 @@ class MatchingPlan:
         self.resident_weights = int(tc_knobs.get("resident_weights", 0))
         self.depth_chunk = int(tc_knobs.get("depth_chunk", 0))
         self.rolling = int(tc_knobs.get("rolling", 0))
+        self.early_drain = int(tc_knobs.get("early_drain", 0))
         self.steps: List[Step] = []
         self.volumes: List[PlanesVol] = []
         self._bn_users: List[Tuple[ConvBR3d, int]] = []     # (module, offset into the BN buffers)
@@ -206,6 +207,7 @@ class MatchingPlan:
             opts.resident_weights = self.resident_weights
             opts.depth_chunk = self.depth_chunk
             opts.rolling = self.rolling
+            opts.early_drain = self.early_drain
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
                                weight=weight, wcat=wcat, opts=opts, ref=src.vol.t))
 
@@ -235,6 +237,7 @@ class MatchingPlan:
             opts.resident_weights = self.resident_weights
             opts.depth_chunk = self.depth_chunk
             opts.rolling = self.rolling
+            opts.early_drain = self.early_drain
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, 2.0 * m_vox * taps * c_in,
                                2.0 * self.P * m_vox * (c_in + dst.c), p=p, mods=(mod,), weight=wcat, wcat=wcat, opts=opts,
                                ref=src.vol.t, wfn=fill))
@@ -724,7 +727,7 @@ DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fus
 
 # tensor-core kernel / plan-rewrite knobs an ``engine_options`` dict may carry (defaults = what the product runs)
 _TC_KNOBS = {"accum_split": 0, "acc_sets": 0, "fuse_cv": True, "fuse_head": True, "collapse_stem0": True, "tile_w_log2": 0,
-             "resident_weights": 0, "depth_chunk": 0, "rolling": 0}
+             "resident_weights": 0, "depth_chunk": 0, "rolling": 0, "early_drain": 0}
 
 
 def _options(model) -> dict:

@@ -326,6 +326,11 @@ TC_ROLL_CASES = [
     (1, 64, 0, 64, 32, 3, (13, 16, 8), True, True, False, 13),      # weights streamed per slab and channel group
     (1, 32, 0, 32, 1, 3, (21, 16, 8), False, False, False, 21),     # fp32 output
     (1, 16, 0, 16, 48, 3, (6, 16, 8), True, True, False, 6),        # 96 columns per depth: chunked kernel, two sets
+    # early-drain schedule (one accumulator set, per-depth hand-over): negative chunk length
+    (1, 32, 0, 32, 32, 3, (19, 20, 12), True, True, True, -7),      # short last chunk: unused depth slots
+    (2, 16, 0, 16, 16, 3, (40, 16, 8), True, True, True, -16),
+    (1, 128, 0, 128, 64, 3, (9, 16, 16), True, True, False, -4),    # streamed weights, 8 channel groups
+    (1, 8, 0, 8, 8, 3, (33, 16, 8), True, True, True, -32),
 ]
 
 
@@ -341,8 +346,9 @@ def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False)
             img = ops.pack_weights_tc(w.contiguous(), planes)
             opts = lea_tc_opts()
             opts.mma_terms = mma_terms
-            opts.depth_chunk = chunk
-            opts.rolling = 1 if chunk else 0          # the TC_ROLL_CASES exercise the rolling-schedule kernel
+            opts.depth_chunk = abs(chunk)
+            opts.rolling = 1 if chunk > 0 else 0      # the TC_ROLL_CASES exercise the rolling-schedule kernel
+            opts.early_drain = 1 if chunk < 0 else 0  # negative chunk: the early-drain single-set schedule
             ops.conv3d_tc(p, img, opts, x)
 
         got, ref = _conv_case(ops, device, B, ct, c0, ci, co, k, sp, bn, relu, res, planes, 300 + 10 * i, fn)

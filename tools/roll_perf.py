@@ -10,7 +10,7 @@ ops = get_ops()
 dev = torch.device("cuda:0")
 B = int(os.environ.get("B", "4"))
 cases = [("stem1", 32, 32, (64, 128, 416), False), ("L1op", 16, 16, (32, 64, 208), True), ("L0op", 8, 8, (64, 128, 416), True),
-         ("L2op", 32, 32, (16, 32, 104), True)]
+         ("L2op", 32, 32, (16, 32, 104), True), ("L1x3", 16, 48, (32, 64, 208), False), ("conv1", 128, 64, (32, 64, 208), False)]
 for name, ci, co, sp, res in cases:
     src = PlanesVol.empty(B, ci, 2, *sp, dev)
     src.t.copy_(torch.randn(src.t.shape, device=dev).bfloat16() * 0.1)
@@ -20,7 +20,7 @@ for name, ci, co, sp, res in cases:
     sc = torch.ones(co, device=dev); sh = torch.zeros(co, device=dev)
     p = ops.make_conv(src, 0, ci, co, 3, sc, sh, True, dst=dst, res=dst if res else None)
     img = ops.pack_weights_tc(w, 2)
-    for knobs in [{}, {"rolling": 1}, {"rolling": 1, "debug": 3}]:
+    for knobs in [{"early_drain": 2}, {}]:
         opts = lea_tc_opts()
         for kk, v in knobs.items():
             setattr(opts, kk, v)
