@@ -1166,10 +1166,10 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // channels and depth.
     // "Early drain" (opts->early_drain == 1, k = 3): one set with twice the depth, the depths handed to the epilogue one
     // by one while the LAST channel group is still being accumulated (depth d is final once slab d+1 of that group is
-    // issued).  Measured: it saves 17 % of stem1's MMAs and gains nothing (521 vs 523 us; 8-ch, batched and 32-ch
-    // level-2 convs lose 3-12 %) - like the rolling kernel, an epilogue that reads the accumulator set the MMAs are
-    // writing slows the MMAs by about what the saved halo is worth; with two sets MMAs and tcgen05.ld work on
-    // different halves of TMEM and the kernel runs at exactly #MMAs x 64 cycles.
+    // issued).  Measured: it saves 17 % of stem1's MMAs and gains nothing (521 vs 515-523 us; 8-ch, batched and 32-ch
+    // level-2 convs lose 3-12 %) - like the rolling kernel, an epilogue interleaved with the MMAs of its own item costs
+    // about what the saved halo is worth (cause not identified; concurrent tcgen05.ld alone is free, see
+    // lea_tc_microbench), while the default two-set schedule runs at exactly #MMAs x 64 cycles.
     const bool want_early = (p.ks == 3) && opts && opts->early_drain == 1;
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
     if (p.nsets == 1 && 512 / (2 * accw) >= 2) {

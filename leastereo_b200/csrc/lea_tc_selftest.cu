@@ -156,7 +156,7 @@ extern "C" int lea_tc_selftest(int32_t verbose, void* stream) {
 // memory (TS), accumulating into `nacc` different accumulators in rotation.  Operand contents are irrelevant.
 // ---------------------------------------------------------------------------------------------------------
 namespace {
-struct MbParams { int n, nacc, a_in_tmem, iters, a_rot, sbo_a, b_rot, a_lbo, b_lbo; };
+struct MbParams { int n, nacc, a_in_tmem, iters, a_rot, sbo_a, b_rot, a_lbo, b_lbo, ld_col; };
 
 __global__ void __launch_bounds__(128, 1) lea_tc_microbench_kernel(MbParams p, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -220,6 +220,24 @@ __global__ void __launch_bounds__(128, 1) lea_tc_microbench_kernel(MbParams p, l
             if (!ok && clock64() - t0 > 4000000000ll) break;
         }
         if (tid == 0) { out[2 * blockIdx.x] = clock64() - t0; out[2 * blockIdx.x + 1] = t_issue - t0; }
+        if (tid == 0) *reinterpret_cast<volatile uint32_t*>(&tmem_slot) = 0xffffffffu;     // stop the loader warps
+    } else if (p.ld_col >= 0) {
+        // loader warps: back-to-back tcgen05.ld of 32 columns at ld_col while warp 0 issues MMAs into [0, nacc*n)
+        uint32_t r[16], sink = 0;
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)p.ld_col;
+        while (*reinterpret_cast<volatile uint32_t*>(&tmem_slot) != 0xffffffffu) {
+#pragma unroll
+            for (int rep = 0; rep < 2; ++rep) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+                    "tcgen05.wait::ld.sync.aligned;"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + (uint32_t)(rep * 16)) : "memory");
+                sink ^= r[0] ^ r[15];
+            }
+        }
+        if (sink == 0x12345678u) out[0] = 1;      // keep the loads alive
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -247,7 +265,7 @@ extern "C" int lea_tc_microbench(int32_t grid, void* stream) {
         {128, 0, 8, 8, 5760, 2048}, {128, 0, 8, 8, 2880, 2112}, {256, 0, 8, 8, 2880, 4160},
     };
     for (const Case& c : cases) {
-        MbParams p{c.n, 1, c.a_in_tmem, iters, c.a_rot, 160, c.b_rot, c.a_lbo, c.b_lbo};
+        MbParams p{c.n, 1, c.a_in_tmem, iters, c.a_rot, 160, c.b_rot, c.a_lbo, c.b_lbo, -1};
         lea_tc_microbench_kernel<<<grid, 128, 64 * 1024, (cudaStream_t)stream>>>(p, d_out);
         cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
         if (e != cudaSuccess) { lea_set_error("microbench: %s", cudaGetErrorString(e)); return 1; }
@@ -257,6 +275,20 @@ extern "C" int lea_tc_microbench(int32_t grid, void* stream) {
         printf("[tc_microbench] %5d %5s a_rot %d b_rot %d a_lbo %5d b_lbo %5d | min %7.1f avg %7.1f issue %7.1f\n", c.n,
                c.a_in_tmem ? "tmem" : "smem", c.a_rot, c.b_rot, c.a_lbo, c.b_lbo, (double)mn / iters, avg / grid / iters,
                iss / grid / iters);
+    }
+    // MMAs accumulating into columns [0, 96) while three other warps read 32 TMEM columns at ld_col in a tight loop:
+    // does a tcgen05.ld next to / in the same half as / in the other half of the accumulator slow the MMAs down?
+    printf("[tc_microbench] N=96 MMAs into columns 0..95 with concurrent tcgen05.ld (3 warps x 32 columns) at column:\n");
+    const int ld_cols[] = {-1, 0, 96, 128, 224, 256, 384, 480};
+    for (int lc : ld_cols) {
+        MbParams p{96, 1, 0, iters, 8, 160, 8, 2880, 1536, lc};
+        lea_tc_microbench_kernel<<<grid, 128, 64 * 1024, (cudaStream_t)stream>>>(p, d_out);
+        cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+        if (e != cudaSuccess) { lea_set_error("microbench: %s", cudaGetErrorString(e)); return 1; }
+        cudaMemcpy(h.data(), d_out, 2 * grid * sizeof(long long), cudaMemcpyDeviceToHost);
+        double avg = 0;
+        for (int k = 0; k < grid; ++k) avg += (double)h[2 * k];
+        printf("[tc_microbench]   ld_col %4d : %7.1f cycles per MMA\n", lc, avg / grid / iters);
     }
     fflush(stdout);
     cudaFree(d_out);
