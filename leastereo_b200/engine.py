@@ -59,6 +59,7 @@ class Step:
     wfn: object = None             # callable(step): fills step.wcat with weights DERIVED from the modules' parameters
     planes: int = 0                # plane count of the packed weight image (0 = the plan's)
     ref_flops: float = -1.0        # 2*M*N*K of the reference conv(s) this launch stands for (-1: same as flops)
+    vols: tuple = ()               # every PlanesVol the launch reads or writes (buffer-liveness analysis)
     # resample
     rs: tuple = ()
 
@@ -96,18 +97,109 @@ class MatchingPlan:
         self._resampled: Dict[tuple, Slice] = {}
         self.flat2d = False
         self._param_key = None
-        total_bn = sum(mod.conv.out_channels for mod in matching.modules() if isinstance(mod, _CONVBR))
+        # a module can have several launches (collapsed stem0: band launch + assemble), each with its own BN slice
+        total_bn = 2 * sum(mod.conv.out_channels for mod in matching.modules() if isinstance(mod, _CONVBR)) + 256
         self.bn_scale = torch.ones(total_bn, dtype=torch.float32, device=self.device)
         self.bn_shift = torch.zeros(total_bn, dtype=torch.float32, device=self.device)
+        self.reuse_buffers = bool(tc_knobs.get("reuse_buffers", True))
+        self._arena: Optional[torch.Tensor] = None        # one allocation the activation volumes are views of
+        self._arena_offsets: Optional[List[int]] = None   # byte offset of the i-th _vol() call inside the arena
+        self._vol_calls = 0
         self._build()
+        if self.reuse_buffers and self.volumes:
+            self._rebuild_with_reuse()
 
     # ---- allocation helpers ---------------------------------------------------------------------------
     def _vol(self, c: int, spatial) -> PlanesVol:
-        v = PlanesVol.empty(self.B, c, self.P, *spatial, self.device)
+        i = self._vol_calls
+        self._vol_calls += 1
+        if self._arena is not None:
+            shape = (self.B, c // 8, self.P) + tuple(int(x) for x in spatial) + (8,)
+            n = 2
+            for x in shape:
+                n *= x
+            off = self._arena_offsets[i]
+            v = PlanesVol(self._arena[off: off + n].view(torch.bfloat16).view(shape))
+        else:
+            # with buffer reuse the first build is a dry run: only sizes and the launch order matter, no memory is taken
+            v = PlanesVol.empty(self.B, c, self.P, *spatial, "meta" if self.reuse_buffers else self.device)
+        v._arena_index = i
         self.volumes.append(v)
         return v
 
+    # ---- buffer reuse -----------------------------------------------------------------------------------
+    def _rebuild_with_reuse(self):
+        """The activation volumes of a forward pass are live only between their first writer and their last reader.
+        Build 1 (plain allocations) records which launch touches which volume; the volumes are then packed into one
+        arena by interval (first-fit over the launch order) and the plan is built a second time on views of it:
+        same launch list, a fraction of the memory (KITTI: ~10 GB per pair -> see DESIGN.md)."""
+        n = self._vol_calls
+        first, last = [None] * n, [None] * n
+        size = [0] * n
+        for v in self.volumes:
+            i = getattr(v, "_arena_index", None)
+            if i is not None:
+                size[i] = (v.nbytes() + 255) & ~255
+        for k, st in enumerate(self.steps):
+            for v in st.vols:
+                i = getattr(v, "_arena_index", None)
+                if i is None:
+                    continue
+                first[i] = k if first[i] is None else first[i]
+                last[i] = k
+        order = sorted(range(n), key=lambda i: (first[i] if first[i] is not None else 0))
+        free: List[Tuple[int, int]] = []          # (offset, size) holes, sorted by offset
+        live: List[Tuple[int, int, int]] = []     # (last step, offset, size)
+        offsets = [0] * n
+        top = peak = 0
+        for i in order:
+            f = first[i] if first[i] is not None else 0
+            l = last[i] if last[i] is not None else len(self.steps)
+            for item in [x for x in live if x[0] < f]:            # volumes dead before this one is first touched
+                live.remove(item)
+                free.append((item[1], item[2]))
+            free.sort()
+            merged: List[Tuple[int, int]] = []
+            for off, sz in free:
+                if merged and merged[-1][0] + merged[-1][1] == off:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + sz)
+                else:
+                    merged.append((off, sz))
+            if merged and merged[-1][0] + merged[-1][1] == top:  # a hole at the end of the arena shrinks it
+                top = merged[-1][0]
+                merged.pop()
+            free = merged
+            slot = next((k for k, (off, sz) in enumerate(free) if sz >= size[i]), None)
+            if slot is None:
+                offsets[i] = top
+                top += size[i]
+            else:
+                off, sz = free.pop(slot)
+                offsets[i] = off
+                if sz > size[i]:
+                    free.append((off + size[i], sz - size[i]))
+            live.append((l, offsets[i], size[i]))
+            peak = max(peak, top)
+        plain_bytes = sum(size)
+        # tear down build 1, then build 2 on the arena
+        self.steps, self.volumes = [], []
+        self._bn_users, self._bn_channels = [], 0
+        self._resampled = {}
+        self._param_key = None
+        self.cost = self.fxp = self.fyp = self.fxy = self.cv_maps = self.fxy3 = None
+        if hasattr(self, "mat"):
+            del self.mat
+        self._vol_calls = 0
+        self._arena_offsets = offsets
+        self._arena = torch.empty(max(peak, 256), dtype=torch.uint8, device=self.device)
+        self.plain_bytes, self.arena_bytes = plain_bytes, peak
+        self._build()
+        if self._vol_calls != n:
+            raise LeaError("buffer reuse: the second build allocated %d volumes, the first %d" % (self._vol_calls, n))
+
     def workspace_bytes(self) -> int:
+        if self._arena is not None:
+            return int(self._arena.numel()) + sum(v.nbytes() for v in self.volumes if getattr(v, "_arena_index", None) is None)
         return sum(v.nbytes() for v in self.volumes)
 
     def _bn_slices(self, mods) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -137,7 +229,7 @@ class MatchingPlan:
             scale, shift = self._bn_slices([bn_of])
         nbytes = 2.0 * self.P * src.c * self.B * (_prod(src.spatial) + _prod(spatial))
         self.steps.append(Step("resample", name, 0.0, nbytes,
-                               rs=(src.vol, src.c0, src.c, dst.vol, dst.c0, scale, shift, relu)))
+                               rs=(src.vol, src.c0, src.c, dst.vol, dst.c0, scale, shift, relu), vols=(src.vol, dst.vol)))
         return dst
 
     def _emit_conv(self, name: str, mods, src: Slice, dst: Optional[Slice], *, res: bool = False,
@@ -209,7 +301,8 @@ class MatchingPlan:
             opts.rolling = self.rolling
             opts.early_drain = self.early_drain
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
-                               weight=weight, wcat=wcat, opts=opts, ref=src.vol.t))
+                               weight=weight, wcat=wcat, opts=opts, ref=src.vol.t,
+                               vols=(src.vol,) + ((dst.vol,) if dst is not None else ())))
 
     def _emit_tap_projection(self, name: str, mod: ConvBR3d, src: Slice, dst: Slice):
         """1x1x1 conv C -> k^3 "tap" channels with weights W[t, c] = mod.weight[0, c, kd, kh, kw], t = kd*9+kh*3+kw:
@@ -240,7 +333,7 @@ class MatchingPlan:
             opts.early_drain = self.early_drain
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, 2.0 * m_vox * taps * c_in,
                                2.0 * self.P * m_vox * (c_in + dst.c), p=p, mods=(mod,), weight=wcat, wcat=wcat, opts=opts,
-                               ref=src.vol.t, wfn=fill))
+                               ref=src.vol.t, wfn=fill, vols=(src.vol, dst.vol)))
 
     # ---- collapsed stem0 ------------------------------------------------------------------------------------
     def _can_collapse_stem0(self, fm: int, L0) -> bool:
@@ -278,7 +371,7 @@ class MatchingPlan:
             opts.accum_split = self.accum_split
             self.steps.append(Step("conv_tc", name, 2.0 * B * H * W * co * fm * 9,
                                    2.0 * P3 * B * H * W * (fm + co), p=p, mods=(st,), weight=wcat, wcat=wcat, opts=opts,
-                                   ref=src_vol.t, wfn=fill, planes=P3))
+                                   ref=src_vol.t, wfn=fill, planes=P3, vols=(src_vol, dst_vol)))
 
         emit_map("stem0.collapsed.L(2-D)", fx3, lmap, c_out, fill_l)
         emit_map("stem0.collapsed.A|B(2-D)", fy3, abmap, 2 * c_out, fill_ab)
@@ -299,7 +392,7 @@ class MatchingPlan:
         scale, shift = self._bn_slices([st]) if st.use_bn else (None, None)
         nbytes = 2.0 * self.P * B * D * H * W * c_out * (1.0 - frac) + 2.0 * P3 * B * H * W * 3 * c_out
         self.steps.append(Step("stem0_assemble", "stem0.collapsed.assemble", 0.0, nbytes,
-                               rs=(lmap, abmap, v0, 0, c_out, scale, shift, st.relu)))
+                               rs=(lmap, abmap, v0, 0, c_out, scale, shift, st.relu), vols=(lmap, abmap, v0)))
 
     def _identity_weight(self, c: int) -> torch.Tensor:
         if c not in self._eye:
@@ -506,7 +599,8 @@ class MatchingPlan:
             self.steps[-1].ref_flops = 2.0 * self.B * _prod(L0) * l3.conv.in_channels * 27      # last_3 on the up-sampled volume
             ws = self.ops.head_taps_workspace(q.vol, L0)
             nbytes = 2.0 * self.P * self.B * _prod(pre.spatial) * 32 + 4.0 * self.B * _prod(L0)
-            self.steps.append(Step("head_taps", "head.upsample_6+last_3", 0.0, nbytes, rs=(q.vol, 0, self.mat, ws)))
+            self.steps.append(Step("head_taps", "head.upsample_6+last_3", 0.0, nbytes, rs=(q.vol, 0, self.mat, ws),
+                                   vols=(q.vol,)))
             return
         if pre is not None:
             feat = self._resample("head.upsample_6", pre, L0)
@@ -638,7 +732,8 @@ class FeaturePlan(MatchingPlan):
         sc1, sh1 = self._bn_slices([f.stem1])
         flops = 2.0 * self.B * (H * W * f.stem0.conv.out_channels * 27 + _prod(L0) * fm * f.stem0.conv.out_channels * 9)
         self.steps.append(Step("feature_stem", "feature.stem0+stem1", flops, 4.0 * self.B * 3 * H * W,
-                               mods=(f.stem0, f.stem1), rs=(self.img, None, sc0, sh0, None, sc1, sh1, stem1.vol)))
+                               mods=(f.stem0, f.stem1), rs=(self.img, None, sc0, sh0, None, sc1, sh1, stem1.vol),
+                               vols=(stem1.vol,)))
         stem2 = Slice(self._vol(fm, L0), 0, fm)
         self._emit_conv("feature.stem2", f.stem2, stem1, stem2)
         out = (stem1, stem2)
@@ -674,10 +769,12 @@ class FeaturePlan(MatchingPlan):
                 tmp = Slice(self._vol(fm, L0), 0, fm)
             self._emit_conv("feature.last_3", f.last_3, feat, tmp)
             self.steps.append(Step("repack", "feature.to_operand_planes", 0.0,
-                                   2.0 * self.B * _prod(L0) * fm * (self.P + self.out.P), rs=(tmp.vol, self.out, fm)))
+                                   2.0 * self.B * _prod(L0) * fm * (self.P + self.out.P), rs=(tmp.vol, self.out, fm),
+                                   vols=(tmp.vol, self.out)))
         if self.out3 is not None and not used3:
             self.steps.append(Step("repack", "feature.to_map_planes", 0.0,
-                                   2.0 * self.B * _prod(L0) * fm * (self.out.P + self.out3.P), rs=(self.out, self.out3, fm)))
+                                   2.0 * self.B * _prod(L0) * fm * (self.out.P + self.out3.P), rs=(self.out, self.out3, fm),
+                                   vols=(self.out, self.out3)))
 
     def refresh_params(self, force: bool = False):
         key = self._current_param_key()
@@ -727,7 +824,7 @@ DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fus
 
 # tensor-core kernel / plan-rewrite knobs an ``engine_options`` dict may carry (defaults = what the product runs)
 _TC_KNOBS = {"accum_split": 0, "acc_sets": 0, "fuse_cv": True, "fuse_head": True, "collapse_stem0": True, "tile_w_log2": 0,
-             "resident_weights": 0, "depth_chunk": 0, "rolling": 0, "early_drain": 0}
+             "resident_weights": 0, "depth_chunk": 0, "rolling": 0, "early_drain": 0, "reuse_buffers": True}
 
 
 def _options(model) -> dict:

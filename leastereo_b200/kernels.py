@@ -88,11 +88,12 @@ class LeaError(RuntimeError):
 class PlanesVol:
     """Python handle of a planes volume: bf16 tensor of shape (B, C/8, P, D, H, W, 8)."""
 
-    __slots__ = ("t", "B", "C", "P", "D", "H", "W")
+    __slots__ = ("t", "B", "C", "P", "D", "H", "W", "_arena_index")
 
     def __init__(self, t: torch.Tensor):
         assert t.dtype == torch.bfloat16 and t.dim() == 7 and t.shape[-1] == 8 and t.is_contiguous()
         self.t = t
+        self._arena_index = None        # set by engine.MatchingPlan for volumes that live in its reuse arena
         self.B, cb, self.P, self.D, self.H, self.W, _ = t.shape
         self.C = cb * 8
 
@@ -106,7 +107,8 @@ class PlanesVol:
         return (self.D, self.H, self.W)
 
     def struct(self) -> lea_vol:
-        return lea_vol(self.t.data_ptr(), self.B, self.C, self.P, self.D, self.H, self.W)
+        ptr = 0 if self.t.is_meta else self.t.data_ptr()        # meta: the engine's dry-run build (sizes only)
+        return lea_vol(ptr, self.B, self.C, self.P, self.D, self.H, self.W)
 
     def nbytes(self) -> int:
         return self.t.numel() * 2

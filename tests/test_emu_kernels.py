@@ -112,3 +112,18 @@ def test_flat_adam(emu_ops):
 
 def test_disparity_metrics(emu_ops):
     K.check_disparity_metrics(emu_ops, DEV)
+
+
+def test_buffer_reuse_is_exact_and_smaller(emu_ops):
+    """The liveness-packed arena must not change a single bit of the result and must shrink the activation memory."""
+    from conftest import load_golden
+    g = load_golden("cal_b2_24x48_d24")
+    outs, sizes = {}, {}
+    for reuse in (False, True):
+        mat, disp, model, plan = K.run_hot_path(emu_ops, DEV, g, planes=2, extra={"reuse_buffers": reuse})
+        outs[reuse] = (mat, disp)
+        sizes[reuse] = plan.workspace_bytes()
+        assert (plan._arena is not None) == reuse
+    assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
+    print("activation bytes: plain %d, reused %d" % (sizes[False], sizes[True]))
+    assert sizes[True] < 0.6 * sizes[False]

@@ -10,6 +10,7 @@ from leastereo_b200 import LEAStereo, default_args  # noqa: E402
 
 def run(name, H, W, maxdisp, B, steps=5, warmup=2):
     dev = torch.device("cuda:0")
+    torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         model = LEAStereo(default_args(maxdisp=maxdisp, cuda=True), dev).to(dev).eval()
@@ -42,6 +43,7 @@ if __name__ == "__main__":
            run("KITTI batch 1 (configs[2])", 384, 1248, 192, 1),
            run("KITTI batch 4 (configs[2])", 384, 1248, 192, 4),
            run("KITTI batch 16 (configs[2])", 384, 1248, 192, 16),
-           run("Middlebury half-res (configs[3])", 1008, 1512, 408, 1)]
+           run("Middlebury half-res (configs[3])", 1008, 1512, 408, 1),
+           run("Middlebury half-res, batch 2", 1008, 1512, 408, 2)]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "config_sweep.json"), "w"), indent=1)
