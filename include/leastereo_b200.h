@@ -74,6 +74,16 @@ int lea_unpack_planes(const lea_vol* src, int32_t src_c0, int32_t c, float* dst,
 int lea_trilinear_ac(const lea_vol* src, int32_t src_c0, const lea_vol* dst, int32_t dst_c0, int32_t c,
                      const float* bn_scale, const float* bn_shift, int32_t relu, void* stream);
 
+/* Down-sampling resample fused with the 1x1x1 ConvBR(s) that consume it (skip_model_3d.py:44-53: resample s0 / s1 to the
+ * cell's size, then pre_preprocess / preprocess).  Up to two consumers (s1 of cell i is s0 of cell i+1) are computed in
+ * ONE pass over the source; weight = PyTorch layout fp32 (c_out, c_in[,1,1,1]); all consumers share the target size. */
+typedef struct lea_rc_out {
+    lea_vol      dst;       int32_t dst_c0, c_out;
+    const float* weight;    const float* bn_scale;   const float* bn_shift;   int32_t relu;
+} lea_rc_out;
+int lea_resample_conv1x1(const lea_vol* src, int32_t src_c0, int32_t c_in, const lea_rc_out* outs, int32_t n_out,
+                         void* stream);
+
 /* ---- ConvBR -------------------------------------------------------------------------------------------------- */
 /* fp32-FMA kernel; weight = PyTorch layout fp32 (c_out, c_in, k, k, k). */
 int lea_conv3d_simt(const lea_conv* p, const float* weight, void* stream);

@@ -87,6 +87,40 @@ extern "C" int lea_trilinear_ac(const lea_vol* src, int32_t src_c0, const lea_vo
     return LEA_POST_LAUNCH();
 }
 
+template <int NT>
+static int lea_launch_resample_conv1(const lea_vol* src, int32_t src_c0, int32_t c_in, const lea_rc_out* o, int32_t n_out,
+                                     void* stream) {
+    const size_t smem = (size_t)c_in * NT * sizeof(float);
+#ifndef LEA_CPU_EMU
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(lea_resample_conv1_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    const lea_vol& dst = o[0].dst;
+    LEA_LAUNCH(lea_resample_conv1_kernel<NT>, dim3((dst.W + 127) / 128, dst.D * dst.H, dst.B), dim3(128), smem, stream,
+               *src, src_c0, c_in, o[0], n_out > 1 ? o[1] : o[0], n_out);
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_resample_conv1x1(const lea_vol* src, int32_t src_c0, int32_t c_in, const lea_rc_out* outs, int32_t n_out,
+                                    void* stream) {
+    if (lea_check_vol(src, "resample_conv1x1 src") || lea_check_slice(src, src_c0, c_in, "resample_conv1x1 src")) return 1;
+    LEA_CHECK(outs != nullptr && (n_out == 1 || n_out == 2), "resample_conv1x1: 1 or 2 consumers");
+    int total = 0;
+    for (int k = 0; k < n_out; ++k) {
+        const lea_rc_out& o = outs[k];
+        if (lea_check_vol(&o.dst, "resample_conv1x1 dst") || lea_check_slice(&o.dst, o.dst_c0, o.c_out, "resample_conv1x1 dst"))
+            return 1;
+        LEA_CHECK(o.weight != nullptr && (o.bn_scale == nullptr) == (o.bn_shift == nullptr), "resample_conv1x1: bad consumer");
+        LEA_CHECK(o.dst.B == src->B && lea_same_space(&o.dst, &outs[0].dst), "resample_conv1x1: consumers must share the target geometry");
+        total += o.c_out;
+    }
+    LEA_CHECK(total <= 64 && c_in <= 256, "resample_conv1x1: at most 64 output channels in total and 256 input channels");
+    LEA_CHECK(outs[0].dst.B <= 65535, "resample_conv1x1: grid too large");
+    if (total <= 16) return lea_launch_resample_conv1<16>(src, src_c0, c_in, outs, n_out, stream);
+    if (total <= 32) return lea_launch_resample_conv1<32>(src, src_c0, c_in, outs, n_out, stream);
+    return lea_launch_resample_conv1<64>(src, src_c0, c_in, outs, n_out, stream);
+}
+
 static int lea_check_conv(const lea_conv* p, const char* what) {
     LEA_CHECK(p != nullptr, "%s: null params", what);
     if (lea_check_vol(&p->src, what) || lea_check_slice(&p->src, p->src_c0, p->c_in, what)) return 1;

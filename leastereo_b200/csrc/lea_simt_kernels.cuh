@@ -186,6 +186,95 @@ lea_trilinear_ac_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c,
                   (int64_t)h * dst.W + w, dPS, dst.P, out);
 }
 
+// K5c  down-sampling resample fused with the 1x1x1 ConvBR(s) that consume it (retrain/skip_model_3d.py:44-53: a cell
+//      resamples s0 / s1 to its own size, then applies pre_preprocess / preprocess = Conv3d 1x1x1 + BN + ReLU).  The
+//      resampled tensor is often needed by two cells (s1 of cell i = s0 of cell i+1) with different 1x1x1 convs; one pass
+//      over the big source volume interpolates each 8-channel group once and feeds it to every consumer's matrix:
+//      the resampled intermediate (and its conv launches) disappear.  One thread per output voxel; weights of all
+//      consumers transposed in shared memory [c_in][n_total]; fp32 FMA.
+template <int NT>              // NT = total output channels of all consumers, padded to 16 / 32 / 64
+__global__ void __launch_bounds__(128)
+lea_resample_conv1_kernel(lea_vol src, int src_c0, int c_in, lea_rc_out o0, lea_rc_out o1, int n_out) {
+    LEA_DYN_SMEM(float, w_s);                       // [c_in][NT]
+    const int tid = threadIdx.x;
+    const int n0 = o0.c_out, n1 = n_out > 1 ? o1.c_out : 0;
+    for (int e = tid; e < c_in * NT; e += 128) {
+        const int ci = e / NT, n = e - ci * NT;
+        float wv = 0.0f;
+        if (n < n0) wv = __ldg(o0.weight + (int64_t)n * c_in + ci);
+        else if (n < n0 + n1) wv = __ldg(o1.weight + (int64_t)(n - n0) * c_in + ci);
+        w_s[e] = wv;
+    }
+    __syncthreads();
+    const lea_vol& dst = o0.dst;                    // all consumers share the target geometry
+    const int w = blockIdx.x * 128 + tid;
+    if (w >= dst.W) return;
+    const int h = blockIdx.y % dst.H, d = blockIdx.y / dst.H, b = blockIdx.z;
+    const lea_axis_lerp ad = lea_axis_ac(d, src.D, dst.D);
+    const lea_axis_lerp ah = lea_axis_ac(h, src.H, dst.H);
+    const lea_axis_lerp aw = lea_axis_ac(w, src.W, dst.W);
+    const int64_t sHW = (int64_t)src.H * src.W, sPS = sHW * src.D;
+    const lea_u4* sb0 = (const lea_u4*)src.data + ((int64_t)b * (src.C >> 3) + (src_c0 >> 3)) * src.P * sPS;
+    float acc[NT];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[n] = 0.0f;
+    for (int cb = 0; cb < (c_in >> 3); ++cb) {
+        const lea_u4* sbase = sb0 + (int64_t)cb * src.P * sPS;
+        float val[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) val[j] = 0.0f;
+#pragma unroll
+        for (int zd = 0; zd < 2; ++zd) {
+            const float wd = zd ? ad.l1 : ad.l0;
+            const lea_u4* sd = sbase + (int64_t)(zd ? ad.i1 : ad.i0) * sHW;
+            float accd[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) accd[j] = 0.0f;
+#pragma unroll
+            for (int zh = 0; zh < 2; ++zh) {
+                const float wh = zh ? ah.l1 : ah.l0;
+                const lea_u4* sh = sd + (zh ? ah.i1 : ah.i0) * src.W;
+                float a[8], bb[8];
+                lea_load8_at(sh + aw.i0, sPS, src.P, a);
+                lea_load8_at(sh + aw.i1, sPS, src.P, bb);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) accd[j] += wh * (aw.l0 * a[j] + aw.l1 * bb[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) val[j] += wd * accd[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4* wr = reinterpret_cast<const float4*>(w_s + (cb * 8 + j) * NT);
+#pragma unroll
+            for (int n4 = 0; n4 < NT / 4; ++n4) {
+                const float4 wv = wr[n4];
+                acc[n4 * 4 + 0] += val[j] * wv.x; acc[n4 * 4 + 1] += val[j] * wv.y;
+                acc[n4 * 4 + 2] += val[j] * wv.z; acc[n4 * 4 + 3] += val[j] * wv.w;
+            }
+        }
+    }
+    const int64_t dHW = (int64_t)dst.H * dst.W, dPS = dHW * dst.D;
+#pragma unroll
+    for (int g8 = 0; g8 < NT / 8; ++g8) {
+        const int n = g8 * 8;
+        if (n >= n0 + n1) break;
+        const bool first = n < n0;                   // consumer channel counts are multiples of 8: a group never straddles
+        const lea_rc_out& o = first ? o0 : o1;
+        const int c = first ? n : n - n0;
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float v = acc[n + j];
+            if (o.bn_scale) v = v * __ldg(o.bn_scale + c + j) + __ldg(o.bn_shift + c + j);
+            if (o.relu) v = v > 0.0f ? v : 0.0f;
+            out[j] = v;
+        }
+        lea_store8_at((lea_u4*)o.dst.data + ((int64_t)b * (o.dst.C >> 3) + ((o.dst_c0 + c) >> 3)) * o.dst.P * dPS + d * dHW +
+                      (int64_t)h * dst.W + w, dPS, o.dst.P, out);
+    }
+}
+
 // Up-sampling variant: one thread owns an output column (h, w) of a chunk of LEA_UP_DCH depths and marches along d.
 // The (h, w)-interpolated values of the two low-res depth slices in use stay in registers; a new slice costs 4 corner
 // loads, and with out/in ~ 2 along d only every second output needs one -> ~5 loads per output instead of 16.

@@ -80,6 +80,7 @@ struct TcParams {
     int wres;                 // 1 = the weight parts of ALL channel groups stay resident in shared memory (loaded once per CTA)
     int fused_cv, ncg_half;   // fused cost volume: channel groups [0,ncg_half) come from x, the rest from y(w-d)
     const CUtensorMap* cvmaps; // [2*D]: x maps for d = 0..D-1, then y maps
+    int fold;                 // folded terms: NP = 2 x padded c_out "virtual" channels [main | correction] (see tc_shape)
     int nsets;                // TMEM accumulator sets: 2 = epilogue of item i overlaps MMAs of item i+1, 1 = larger Dc
     int swap_lbo_sbo;         // debug switch for the descriptor convention
     const uint8_t* wimg;
@@ -546,10 +547,12 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         {
                             uint32_t ra[16], rb[16];
                             tc_ld16_nowait(trow + (uint32_t)c16, ra);
-                            if (p.ngroups == 2) tc_ld16_nowait(trow + (uint32_t)(p.Dc * p.NP + c16), rb);
+                            const bool two_regions = (p.ngroups == 2) || p.fold;
+                            if (two_regions)
+                                tc_ld16_nowait(trow + (uint32_t)((p.fold ? (p.NP >> 1) : p.Dc * p.NP) + c16), rb);
                             tc_wait_ld();
                             tc_touch16(ra);
-                            if (p.ngroups == 2) {
+                            if (two_regions) {
                                 tc_touch16(rb);
 #pragma unroll
                                 for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]) + __uint_as_float(rb[i]);
@@ -854,7 +857,8 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
         const int64_t sp = (int64_t)p.D * p.H * p.W;
         const int nblk = R + 2;
         const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
-        const uint32_t region1 = (uint32_t)(nblk * p.NP);
+        const uint32_t region1 = (uint32_t)(p.fold ? (p.NP >> 1) : nblk * p.NP);
+        const bool two_regions = (p.ngroups == 2) || p.fold;
         int e = 0, par = 1;                            // entry / parity of the next depth (see the issuer)
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const ItemGeom g = decode_item(p, item);
@@ -895,11 +899,11 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
                             for (int i = 0; i < 16; ++i) { ra[i] = 0; rb[i] = 0; rc[i] = 0; rd[i] = 0; }
                         } else {
                         tc_ld16_nowait(home + (uint32_t)c16, ra);
-                        if (p.ngroups == 2) tc_ld16_nowait(home + region1 + (uint32_t)c16, rb);
+                        if (two_regions) tc_ld16_nowait(home + region1 + (uint32_t)c16, rb);
                         }
                         if (has_alias && !(p.dbg & 2)) {
                             tc_ld16_nowait(alias + (uint32_t)c16, rc);
-                            if (p.ngroups == 2) tc_ld16_nowait(alias + region1 + (uint32_t)c16, rd);
+                            if (two_regions) tc_ld16_nowait(alias + region1 + (uint32_t)c16, rd);
                         }
                         tc_wait_ld();
                         tc_touch16(ra);
@@ -910,7 +914,7 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
 #pragma unroll
                             for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(rc[i]);
                         }
-                        if (p.ngroups == 2) {
+                        if (two_regions) {
                             tc_touch16(rb);
                             if (has_alias) {
                                 tc_touch16(rd);
@@ -987,12 +991,19 @@ static TcKernelFn tc_kernel_for(int ks, int nterm, int planes) {
 //   standard (c_in % 16 == 0): tile j = weight plane j; row holds plane j of W[co][cg*16 + khalf*8 + 0..7][kd,kh,kw]
 //   c_in == 8, P == 2 ("C8"):  the A operand is [hi(8) | lo(8)] of the same 8 channels, so
 //       tile 0: khalf0 = Whi, khalf1 = Whi   (hi*Whi + lo*Whi)        tile 1: khalf0 = Wlo, khalf1 = 0   (hi*Wlo)
+//   FOLDED (k = 3, P == 2, c_out <= 16):  one tcgen05.mma costs max(64, N/2) cycles, so for N = 3*16 two thirds of
+//       the instruction are idle.  Product terms that share their A operand are therefore issued as ONE MMA against a
+//       weight tile with 2*16 "virtual" output channels per kd, row = kd*32 + region*16 + co: region 0 accumulates the
+//       main term, region 1 the 2^-8-scaled corrections (the two accumulator regions of accum_split, now adjacent
+//       columns of the same depth), and the epilogue adds column c and c+16:
+//         standard: tile 0 (A = a_hi) = [Whi | Wlo],  tile 1 (A = a_lo) = [0 | Whi]      3 MMAs -> 2 per tap
+//         C8:       tile 0 (A = [hi|lo]) = [[Whi;Whi] | [Wlo;0]]                          2 MMAs -> 1 per tap
 // ---------------------------------------------------------------------------------------------------------
 struct TcShape {
-    bool ok; bool c8;
+    bool ok; bool c8; bool fold;
     int NP, nb_rows, nbt, btile_bytes, taps2d, ncg, wpart_bytes, ngroups;
 };
-__host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) {
+__host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P, int allow_fold) {
     TcShape s{};
     s.ok = false;
     if (!(ks == 1 || ks == 3) || P < 1 || P > 3) return s;
@@ -1000,9 +1011,11 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) 
     s.c8 = (c_in == 8);
     if (s.c8 ? (P < 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
     s.NP = (c_out + 15) & ~15;                                 // UMMA N granularity at M = 128
+    s.fold = allow_fold && ks == 3 && P == 2 && s.NP == 16;
+    if (s.fold) s.NP = 32;                                     // [main 16 | correction 16] virtual channels
     s.taps2d = ks * ks;
     s.nb_rows = ks * s.NP;
-    if (s.c8) { s.nbt = P; s.ncg = 1; s.ngroups = 1; }
+    if (s.c8) { s.nbt = s.fold ? 1 : P; s.ncg = 1; s.ngroups = 1; }
     else      { s.nbt = P; s.ncg = c_in / 16; s.ngroups = P; }
     s.btile_bytes = 2 * s.nb_rows * 16;
     s.wpart_bytes = s.taps2d * s.nbt * s.btile_bytes;
@@ -1011,23 +1024,32 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P) 
 }
 
 __global__ void lea_pack_weights_tc_kernel(const float* __restrict__ w, lea_u4* __restrict__ img,
-                                           int c_in, int c_out, int ks, int P, int total_groups) {
+                                           int c_in, int c_out, int ks, int P, int total_groups, int allow_fold) {
     const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (gidx >= total_groups) return;
-    const TcShape s = tc_shape(c_in, c_out, ks, P);
+    const TcShape s = tc_shape(c_in, c_out, ks, P, allow_fold);
     int r = gidx;
     const int row = r % s.nb_rows; r /= s.nb_rows;
     const int khalf = r % 2; r /= 2;
     const int bt = r % s.nbt; r /= s.nbt;
     const int tap2d = r % s.taps2d; r /= s.taps2d;
     const int cg = r;
-    const int kd = row / s.NP, co = row % s.NP;
+    const int kd = row / s.NP;
+    int co = row % s.NP, region = 0;
+    if (s.fold) { region = co >> 4; co &= 15; }
     const int tap = kd * s.taps2d + tap2d;                      // PyTorch order (kd, kh, kw)
     const int ntaps = s.taps2d * ks;
     uint32_t q[4] = {0, 0, 0, 0};
     int plane, ci0;
     bool zero = false;
-    if (s.c8) {
+    if (s.fold) {
+        if (s.c8) { ci0 = 0; plane = region; zero = (region == 1 && khalf == 1); }
+        else {
+            ci0 = cg * 16 + khalf * 8;
+            if (bt == 0) plane = region;                       // A = a_hi:  [Whi | Wlo]
+            else { plane = 0; zero = (region == 0); }          // A = a_lo:  [ 0  | Whi]
+        }
+    } else if (s.c8) {
         // K16 = two plane blocks of the same 8 channels.  P=2: tile0 [w0;w0], tile1 [w1;0].
         //                                                  P=3: tile0 [w0;w0], tile1 [w1;w1], tile2 [w2;w0].
         ci0 = 0;
@@ -1077,10 +1099,17 @@ int device_sm_count() {
     return n;
 }
 
+// Folded weight images (see the layout comment above tc_shape) are the default; LEA_TC_FOLD=0 in the environment of the
+// process restores the term-by-term images for A/B measurements.  Read once: pack and launch must agree.
+int tc_fold_enabled() {
+    static const int v = [] { const char* e = getenv("LEA_TC_FOLD"); return (e && e[0] == '0') ? 0 : 1; }();
+    return v;
+}
+
 int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void* stream, int swap_lbo_sbo) {
     const bool fused = opts && opts->fused_cv;
     const int P = fused ? opts->fx.P : c->src.P;
-    const TcShape s = tc_shape(c->c_in, c->c_out, c->ksize, P);
+    const TcShape s = tc_shape(c->c_in, c->c_out, c->ksize, P, tc_fold_enabled());
     if (fused) {
         LEA_CHECK(opts->cv_maps != nullptr, "conv3d_tc: fused_cv needs cv_maps (lea_build_fused_cv_maps)");
         LEA_CHECK(c->ksize == 3 && c->c_in == 2 * opts->fx.C && (opts->fx.C % 16) == 0,
@@ -1122,7 +1151,19 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         p.term_aoff[p.nterm] = aoff; p.term_lbo_blocks[p.nterm] = lbo; p.term_btile[p.nterm] = btile;
         p.term_region[p.nterm] = region; p.term_first[p.nterm] = first; ++p.nterm;
     };
-    if (s.c8) {
+    p.fold = s.fold ? 1 : 0;
+    if (s.fold) {
+        // terms that share their A operand are one MMA over [main | correction] virtual channels (layout comment above)
+        p.ngroups = 1;
+        if (s.c8) {
+            p.blocks_per_cg = P;
+            add_term(0, 1, 0, 0, 1);                           // [a0|a1] x [[w0;w0] | [w1;0]]
+        } else {
+            p.blocks_per_cg = 2 * P;
+            add_term(0, P, 0, 0, 1);                           // a0 x [w0 | w1]
+            if (!single) add_term(1, P, 1, 0, 0);              // a1 x [ 0 | w0]
+        }
+    } else if (s.c8) {
         p.blocks_per_cg = P;                                   // 1 channel block x P planes
         p.ngroups = 1;
         add_term(0, 1, 0, 0, 1);                               // [a0|a1] x [w0;w0]
@@ -1292,19 +1333,19 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
 }  // namespace
 
 extern "C" int64_t lea_tc_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t ksize, int32_t planes) {
-    const TcShape s = tc_shape(c_in, c_out, ksize, planes);
+    const TcShape s = tc_shape(c_in, c_out, ksize, planes, tc_fold_enabled());
     if (!s.ok) return 0;
     return (int64_t)s.ncg * s.wpart_bytes;
 }
 
 extern "C" int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
                                    int32_t planes, void* stream) {
-    const TcShape s = tc_shape(c_in, c_out, ksize, planes);
+    const TcShape s = tc_shape(c_in, c_out, ksize, planes, tc_fold_enabled());
     LEA_CHECK(s.ok, "pack_weights_tc: unsupported shape c_in=%d c_out=%d k=%d planes=%d", c_in, c_out, ksize, planes);
     LEA_CHECK(weight && wimg && ((((uintptr_t)wimg) & 15) == 0), "pack_weights_tc: bad pointer");
     const int total = (int)((int64_t)s.ncg * s.wpart_bytes / 16);
     lea_pack_weights_tc_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        weight, reinterpret_cast<lea_u4*>(wimg), c_in, c_out, ksize, planes, total);
+        weight, reinterpret_cast<lea_u4*>(wimg), c_in, c_out, ksize, planes, total, tc_fold_enabled());
     cudaError_t e = cudaGetLastError();
     LEA_CHECK(e == cudaSuccess, "pack_weights_tc: launch failed: %s", cudaGetErrorString(e));
     return 0;

@@ -82,6 +82,7 @@ class MatchingPlan:
         self.fuse_cv = bool(tc_knobs.get("fuse_cv", True))
         self.fuse_head = bool(tc_knobs.get("fuse_head", True))
         self.collapse_stem0 = bool(tc_knobs.get("collapse_stem0", True))
+        self.fuse_resample_conv = bool(tc_knobs.get("fuse_resample_conv", False))
         self.accum_split = int(tc_knobs.get("accum_split", 0))
         self.acc_sets = int(tc_knobs.get("acc_sets", 0))
         self.tile_w_log2 = int(tc_knobs.get("tile_w_log2", 0))
@@ -414,9 +415,26 @@ class MatchingPlan:
             self._emit_conv(name + "(raw,low-res)", mod, src, small, raw=True)
             self.steps[-1].ref_flops = self.steps[-1].flops * _prod(spatial) / _prod(src.spatial)   # reference: after the up-sample
             self._resample(name + ".upsample+bn+relu", small, spatial, dst=dst, bn_of=mod, relu=mod.relu)
+        elif self.fuse and self.fuse_resample_conv and self._can_fuse_resample_conv(mod, src, dst):
+            self._emit_resample_conv(name + "(fused into the down-sampling resample)", mod, src, dst)
         else:
             r = self._resample(name + ".resample", src, spatial)
             self._emit_conv(name, mod, r, dst)
+
+    def _can_fuse_resample_conv(self, mod: ConvBR3d, src: Slice, dst: Slice) -> bool:
+        w = mod.conv.weight
+        return (all(int(k) == 1 for k in w.shape[2:]) and w.shape[0] == dst.c and w.shape[1] == src.c
+                and dst.c % 8 == 0 and dst.c <= 64 and src.c % 8 == 0 and src.c <= 256)
+
+    def _emit_resample_conv(self, name: str, mod: ConvBR3d, src: Slice, dst: Slice):
+        """Down-sampling resample + the 1x1x1 ConvBR that consumes it in one pass over the source
+        (skip_model_3d.py:44-53; ``lea_resample_conv1x1``): the resampled intermediate is never written."""
+        scale, shift = self._bn_slices([mod]) if mod.use_bn else (None, None)
+        m_vox = self.B * _prod(dst.spatial)
+        nbytes = 2.0 * self.P * self.B * (_prod(src.spatial) * src.c + _prod(dst.spatial) * dst.c)
+        self.steps.append(Step("resample_conv1x1", name, 2.0 * m_vox * dst.c * src.c, nbytes, mods=(mod,),
+                               weight=mod.conv.weight.detach(), rs=(src, dst, scale, shift, mod.relu),
+                               vols=(src.vol, dst.vol)))
 
     def _cell(self, i: int, s0: Slice, s1: Slice, out: Optional[Slice] = None, cell=None, bm=None,
               prefix: str = "") -> Tuple[Slice, Slice]:
@@ -638,6 +656,11 @@ class MatchingPlan:
                 self.bn_scale[: scale.numel()].copy_(scale)
                 self.bn_shift[: scale.numel()].copy_(b - mu * scale)
             for s in self.steps:
+                if s.kind == "resample_conv1x1":
+                    w = s.mods[0].conv.weight
+                    if not (w.is_contiguous() and w.dtype == torch.float32 and w.device == self.device):
+                        raise LeaError("%s: weights must be contiguous fp32 on %s" % (s.name, self.device))
+                    s.weight = w.detach()
                 if not s.kind.startswith("conv"):
                     continue
                 if s.mods:
@@ -664,6 +687,9 @@ class MatchingPlan:
         if s.kind == "resample":
             src, c0, c, dst, dst_c0, scale, shift, relu = s.rs
             self.ops.trilinear_ac(src, c0, c, dst, dst_c0, scale, shift, relu)
+        elif s.kind == "resample_conv1x1":
+            src, dst, scale, shift, relu = s.rs
+            self.ops.resample_conv1x1(src.vol, src.c0, src.c, [(dst.vol, dst.c0, dst.c, s.weight, scale, shift, relu)])
         elif s.kind == "conv_simt":
             self.ops.conv3d_simt(s.p, s.weight, s.ref)
         elif s.kind == "conv_tc":
@@ -824,7 +850,8 @@ DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fus
 
 # tensor-core kernel / plan-rewrite knobs an ``engine_options`` dict may carry (defaults = what the product runs)
 _TC_KNOBS = {"accum_split": 0, "acc_sets": 0, "fuse_cv": True, "fuse_head": True, "collapse_stem0": True, "tile_w_log2": 0,
-             "resident_weights": 0, "depth_chunk": 0, "rolling": 0, "early_drain": 0, "reuse_buffers": True}
+             "resident_weights": 0, "depth_chunk": 0, "rolling": 0, "early_drain": 0, "reuse_buffers": True,
+             "fuse_resample_conv": False}
 
 
 def _options(model) -> dict:

@@ -30,6 +30,11 @@ class lea_conv(C.Structure):
                 ("dst", lea_vol), ("dst_c0", C.c_int32), ("dst_f32", C.c_void_p)]
 
 
+class lea_rc_out(C.Structure):
+    _fields_ = [("dst", lea_vol), ("dst_c0", C.c_int32), ("c_out", C.c_int32), ("weight", C.c_void_p),
+                ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p), ("relu", C.c_int32)]
+
+
 class lea_tc_opts(C.Structure):
     _fields_ = [("mma_terms", C.c_int32), ("fused_cv", C.c_int32), ("fx", lea_vol), ("fy", lea_vol),
                 ("d3", C.c_int32), ("num_sms", C.c_int32), ("accum_split", C.c_int32), ("acc_sets", C.c_int32), ("cv_maps", C.c_void_p),
@@ -49,6 +54,7 @@ SYMBOLS = {
     "lea_pack_planes": (C.c_int, [_vp, _VOLP, _i32, _i32, _vp]),
     "lea_unpack_planes": (C.c_int, [_VOLP, _i32, _i32, _vp, _vp]),
     "lea_trilinear_ac": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "lea_resample_conv1x1": (C.c_int, [_VOLP, _i32, _i32, _vp, _i32, _vp]),
     "lea_conv3d_simt": (C.c_int, [_CONVP, _vp, _vp]),
     "lea_tc_weight_image_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "lea_pack_weights_tc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
@@ -226,6 +232,22 @@ class Ops:
         with torch.cuda.device(src.t.device) if src.t.is_cuda else _null():
             self._check(self.lib.lea_trilinear_ac(C.byref(s), src_c0, C.byref(d), dst_c0, c, sc, sh, int(bool(relu)),
                                                   self._stream(src.t)))
+
+    def resample_conv1x1(self, src: PlanesVol, src_c0: int, c_in: int, outs):
+        """outs: list of (dst PlanesVol, dst_c0, c_out, weight fp32 (c_out, c_in, ...), bn_scale ptr|tensor|None,
+        bn_shift, relu) - one or two 1x1x1 ConvBR consumers of the align_corners=True resample of src."""
+        self._dev(src.t)
+        arr = (lea_rc_out * len(outs))()
+        for k, (dst, dst_c0, c_out, weight, sc, sh, relu) in enumerate(outs):
+            assert weight.dtype == torch.float32 and weight.is_contiguous() and weight.numel() == c_out * c_in
+            arr[k].dst, arr[k].dst_c0, arr[k].c_out = dst.struct(), dst_c0, c_out
+            arr[k].weight = weight.data_ptr()
+            arr[k].bn_scale = sc if isinstance(sc, int) or sc is None else sc.data_ptr()
+            arr[k].bn_shift = sh if isinstance(sh, int) or sh is None else sh.data_ptr()
+            arr[k].relu = int(bool(relu))
+        s = src.struct()
+        with self._dev_ctx(src.t):
+            self._check(self.lib.lea_resample_conv1x1(C.byref(s), src_c0, c_in, arr, len(outs), self._stream(src.t)))
 
     # ---- conv -------------------------------------------------------------------------------------------
     def make_conv(self, src: PlanesVol, src_c0: int, c_in: int, c_out: int, ksize: int,

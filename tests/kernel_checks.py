@@ -79,6 +79,31 @@ def check_trilinear(ops, device):
         assert float((got - want).abs().max()) <= 2e-6 * max(1.0, float(want.abs().max())), (src_sp, dst_sp)
 
 
+def check_resample_conv1x1(ops, device):
+    """lea_resample_conv1x1 against interpolate(align_corners=True) -> 1x1x1 conv -> BN -> ReLU for one and two consumers."""
+    for i, (src_sp, dst_sp, n_out) in enumerate([((8, 6, 12), (4, 3, 6), 2), ((5, 9, 7), (3, 5, 4), 1), ((4, 4, 8), (2, 2, 4), 2)]):
+        B, ct, c0, ci = 2, 24, 8, 16
+        x = _rand((B, ct) + src_sp, 90 + i, device)
+        src = ops.pack(x, 3)
+        outs, refs = [], []
+        xr = F.interpolate(x[:, c0:c0 + ci].cpu(), dst_sp, mode="trilinear", align_corners=True)
+        for k, co in enumerate([8, 16][:n_out]):
+            w = _rand((co, ci, 1, 1, 1), 95 + i + k, device, scale=0.3).contiguous()
+            sc = (_rand((co,), 97 + k, device).abs() + 0.5).contiguous()
+            sh = _rand((co,), 98 + k, device).contiguous()
+            relu = (k == 0)
+            dst = PlanesVol.empty(B, co + 8, 3, *dst_sp, device)
+            dst.t.zero_()
+            outs.append((dst, 8, co, w, sc, sh, relu))
+            r = F.conv3d(xr, w.cpu()) * sc.cpu().view(1, -1, 1, 1, 1) + sh.cpu().view(1, -1, 1, 1, 1)
+            refs.append(F.relu(r) if relu else r)
+        ops.resample_conv1x1(src, c0, ci, outs)
+        for (dst, dc0, co, *_), ref in zip(outs, refs):
+            got = ops.unpack(dst, dc0, co).cpu()
+            assert float((got - ref).abs().max()) <= 5e-6 * max(1.0, float(ref.abs().max())), (src_sp, dst_sp)
+            assert float(ops.unpack(dst, 0, 8).abs().max()) == 0.0
+
+
 def _conv_case(ops, device, B, c_in_total, c0, c_in, c_out, k, sp, bn, relu, res, planes, seed, conv_fn):
     x = _rand((B, c_in_total) + sp, seed, device)
     w = _rand((c_out, c_in, k, k, k), seed + 1, device, scale=0.2)

@@ -59,6 +59,10 @@ def test_trilinear(emu_ops):
     K.check_trilinear(emu_ops, DEV)
 
 
+def test_resample_conv1x1(emu_ops):
+    K.check_resample_conv1x1(emu_ops, DEV)
+
+
 def test_conv_simt(emu_ops):
     K.check_conv_simt(emu_ops, DEV)
 
@@ -127,3 +131,19 @@ def test_buffer_reuse_is_exact_and_smaller(emu_ops):
     assert torch.equal(outs[True][0], outs[False][0]) and torch.equal(outs[True][1], outs[False][1])
     print("activation bytes: plain %d, reused %d" % (sizes[False], sizes[True]))
     assert sizes[True] < 0.6 * sizes[False]
+
+
+def test_fused_resample_conv_is_on_the_plan_and_matches(emu_ops):
+    """The down-sampling resample + 1x1x1 ConvBR fusion (lea_resample_conv1x1) replaces resample + conv launches and
+    agrees with the two-launch form to the rounding of the intermediate it no longer stores."""
+    from conftest import load_golden
+    g = load_golden("cal_b2_24x48_d24")
+    outs = {}
+    for fused in (False, True):
+        mat, disp, model, plan = K.run_hot_path(emu_ops, DEV, g, planes=3, extra={"fuse_resample_conv": fused})
+        kinds = [s.kind for s in plan.steps]
+        assert ("resample_conv1x1" in kinds) == fused
+        outs[fused] = (mat, disp, len(kinds))
+    assert outs[True][2] < outs[False][2]
+    assert float((outs[True][1] - outs[False][1]).abs().max()) <= 1e-3
+    assert float((outs[True][0] - outs[False][0]).abs().max()) <= 2e-4 * float(outs[False][0].abs().max())

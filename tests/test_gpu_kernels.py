@@ -48,6 +48,10 @@ def test_trilinear(ops):
     K.check_trilinear(ops, DEV)
 
 
+def test_resample_conv1x1(ops):
+    K.check_resample_conv1x1(ops, DEV)
+
+
 def test_conv_simt(ops):
     K.check_conv_simt(ops, DEV)
 
@@ -155,6 +159,20 @@ def test_collapsed_stem0_matches_plain(ops):
     print("collapsed vs plain stem0: rel err", err)
     assert err <= 1e-4
     assert O.tolerance_report(disps[True], disps[False])["ok"]
+
+
+@pytest.mark.parametrize("conv", ["tc", "simt"])
+def test_fused_resample_conv_is_on_the_plan_and_matches(ops, conv):
+    """lea_resample_conv1x1 on the plan (default) against the resample + conv launches it replaces."""
+    g = load_golden("cal_48x96_d48")
+    outs = {}
+    for fused in (False, True):
+        mat, disp, model, plan = K.run_hot_path(ops, DEV, g, planes=3, conv=conv, extra={"fuse_resample_conv": fused})
+        kinds = [s.kind for s in plan.steps]
+        assert ("resample_conv1x1" in kinds) == fused
+        outs[fused] = (mat, disp)
+    assert float((outs[True][1] - outs[False][1]).abs().max()) <= 2e-3
+    assert float((outs[True][0] - outs[False][0]).abs().max()) <= 5e-4 * float(outs[False][0].abs().max())
 
 
 def test_cost_volume_full_kitti_bit_exact(ops):
