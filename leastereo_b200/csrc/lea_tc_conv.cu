@@ -75,7 +75,8 @@ struct TcParams {
     int tw_log2;              // tile = (1 << tw_log2) voxels along w x (128 >> tw_log2) along h  (3 for k = 3)
     int early;                // one accumulator set, depths handed to the epilogue one by one while the last channel group runs
     int cv_skip;              // collapsed stem0: skip the voxels lea_stem0_assemble writes (lea_cv_interior)
-    int dbg;                  // development switches (bit 0: epilogue skips its stores, bit 1: skips the TMEM loads)
+    int dbg;                  // development switches (bit 0: epilogue skips its stores, bit 1: skips the TMEM loads, bit 2: skips the
+                              // residual reads, bit 3: the issuer issues no MMAs) - timing ablations only, results are wrong
     int roll, R;              // rolling schedule (see lea_conv_tc_roll_kernel): R home accumulator blocks + 2 alias blocks
     int wres;                 // 1 = the weight parts of ALL channel groups stay resident in shared memory (loaded once per CTA)
     int fused_cv, ncg_half;   // fused cost volume: channel groups [0,ncg_half) come from x, the rest from y(w-d)
@@ -314,6 +315,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    // Programmatic dependent launch: the next launch of the stream may be scheduled as soon as every CTA of this grid
+    // has started (its CTAs take an SM when one of ours exits - one CTA fits per SM - and run their prologue there);
+    // no global memory is touched before griddepcontrol.wait, which returns once the PREVIOUS grid has completed and
+    // flushed, so the launch chain keeps stream order for every buffer, including the re-used arena.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
         for (int i = 0; i < 2; ++i) {
@@ -323,15 +329,16 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int i = 0; i < kMaxRing; ++i) mbar_init(smem_u32(dready + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x >= 64 && threadIdx.x < 128) {
-        const int n = threadIdx.x - 64;
-        s_scale[n] = (p.bn_scale && n < p.c_out) ? __ldg(p.bn_scale + n) : 1.0f;
-        s_shift[n] = (p.bn_shift && n < p.c_out) ? __ldg(p.bn_shift + n) : 0.0f;
-    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int n = threadIdx.x - 64;
+        s_scale[n] = (p.bn_scale && n < p.c_out) ? __ldg(p.bn_scale + n) : 1.0f;
+        s_shift[n] = (p.bn_shift && n < p.c_out) ? __ldg(p.bn_shift + n) : 0.0f;
     }
     tc_fence_before();
     __syncthreads();
@@ -445,6 +452,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     const uint32_t idesc_fresh = nfresh == 2 ? idesc2 : idesc1;
                     const int nrest = nkd - nfresh;
                     const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
+                    if (p.dbg & 8) {                  // development: no MMAs - what the TMA ring and the epilogue cost alone
+                        const bool wrap = (stage + 1 == p.nstages);
+                        probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
+                    } else
 #pragma unroll
                     for (int kh = 0; kh < KS; ++kh) {
 #pragma unroll
@@ -515,7 +526,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 for (int c16 = 0; c16 < p.c_out; c16 += 16) {
                     const bool two = (c16 + 8 < p.c_out);
                     uint4 rq[kJB][2][PL];
-                    if (p.has_res && valid) {
+                    if (p.has_res && valid && !(p.dbg & 4)) {
 #pragma unroll
                         for (int jj = 0; jj < kJB; ++jj) {
                             if (j0 + jj < nd) {
@@ -544,7 +555,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
                         float acc[16];
-                        {
+                        if (p.dbg & 2) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+                        } else {
                             uint32_t ra[16], rb[16];
                             tc_ld16_nowait(trow + (uint32_t)c16, ra);
                             const bool two_regions = (p.ngroups == 2) || p.fold;
@@ -561,7 +575,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
                             }
                         }
-                        if (!valid || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
+                        if (!valid || (p.dbg & 1) || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
@@ -572,7 +586,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h) * p.W + w;
                             for (int n = 0; n < 16 && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
                         } else {
-                            if (p.has_res) {
+                            if (p.has_res && !(p.dbg & 4)) {
                                 ep_add_raw8<PL>(rq[jj][0], acc);
                                 if (two) ep_add_raw8<PL>(rq[jj][1], acc + 8);
                             }
@@ -1323,9 +1337,19 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
     // always request the full budget so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
-    kernel<<<grid, p.roll ? kThreads : tc_threads(P), kSmemBudget, (cudaStream_t)stream>>>(tmap, p);
+    // programmatic stream serialization (see the kernel's prologue): opt-in with LEA_TC_PDL=1.  Measured inside the CUDA
+    // graph of the KITTI step: 196.0 pairs/s with, 196.1 without - launch gaps are not what the step loses.
+    static const int use_pdl = [] { const char* v = getenv("LEA_TC_PDL"); return (v && v[0] == '1') ? 1 : 0; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)(p.roll ? kThreads : tc_threads(P)));
+    cfg.dynamicSmemBytes = kSmemBudget; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = (use_pdl && !p.roll) ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, kernel, tmap, p);
     (void)smem;
-    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: launch failed: %s", cudaGetErrorString(e));
     return 0;
 }

@@ -22,8 +22,8 @@ for name, ci, co, sp in cases:
     img = ops.pack_weights_tc(w, 2)
     for res in (True, False):
         p = ops.make_conv(src, 0, ci, co, 3, sc, sh, True, dst=dst, res=dst if res else None)
-        for knobs in [{}, {"debug": 1}, {"debug": 3}, {"mma_terms": 1}, {"mma_terms": 1, "debug": 3}, {"acc_sets": 1},
-                      {"depth_chunk": 4}, {"depth_chunk": 16, "acc_sets": 1}]:
+        for knobs in [{}, {"debug": 1}, {"debug": 3}, {"debug": 4}, {"debug": 7}, {"debug": 8}, {"debug": 15}, {"mma_terms": 1},
+                      {"mma_terms": 1, "debug": 7}]:
             opts = lea_tc_opts()
             for kk, v in knobs.items():
                 setattr(opts, kk, v)
