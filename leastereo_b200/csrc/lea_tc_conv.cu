@@ -57,6 +57,14 @@ constexpr unsigned long long kWaitTimeoutCycles = 100000000ull;
 constexpr unsigned long long kWaitTimeoutCycles = 4000000000ull;
 #endif    // ~2 s: a stuck pipeline traps instead of hanging
 
+// Timing-ablation switches of the chunked kernel (lea_tc_opts.debug) exist only in builds with -DLEA_TC_ABLATION: even as
+// never-taken branches they cost the epilogue-bound 8-channel convs 8 % (629 -> 684 us, measured).
+#ifdef LEA_TC_ABLATION
+#define TC_DBG(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define TC_DBG(p, bit) false
+#endif
+
 struct TcParams {
     int B, D, H, W;
     int g0_stride_b;          // tensor-map dim-4 blocks per batch element = src channel blocks * P
@@ -452,7 +460,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     const uint32_t idesc_fresh = nfresh == 2 ? idesc2 : idesc1;
                     const int nrest = nkd - nfresh;
                     const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
-                    if (p.dbg & 8) {                  // development: no MMAs - what the TMA ring and the epilogue cost alone
+                    if (TC_DBG(p, 8)) {                // development: no MMAs - what the TMA ring and the epilogue cost alone
                         const bool wrap = (stage + 1 == p.nstages);
                         probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
                     } else
@@ -526,7 +534,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 for (int c16 = 0; c16 < p.c_out; c16 += 16) {
                     const bool two = (c16 + 8 < p.c_out);
                     uint4 rq[kJB][2][PL];
-                    if (p.has_res && valid && !(p.dbg & 4)) {
+                    if (p.has_res && valid && !TC_DBG(p, 4)) {
 #pragma unroll
                         for (int jj = 0; jj < kJB; ++jj) {
                             if (j0 + jj < nd) {
@@ -555,7 +563,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
                         float acc[16];
-                        if (p.dbg & 2) {
+                        if (TC_DBG(p, 2)) {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
                         } else {
@@ -575,7 +583,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
                             }
                         }
-                        if (!valid || (p.dbg & 1) || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
+                        if (!valid || TC_DBG(p, 1) || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
@@ -586,7 +594,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h) * p.W + w;
                             for (int n = 0; n < 16 && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
                         } else {
-                            if (p.has_res && !(p.dbg & 4)) {
+                            if (p.has_res && !TC_DBG(p, 4)) {
                                 ep_add_raw8<PL>(rq[jj][0], acc);
                                 if (two) ep_add_raw8<PL>(rq[jj][1], acc + 8);
                             }

@@ -1,5 +1,6 @@
 """Development aid: what bounds the single 16-/8-channel 3x3x3 convs (folded vs term-by-term weight images are chosen by
-LEA_TC_FOLD in the environment; epilogue ablations through lea_tc_opts.debug: bit 0 no stores, bit 1 no TMEM loads)."""
+LEA_TC_FOLD in the environment; epilogue ablations through lea_tc_opts.debug - bit 0 no stores, bit 1 no TMEM loads, bit 2 no
+residual reads, bit 3 no MMAs - only in a library built with -DLEA_TC_ABLATION)."""
 import sys, os
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
