@@ -294,6 +294,15 @@ __device__ __forceinline__ void tc_ld16_nowait(uint32_t taddr, uint32_t* r) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_touch8(uint32_t* r) {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]));
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // orders later uses of r[] after the preceding tcgen05.wait::ld (the registers are "rewritten" by an empty asm)
 __device__ __forceinline__ void tc_touch16(uint32_t* r) {
@@ -301,7 +310,65 @@ __device__ __forceinline__ void tc_touch16(uint32_t* r) {
                       "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
 }
 
-template <int KS, int NTERM, int PL>
+// Epilogue of one depth batch [j0, j0 + JB) of an item for the channel group at c16: NV = 8 or 16 accumulator columns
+// per region, SB depths per tcgen05.wait::ld.  rq = residual groups loaded by the caller (valid when p.has_res).
+template <int PL, int NV, int SB, int JB>
+__device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom& g, uint32_t tcol, uint32_t r1off,
+                                               bool two_regions, int j0, int nd, int c16, bool valid, int h, int w,
+                                               int64_t sp, const float* s_scale, const float* s_shift,
+                                               const uint4 (*rq)[2][PL]) {
+#pragma unroll
+    for (int jb = 0; jb < JB; jb += SB) {
+        if (j0 + jb >= nd) break;
+        uint32_t ra[SB][NV], rb[SB][NV];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+            const int j = j0 + jb + s;
+            if (j < nd) {
+                const uint32_t col = tcol + (uint32_t)((nd - 1 - j) * p.NP);
+                if (NV == 8) { tc_ld8_nowait(col, ra[s]); if (two_regions) tc_ld8_nowait(col + r1off, rb[s]); }
+                else         { tc_ld16_nowait(col, ra[s]); if (two_regions) tc_ld16_nowait(col + r1off, rb[s]); }
+            }
+        }
+        tc_wait_ld();
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+            const int jj = jb + s;
+            if (j0 + jj >= nd) break;
+            const int d = g.d0 + j0 + jj;
+            float acc[NV];
+            if (NV == 8) tc_touch8(ra[s]); else tc_touch16(ra[s]);
+            if (two_regions) {
+                if (NV == 8) tc_touch8(rb[s]); else tc_touch16(rb[s]);
+#pragma unroll
+                for (int i = 0; i < NV; ++i) acc[i] = __uint_as_float(ra[s][i]) + __uint_as_float(rb[s][i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NV; ++i) acc[i] = __uint_as_float(ra[s][i]);
+            }
+            if (!valid || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
+                if (p.relu) v = fmaxf(v, 0.0f);
+                acc[i] = v;
+            }
+            if (p.dst_f32) {
+                float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h) * p.W + w;
+                for (int n = 0; n < NV && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
+            } else {
+                if (p.has_res) {
+                    ep_add_raw8<PL>(rq[jj][0], acc);
+                    if (NV == 16) ep_add_raw8<PL>(rq[jj][1], acc + 8);
+                }
+                ep_store8<PL>(p.dst, g.b, (p.dst_c0 + c16) >> 3, d, h, w, acc);
+                if (NV == 16) ep_store8<PL>(p.dst, g.b, ((p.dst_c0 + c16) >> 3) + 1, d, h, w, acc + 8);
+            }
+        }
+    }
+}
+
+template <int KS, int NTERM, int PL, bool E8>
 __global__ void __launch_bounds__(tc_threads(PL), 1)
 lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -549,6 +616,21 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         mbar_wait(smem_u32(accfull + set), aphase, 301);
                         tc_fence_after();
                         waited = true;
+                    }
+                    if (E8 && !two && !p.early) {
+                        // The group holds ONE 8-channel block (8-channel convs, the tail of 24): read only its 8 columns,
+                        // and the whole depth batch with one tcgen05.wait::ld so that the TMEM latencies overlap.
+                        // Measured: the epilogue-bound 8-channel convs 640 -> 456 us.  Compiled only into the instances
+                        // that serve c_out % 16 == 8 (E8): the same treatment of full 16-channel groups (2 depths per
+                        // wait) needs 255 registers and spills - every conv lost 10-30 % - and even this extra path
+                        // costs the other convs 4-5 % when it is merely present in their kernel.
+                        const bool two_regions = (p.ngroups == 2) || p.fold;
+                        const uint32_t r1off = (uint32_t)(p.fold ? (p.NP >> 1) : p.Dc * p.NP);
+                        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                              (uint32_t)(set * p.ngroups * p.Dc * p.NP + c16);
+                        ep_depth_batch<PL, 8, kJB, kJB>(p, g, tcol, r1off, two_regions, j0, nd, c16, valid, h, w, sp,
+                                                        s_scale, s_shift, rq);
+                        continue;
                     }
 #pragma unroll
                     for (int jj = 0; jj < kJB; ++jj) {
@@ -981,17 +1063,17 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const TcParams);
-template <int KS>
+template <int KS, bool E8>
 static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
-    if (planes == 1) return lea_conv_tc_kernel<KS, 1, 1>;
+    if (planes == 1) return lea_conv_tc_kernel<KS, 1, 1, E8>;
     if (planes == 2) {
-        if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 2>;
-        if (nterm == 2) return lea_conv_tc_kernel<KS, 2, 2>;      // 8-channel layout
-        return lea_conv_tc_kernel<KS, 3, 2>;                       // bf16x3
+        if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 2, E8>;
+        if (nterm == 2) return lea_conv_tc_kernel<KS, 2, 2, E8>;  // 8-channel layout / folded terms
+        return lea_conv_tc_kernel<KS, 3, 2, E8>;                   // bf16x3
     }
-    if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 3>;
-    if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3>;          // 8-channel layout, 3 planes
-    return lea_conv_tc_kernel<KS, 6, 3>;                           // bf16x6
+    if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 3, E8>;
+    if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3, E8>;      // 8-channel layout, 3 planes
+    return lea_conv_tc_kernel<KS, 6, 3, E8>;                       // bf16x6
 }
 static TcKernelFn tc_roll_kernel_for(int nterm, int planes) {
     if (planes == 1) return lea_conv_tc_roll_kernel<1, 1>;
@@ -1004,8 +1086,9 @@ static TcKernelFn tc_roll_kernel_for(int nterm, int planes) {
     if (nterm == 3) return lea_conv_tc_roll_kernel<3, 3>;
     return lea_conv_tc_roll_kernel<6, 3>;
 }
-static TcKernelFn tc_kernel_for(int ks, int nterm, int planes) {
-    return ks == 3 ? tc_kernel_for_ks<3>(nterm, planes) : tc_kernel_for_ks<1>(nterm, planes);
+static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, bool e8) {
+    if (e8) return ks == 3 ? tc_kernel_for_ks<3, true>(nterm, planes) : tc_kernel_for_ks<1, true>(nterm, planes);
+    return ks == 3 ? tc_kernel_for_ks<3, false>(nterm, planes) : tc_kernel_for_ks<1, false>(nterm, planes);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1340,7 +1423,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    TcKernelFn kernel = p.roll ? tc_roll_kernel_for(p.nterm, P) : tc_kernel_for(p.ks, p.nterm, P);
+    TcKernelFn kernel = p.roll ? tc_roll_kernel_for(p.nterm, P) : tc_kernel_for(p.ks, p.nterm, P, (p.c_out & 15) == 8);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
