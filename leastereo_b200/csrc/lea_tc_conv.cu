@@ -581,7 +581,9 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // ================= epilogue warps 2..5 =================
         // Thread m owns output voxel m of the tile (TMEM lane m).  Depth slices are processed kJB at a time so that
         // the residual reads of kJB slices are in flight together (the epilogue is otherwise latency-bound).
-        constexpr int kJB = 4;
+        // depth slices per batch: 4 where the 8-column path exists, 2 elsewhere (the 16-column batch below holds
+        // 2 depths x 2 regions x 16 columns in registers; with 4-deep residual prefetch on top it spills)
+        constexpr int kJB = E8 ? 4 : 2;
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;                 // tile row = TMEM lane
         const int lh = m >> p.tw_log2, lw = m & ((1 << p.tw_log2) - 1);
@@ -630,6 +632,17 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + c16);
                         ep_depth_batch<PL, 8, kJB, kJB>(p, g, tcol, r1off, two_regions, j0, nd, c16, valid, h, w, sp,
                                                         s_scale, s_shift, rq);
+                        continue;
+                    }
+                    if (!E8 && two && !p.early) {
+                        // full 16-channel group: 2 depths per tcgen05.wait::ld.  Measured (KITTI, 4 pairs): 16-channel
+                        // cell ops 125 -> 106 us, batched ones 240 -> 211, conv1/conv2 -3 %; 199.8 -> 209.2 pairs/s.
+                        const bool two_regions = (p.ngroups == 2) || p.fold;
+                        const uint32_t r1off = (uint32_t)(p.fold ? (p.NP >> 1) : p.Dc * p.NP);
+                        const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) +
+                                              (uint32_t)(set * p.ngroups * p.Dc * p.NP + c16);
+                        ep_depth_batch<PL, 16, 2, kJB>(p, g, tcol, r1off, two_regions, j0, nd, c16, valid, h, w, sp,
+                                                       s_scale, s_shift, rq);
                         continue;
                     }
 #pragma unroll
