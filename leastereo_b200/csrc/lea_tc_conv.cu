@@ -368,7 +368,7 @@ __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom
     }
 }
 
-template <int KS, int NTERM, int PL, bool E8>
+template <int KS, int NTERM, int PL, int E8>
 __global__ void __launch_bounds__(tc_threads(PL), 1)
 lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -583,7 +583,9 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // the residual reads of kJB slices are in flight together (the epilogue is otherwise latency-bound).
         // depth slices per batch: 4 where the 8-column path exists, 2 elsewhere (the 16-column batch below holds
         // 2 depths x 2 regions x 16 columns in registers; with 4-deep residual prefetch on top it spills)
-        constexpr int kJB = E8 ? 4 : 2;
+        // (E8: 0 = every group is a full 16-channel group, 1 = c_out == 8, 2 = 16-channel groups and an 8-channel tail;
+        //  with kJB = 2 everywhere the 8-channel convs lose 21 %, with kJB = 4 and both batch paths the kernel spills)
+        constexpr int kJB = (E8 == 1) ? 4 : 2;
         const int q = warp & 3;                      // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;                 // tile row = TMEM lane
         const int lh = m >> p.tw_log2, lw = m & ((1 << p.tw_log2) - 1);
@@ -619,13 +621,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         tc_fence_after();
                         waited = true;
                     }
-                    if (E8 && !two && !p.early) {
+                    if (E8 != 0 && !two && !p.early) {
                         // The group holds ONE 8-channel block (8-channel convs, the tail of 24): read only its 8 columns,
                         // and the whole depth batch with one tcgen05.wait::ld so that the TMEM latencies overlap.
                         // Measured: the epilogue-bound 8-channel convs 640 -> 456 us.  Compiled only into the instances
-                        // that serve c_out % 16 == 8 (E8): the same treatment of full 16-channel groups (2 depths per
-                        // wait) needs 255 registers and spills - every conv lost 10-30 % - and even this extra path
-                        // costs the other convs 4-5 % when it is merely present in their kernel.
+                        // that serve c_out % 16 == 8: merely present in the other kernels it costs them 4-5 %.
                         const bool two_regions = (p.ngroups == 2) || p.fold;
                         const uint32_t r1off = (uint32_t)(p.fold ? (p.NP >> 1) : p.Dc * p.NP);
                         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) +
@@ -634,7 +634,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                                         s_scale, s_shift, rq);
                         continue;
                     }
-                    if (!E8 && two && !p.early) {
+                    if (E8 != 1 && two && !p.early) {
                         // full 16-channel group: 2 depths per tcgen05.wait::ld.  Measured (KITTI, 4 pairs): 16-channel
                         // cell ops 125 -> 106 us, batched ones 240 -> 211, conv1/conv2 -3 %; 199.8 -> 209.2 pairs/s.
                         const bool two_regions = (p.ngroups == 2) || p.fold;
@@ -1076,7 +1076,7 @@ lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_c
 }
 
 typedef void (*TcKernelFn)(const CUtensorMap, const TcParams);
-template <int KS, bool E8>
+template <int KS, int E8>
 static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
     if (planes == 1) return lea_conv_tc_kernel<KS, 1, 1, E8>;
     if (planes == 2) {
@@ -1099,9 +1099,10 @@ static TcKernelFn tc_roll_kernel_for(int nterm, int planes) {
     if (nterm == 3) return lea_conv_tc_roll_kernel<3, 3>;
     return lea_conv_tc_roll_kernel<6, 3>;
 }
-static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, bool e8) {
-    if (e8) return ks == 3 ? tc_kernel_for_ks<3, true>(nterm, planes) : tc_kernel_for_ks<1, true>(nterm, planes);
-    return ks == 3 ? tc_kernel_for_ks<3, false>(nterm, planes) : tc_kernel_for_ks<1, false>(nterm, planes);
+static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, int e8) {
+    if (e8 == 1) return ks == 3 ? tc_kernel_for_ks<3, 1>(nterm, planes) : tc_kernel_for_ks<1, 1>(nterm, planes);
+    if (e8 == 2) return ks == 3 ? tc_kernel_for_ks<3, 2>(nterm, planes) : tc_kernel_for_ks<1, 2>(nterm, planes);
+    return ks == 3 ? tc_kernel_for_ks<3, 0>(nterm, planes) : tc_kernel_for_ks<1, 0>(nterm, planes);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1436,7 +1437,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    TcKernelFn kernel = p.roll ? tc_roll_kernel_for(p.nterm, P) : tc_kernel_for(p.ks, p.nterm, P, (p.c_out & 15) == 8);
+    TcKernelFn kernel = p.roll ? tc_roll_kernel_for(p.nterm, P) : tc_kernel_for(p.ks, p.nterm, P, (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
