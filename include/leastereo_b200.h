@@ -208,10 +208,17 @@ int lea_masked_smooth_l1_bwd(const float* disp, const float* target, int64_t n, 
 /* optim.Adam(lr, betas=(0.9, 0.999)) of train.py:76 as one launch over a flat fp32 parameter buffer; step >= 1. */
 int lea_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                   float beta2, float eps, int32_t step, void* stream);
-/* utils/metrics.py:6-46 in one pass: acc7 (zeroed by the caller) += {#valid, sum |d| (EPE), #3-px-correct
- * (|d| < 3 or |d| < 0.05 target), #(|d| <= thresholds4[0..3])}; bad-N fraction = 1 - acc[3+k] / acc[0]. */
+/* Evaluation metrics in one pass, reference-identical by default: utils/metrics.py:6-46 (validity mask
+ * 0.001 < t < maxdisp; the reference stores |true - pred| into an int64 array, so its 3-px and bad-N tests see the
+ * error TRUNCATED toward zero, and invalid pixels stand at 10000 in those tests), evaluation.py:290-291 (EPE over the
+ * inclusive mask 0.001 <= t <= maxdisp) and train.py:203 (EPE over the strict mask).  acc9 (zeroed by the caller) +=
+ * {#valid, sum |d| inclusive mask, #3-px-correct (e < 3 or e < float32(0.05 t)), #(e <= thresholds4[0..3]),
+ *  #inclusive-valid, sum |d| strict mask};  3-px error = 1 - acc[2]/acc[0], bad-N = 1 - acc[3+k]/acc[0],
+ * EPE(evaluation.py) = acc[1]/acc[7], EPE(train.py) = acc[8]/acc[0].
+ * flags: LEA_METRICS_FLOAT_DIFF (1) compares the un-truncated float error instead (NOT the reference's numbers). */
+#define LEA_METRICS_FLOAT_DIFF 1
 int lea_disparity_metrics(const float* pred, const float* target, int64_t n, float maxdisp, const float* thresholds4,
-                          double* acc7, void* stream);
+                          int32_t flags, double* acc9, void* stream);
 
 #ifdef __cplusplus
 }

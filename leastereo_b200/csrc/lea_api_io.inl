@@ -49,9 +49,10 @@ extern "C" int lea_adam_step(float* param, const float* grad, float* exp_avg, fl
 }
 
 extern "C" int lea_disparity_metrics(const float* pred, const float* target, int64_t n, float maxdisp,
-                                     const float* thresholds4, double* acc7, void* stream) {
-    LEA_CHECK(pred && target && thresholds4 && acc7 && n > 0, "disparity_metrics: bad argument");
+                                     const float* thresholds4, int32_t flags, double* acc9, void* stream) {
+    LEA_CHECK(pred && target && thresholds4 && acc9 && n > 0, "disparity_metrics: bad argument");
+    LEA_CHECK((flags & ~LEA_METRICS_FLOAT_DIFF) == 0, "disparity_metrics: unknown flag");
     LEA_LAUNCH(lea_disparity_metrics_kernel, dim3(lea_io_grid(n)), dim3(LEA_IO_THREADS), 0, stream, pred, target, n,
-               maxdisp, thresholds4[0], thresholds4[1], thresholds4[2], thresholds4[3], acc7);
+               maxdisp, thresholds4[0], thresholds4[1], thresholds4[2], thresholds4[3], (int)flags, acc9);
     return LEA_POST_LAUNCH();
 }

@@ -138,34 +138,49 @@ lea_adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// M1  disparity metrics (utils/metrics.py:6-46, evaluation.py:290-307) in one pass.  Over valid pixels
-//     (0.001 < target < maxdisp):  acc[0] = count, acc[1] = sum |d| (EPE numerator), acc[2] = # "3-px correct"
-//     (|d| < 3 or |d| < 0.05 * target), acc[3 + k] = # pixels with |d| <= thr[k]  (bad-N = 1 - acc[3+k]/count).
+// M1  disparity metrics in one pass, REFERENCE-IDENTICAL by default (utils/metrics.py:6-46, evaluation.py:290-307,
+//     train.py:116-118,203).  The reference fills `abs_diff = np.full(shape, 10000)` - an int64 array - and assigns
+//     `abs_diff[mask] = |true - pred|` into it, which truncates the error toward zero; its tests are therefore
+//     `trunc|d| < 3 or trunc|d| < float32(target * 0.05)` and `trunc|d| <= thr`, evaluated over EVERY pixel with the
+//     invalid ones standing at 10000 (so an invalid pixel with target * 0.05 > 10000, or a threshold >= 10000, counts
+//     as correct - reproduced).  evaluation.py:290-291 takes its EPE over the INCLUSIVE mask 0.001 <= t <= maxdisp,
+//     train.py:203 over the strict one.  flags bit 0 (LEA_METRICS_FLOAT_DIFF) compares the un-truncated float |d|
+//     instead (not what the reference computes; opt-in only).
+//       acc[0] = # valid (0.001 < t < maxdisp)          acc[1] = sum |d| over 0.001 <= t <= maxdisp
+//       acc[2] = # "3-px correct"                      acc[3 + k] = # pixels passing threshold k (k < 4)
+//       acc[7] = # pixels with 0.001 <= t <= maxdisp    acc[8] = sum |d| over the strict mask
 // ---------------------------------------------------------------------------------------------------------
 #define LEA_METRIC_THR 4
+#define LEA_METRIC_ACC (5 + LEA_METRIC_THR)
+#define LEA_METRICS_FLOAT_DIFF 1
 __global__ void __launch_bounds__(LEA_IO_THREADS)
 lea_disparity_metrics_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t n, float maxdisp,
-                             float t0, float t1, float t2, float t3, double* __restrict__ acc) {
-    __shared__ double scratch[(3 + LEA_METRIC_THR) * LEA_IO_THREADS];
-    double v[3 + LEA_METRIC_THR];
+                             float t0, float t1, float t2, float t3, int flags, double* __restrict__ acc) {
+    __shared__ double scratch[LEA_METRIC_ACC * LEA_IO_THREADS];
+    double v[LEA_METRIC_ACC];
 #pragma unroll
-    for (int q = 0; q < 3 + LEA_METRIC_THR; ++q) v[q] = 0.0;
+    for (int q = 0; q < LEA_METRIC_ACC; ++q) v[q] = 0.0;
+    const bool float_diff = (flags & LEA_METRICS_FLOAT_DIFF) != 0;
+    const double thr[LEA_METRIC_THR] = {(double)t0, (double)t1, (double)t2, (double)t3};
     for (int64_t i = (int64_t)blockIdx.x * LEA_IO_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * LEA_IO_THREADS) {
         const float t = target[i];
-        if (t < maxdisp && t > 0.001f) {
-            const float d = t - pred[i];
-            const float a = d < 0.0f ? -d : d;
-            v[0] += 1.0; v[1] += (double)a;
-            if (a < 3.0f || a < t * 0.05f) v[2] += 1.0;
-            if (a <= t0) v[3] += 1.0;
-            if (a <= t1) v[4] += 1.0;
-            if (a <= t2) v[5] += 1.0;
-            if (a <= t3) v[6] += 1.0;
+        const float d = t - pred[i];                         // float32 like the numpy expression
+        const float a = d < 0.0f ? -d : d;
+        const bool valid = (t < maxdisp) && (t > 0.001f);
+        double e = 10000.0;                                  // the reference's fill value for invalid pixels
+        if (valid) {
+            e = float_diff ? (double)a : (double)truncf(a);  // float -> int64 assignment truncates toward zero
+            v[0] += 1.0; v[8] += (double)a;
         }
+        if (t >= 0.001f && t <= maxdisp) { v[1] += (double)a; v[7] += 1.0; }
+        if (e < 3.0 || e < (double)(t * 0.05f)) v[2] += 1.0;
+#pragma unroll
+        for (int k = 0; k < LEA_METRIC_THR; ++k)
+            if (e <= thr[k]) v[3 + k] += 1.0;
     }
-    lea_block_sum<double, 3 + LEA_METRIC_THR>(v, scratch);
+    lea_block_sum<double, LEA_METRIC_ACC>(v, scratch);
     if (threadIdx.x == 0) {
 #pragma unroll
-        for (int q = 0; q < 3 + LEA_METRIC_THR; ++q) atomicAdd(acc + q, v[q]);
+        for (int q = 0; q < LEA_METRIC_ACC; ++q) atomicAdd(acc + q, v[q]);
     }
 }

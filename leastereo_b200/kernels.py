@@ -80,7 +80,7 @@ SYMBOLS = {
     "lea_masked_smooth_l1": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, _vp]),
     "lea_masked_smooth_l1_bwd": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, C.c_float, _vp, _vp]),
     "lea_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_float, C.c_float, C.c_float, C.c_float, _i32, _vp]),
-    "lea_disparity_metrics": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, _vp, _vp]),
+    "lea_disparity_metrics": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, C.c_int32, _vp, _vp]),
 }
 # symbols only the CUDA build has (tcgen05 path); the CPU emulation used by the no-GPU tests lacks them
 DEVICE_ONLY = {"lea_tc_weight_image_bytes", "lea_pack_weights_tc", "lea_conv3d_tc", "lea_tc_selftest",
@@ -503,16 +503,18 @@ class Ops:
                                                float(beta2), float(eps), int(step), self._stream(param)))
 
     def disparity_metrics(self, pred: torch.Tensor, target: torch.Tensor, maxdisp: float,
-                          thresholds=(1.0, 2.0, 3.0, 5.0)) -> torch.Tensor:
-        """float64 [#valid, sum |d|, #3-px-correct, #(|d| <= thr_k) x4] (utils/metrics.py:6-46); device tensor."""
+                          thresholds=(1.0, 2.0, 3.0, 5.0), float_diff: bool = False) -> torch.Tensor:
+        """float64 [#valid, sum |d| (inclusive mask), #3-px-correct, #(e <= thr_k) x4, #inclusive-valid, sum |d| (strict
+        mask)] - ``lea_disparity_metrics`` (utils/metrics.py:6-46, evaluation.py:290-291, train.py:203); device tensor.
+        ``float_diff`` switches OFF the reference's int64 truncation of the error (not the reference's numbers)."""
         pred, target = self._f32(pred), self._f32(target)
         self._dev(pred, target)
         assert pred.shape == target.shape and len(thresholds) == 4
-        acc = torch.zeros(7, dtype=torch.float64, device=pred.device)
+        acc = torch.zeros(9, dtype=torch.float64, device=pred.device)
         thr = (C.c_float * 4)(*[float(t) for t in thresholds])
         with self._dev_ctx(pred):
             self._check(self.lib.lea_disparity_metrics(pred.data_ptr(), target.data_ptr(), pred.numel(), float(maxdisp),
-                                                       thr, acc.data_ptr(), self._stream(pred)))
+                                                       thr, 1 if float_diff else 0, acc.data_ptr(), self._stream(pred)))
         return acc
 
     def disparity_regression(self, p: torch.Tensor, maxdisp: int) -> torch.Tensor:

@@ -54,6 +54,10 @@ class InputPipeline:
         if self._head - self._tail >= self.depth:
             raise RuntimeError("InputPipeline: %d pairs already in flight" % self.depth)
         s = self._head % self.depth
+        if self._head >= self.depth:
+            # the pinned slot still feeds the slot's previous (asynchronous) upload until ``ready[s]`` has completed:
+            # wait for it on the HOST before overwriting the staging buffer (the caller need not synchronise)
+            self.ready[s].synchronize()
         self.host[s][0].copy_(torch.as_tensor(left_u8))
         self.host[s][1].copy_(torch.as_tensor(right_u8))
         with torch.cuda.stream(self.copy_stream):
@@ -173,16 +177,19 @@ class FlatAdam:
 # evaluation metrics
 # ---------------------------------------------------------------------------------------------------------
 def disparity_metrics(pred: torch.Tensor, target: torch.Tensor, maxdisp: float, thresholds=(1.0, 2.0, 3.0, 5.0),
-                      ops: Optional[Ops] = None) -> Dict[str, float]:
-    """EPE, 3-px error and bad-N fractions of ``utils/metrics.py:6-46`` / ``evaluation.py:290-307``; one kernel, one
-    56-byte device->host read."""
+                      ops: Optional[Ops] = None, float_diff: bool = False) -> Dict[str, float]:
+    """The numbers ``evaluation.py:290-307`` prints for one frame, from one kernel and one 72-byte device->host read:
+    ``epe`` (mean |d| over ``0.001 <= t <= maxdisp``, ``evaluation.py:290-292``), ``three_px_error`` and ``bad_N``
+    (``utils/metrics.py:11-46`` - including its int64 truncation of |d|, so e.g. bad-1 counts ``|d| < 2`` as good) and
+    ``train_epe`` (the strict-mask error ``train.py:203`` logs during validation).  ``float_diff=True`` gives the
+    un-truncated variant, which is NOT what the reference reports."""
     ops = ops or get_ops()
-    acc = ops.disparity_metrics(pred, target, maxdisp, thresholds).cpu().tolist()
+    acc = ops.disparity_metrics(pred, target, maxdisp, thresholds, float_diff=float_diff).cpu().tolist()
     n = acc[0]
-    if n <= 0:
-        return {"valid": 0, "epe": float("nan"), "three_px_error": float("nan"),
-                **{"bad_%g" % t: float("nan") for t in thresholds}}
-    out = {"valid": int(n), "epe": acc[1] / n, "three_px_error": 1.0 - acc[2] / n}
+    nan = float("nan")
+    out = {"valid": int(n), "epe": acc[1] / acc[7] if acc[7] > 0 else nan,
+           "train_epe": acc[8] / n if n > 0 else nan,
+           "three_px_error": 1.0 - acc[2] / n if n > 0 else nan}
     for k, t in enumerate(thresholds):
-        out["bad_%g" % t] = 1.0 - acc[3 + k] / n
+        out["bad_%g" % t] = 1.0 - acc[3 + k] / n if n > 0 else nan
     return out

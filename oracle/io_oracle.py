@@ -2,9 +2,12 @@
 only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module; the product never does.
 
 Each function cites the reference lines it follows (paths relative to /root/reference).  The reference holds no tests or
-golden vectors for this code either ("parity unpinned" by the reference's own fixtures); tests/test_oracle.py pins these
-restatements against the live reference functions where /root/reference is mounted (utils/metrics.py imports cleanly;
-predict.py does not - missing skimage/matplotlib - so its two functions are pinned by line-by-line restatement only).
+golden vectors for this code, so the restatements are pinned against RUNS OF THE REFERENCE ITSELF:
+tests/golden/make_io_golden.py imports utils/metrics.py and executes the source of predict.py's test_transform /
+load_data (the module itself needs skimage / matplotlib, which are absent, so those two functions are exec'd from their
+own source lines with PIL's Image.open replaced by an in-memory array) and of evaluation.py:290-292's EPE expression, and
+commits inputs + outputs as tests/golden/io_*.npz; tests/test_oracle.py checks this module against those fixtures and,
+where /root/reference is mounted, against the live functions.
 """
 import numpy as np
 import torch
@@ -46,26 +49,37 @@ def validity_mask(target: np.ndarray, max_disp):
     return (target < max_disp) & (target > 0.001)
 
 
-def three_px_error(pred: np.ndarray, true: np.ndarray, max_disp) -> float:
-    """utils/metrics.py:11-21."""
+def _abs_diff(pred: np.ndarray, true: np.ndarray, max_disp):
+    """utils/metrics.py:13-17 / :40-43: `np.full(shape, 10000)` is an INT64 array, so the assignment truncates |d| toward
+    zero; invalid pixels stand at 10000."""
     mask = validity_mask(true, max_disp)
-    abs_diff = np.full(true.shape, 10000.0)
+    abs_diff = np.full(true.shape, 10000)
     abs_diff[mask] = np.abs(true[mask] - pred[mask])
+    return mask, abs_diff
+
+
+def three_px_error(pred: np.ndarray, true: np.ndarray, max_disp) -> float:
+    """utils/metrics.py:11-21 (and :24-34, which also returns the `correct` map)."""
+    mask, abs_diff = _abs_diff(pred, true, max_disp)
     correct = (abs_diff < 3) | (abs_diff < true * 0.05)
     return 1 - (float(np.sum(correct)) / float(len(np.argwhere(mask))))
 
 
 def bad_pixel_frac(pred: np.ndarray, true: np.ndarray, max_disp, threshold) -> float:
     """utils/metrics.py:37-46."""
-    mask = validity_mask(true, max_disp)
-    abs_diff = np.full(true.shape, 10000.0)
-    abs_diff[mask] = np.abs(true[mask] - pred[mask])
+    mask, abs_diff = _abs_diff(pred, true, max_disp)
     correct = abs_diff <= threshold
     return 1 - (float(np.sum(correct)) / float(len(np.argwhere(mask))))
 
 
 def epe(pred: np.ndarray, true: np.ndarray, max_disp) -> float:
-    """train.py:162 / evaluation.py: mean |disp - target| over the validity mask."""
+    """evaluation.py:290-292: mean |prediction - disp| over the INCLUSIVE mask (disp >= 0.001) & (disp <= maxdisp)."""
+    mask = np.logical_and(true >= 0.001, true <= max_disp)
+    return float(np.mean(np.abs(pred[mask] - true[mask])))
+
+
+def train_epe(pred: np.ndarray, true: np.ndarray, max_disp) -> float:
+    """train.py:162 / :203: torch.mean(torch.abs(disp[mask] - target[mask])) over the strict validity mask."""
     mask = validity_mask(true, max_disp)
     return float(np.mean(np.abs(pred[mask] - true[mask])))
 

@@ -418,8 +418,18 @@ def check_feature_plan(ops, device, name="cal_46x94_d50", planes=3, conv="simt",
 # callers on either side of the path: input normalisation, loss, Adam, metrics
 # ---------------------------------------------------------------------------------------------------------
 def check_normalize_pad(ops, device):
-    """lea_image_stats_u8 + lea_normalize_pad_u8 against predict.py:144-184 restated in oracle/io_oracle.py."""
+    """lea_image_stats_u8 + lea_normalize_pad_u8 against (i) the outputs of predict.py's own load_data /
+    test_transform (tests/golden/io_predict.npz, written by tests/golden/make_io_golden.py) and (ii) the restatement in
+    oracle/io_oracle.py.  Tolerance 2e-6: the reference rounds (x - mean) / std once to float32 from numpy's fp64
+    mean / std, the kernel from exact integer sums - the last-ulp difference of a z-score of magnitude <= 4."""
     from oracle import io_oracle as IO
+    z = load_golden("io_predict")
+    for i in range(int(z["n_cases"])):
+        ch, cw = (int(v) for v in z["crop%d" % i])
+        for img, want in ((z["left%d" % i], z["input1_%d" % i]), (z["right%d" % i], z["input2_%d" % i])):
+            got = ops.normalize_pad_u8(torch.from_numpy(img).to(device), ch, cw).cpu().numpy()
+            assert got.shape == want.shape[1:], i
+            assert float(np.abs(got - want[0]).max()) <= 2e-6, i
     g = np.random.RandomState(7)
     for (h, w, ch, cw) in [(20, 30, 24, 36), (20, 30, 20, 30), (20, 30, 16, 24), (37, 53, 24, 48), (5, 300, 8, 512)]:
         left = g.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
@@ -488,14 +498,34 @@ def check_adam(ops, device):
 
 
 def check_disparity_metrics(ops, device):
+    """lea_disparity_metrics against (i) the fixtures written by RUNNING utils/metrics.py / evaluation.py:290-292
+    (tests/golden/io_metrics.npz) and (ii) the oracle restatement on a seeded case; counts are integers, so the
+    fractions must agree to rounding (1e-12), the EPE (float32 mean in numpy, fp64 sum here) to 1e-5."""
     from oracle import io_oracle as IO
     from leastereo_b200.pipeline import disparity_metrics
+    z = load_golden("io_metrics")
+    for i in range(int(z["n_cases"])):
+        p, t, maxdisp = z["pred%d" % i], z["true%d" % i], int(z["maxdisp%d" % i])
+        want = z["result%d" % i]                                        # [3px, bad1, bad2, bad3, bad5, epe, #valid]
+        got = disparity_metrics(torch.from_numpy(p).to(device), torch.from_numpy(t).to(device), maxdisp,
+                                (1.0, 2.0, 3.0, 5.0), ops=ops)
+        assert got["valid"] == int(want[6]), i
+        assert abs(got["three_px_error"] - want[0]) <= 1e-12, (i, got, want)
+        for k, thr in enumerate((1.0, 2.0, 3.0, 5.0)):
+            assert abs(got["bad_%g" % thr] - want[1 + k]) <= 1e-12, (i, thr, got, want)
+        assert abs(got["epe"] - want[5]) <= 1e-5 * max(1.0, abs(want[5])), (i, got, want)
     disp, target, maxdisp = _loss_case(device, seed=5, shape=(3, 31, 29), maxdisp=96.0)
     disp = disp + (torch.rand(disp.shape) < 0.1).to(device) * 7.0          # some gross errors
     got = disparity_metrics(disp, target, maxdisp, (1.0, 2.0, 3.0, 5.0), ops=ops)
     p, t = disp.cpu().numpy(), target.cpu().numpy()
     assert got["valid"] == int(IO.validity_mask(t, maxdisp).sum())
     assert abs(got["epe"] - IO.epe(p, t, maxdisp)) <= 1e-5
+    assert abs(got["train_epe"] - IO.train_epe(p, t, maxdisp)) <= 1e-5
     assert abs(got["three_px_error"] - IO.three_px_error(p, t, maxdisp)) <= 1e-12
     for thr in (1.0, 2.0, 3.0, 5.0):
         assert abs(got["bad_%g" % thr] - IO.bad_pixel_frac(p, t, maxdisp, thr)) <= 1e-12
+    # the opt-in un-truncated variant differs from the reference exactly as ADVICE r1 measured (more pixels "bad")
+    flt = disparity_metrics(disp, target, maxdisp, (1.0, 2.0, 3.0, 5.0), ops=ops, float_diff=True)
+    assert flt["bad_1"] > got["bad_1"] and flt["valid"] == got["valid"]
+    mask = IO.validity_mask(t, maxdisp)
+    assert abs(flt["bad_1"] - (1.0 - float((np.abs(t - p)[mask] <= 1.0).sum()) / float(mask.sum()))) <= 1e-12

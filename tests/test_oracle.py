@@ -88,6 +88,65 @@ def test_cost_volume_edges():
     assert O.cost_volume_numpy(x, y, 2).shape[2] == 0   # int(2/3) == 0 -> empty volume
 
 
+def test_io_oracle_metrics_against_reference_fixtures():
+    """oracle/io_oracle.py against numbers produced by running utils/metrics.py and evaluation.py:290-292
+    (tests/golden/io_metrics.npz, written by tests/golden/make_io_golden.py)."""
+    from oracle import io_oracle as IO
+    z = load_golden("io_metrics")
+    assert int(z["n_cases"]) >= 3
+    for i in range(int(z["n_cases"])):
+        p, t, maxdisp = z["pred%d" % i], z["true%d" % i], int(z["maxdisp%d" % i])
+        want = z["result%d" % i]
+        assert IO.three_px_error(p, t, maxdisp) == want[0]
+        for k, thr in enumerate((1, 2, 3, 5)):
+            assert IO.bad_pixel_frac(p, t, maxdisp, thr) == want[1 + k]
+        assert IO.epe(p, t, maxdisp) == want[5]
+        assert float(IO.validity_mask(t, maxdisp).sum()) == want[6]
+
+
+def test_io_oracle_predict_against_reference_fixtures():
+    """normalize_pair / test_transform against outputs of predict.py's own load_data / test_transform source."""
+    from oracle import io_oracle as IO
+    z = load_golden("io_predict")
+    for i in range(int(z["n_cases"])):
+        data = IO.normalize_pair(z["left%d" % i], z["right%d" % i])
+        assert data.dtype == np.float32 and np.array_equal(data, z["data%d" % i])
+        ch, cw = (int(v) for v in z["crop%d" % i])
+        left, right = IO.test_transform(data, ch, cw)
+        assert np.array_equal(left, z["input1_%d" % i]) and np.array_equal(right, z["input2_%d" % i])
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_DIR), reason="reference tree only exists in the build container")
+def test_io_oracle_against_live_reference():
+    """Same two comparisons on fresh random data against the LIVE reference functions (utils/metrics.py imported,
+    predict.py's two functions and evaluation.py's EPE lines executed from their own source)."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    import make_io_golden as G
+    from oracle import io_oracle as IO
+    M = G.reference_metrics()
+    rs = np.random.RandomState(123)
+    for maxdisp in (48, 192):
+        t = (rs.rand(3, 40, 50) * maxdisp * 1.1).astype(np.float32)
+        t[rs.rand(*t.shape) < 0.2] = 0
+        p = (t + rs.randn(*t.shape) * 1.7).astype(np.float32)
+        assert IO.three_px_error(p, t, maxdisp) == M.calculate_3px_error(p, t, maxdisp)
+        assert IO.three_px_error(p, t, maxdisp) == M.calculate_3px_error_and_correct_mask(p, t, maxdisp)[0]
+        for thr in (1, 2, 3):
+            assert IO.bad_pixel_frac(p, t, maxdisp, thr) == M.calculate_bad_pixel_frac(p, t, maxdisp, thr)
+        assert np.array_equal(IO.validity_mask(t, maxdisp), M.calculate_validity_mask(t, maxdisp))
+        assert IO.epe(p, t, maxdisp) == G.reference_epe(p, t, maxdisp)
+    left = rs.randint(0, 256, size=(19, 27, 3)).astype(np.uint8)
+    right = rs.randint(0, 256, size=(19, 27, 3)).astype(np.uint8)
+    test_transform, load_data = G.reference_predict_functions({"L": left, "R": right})
+    data = load_data("L", "R")
+    assert np.array_equal(IO.normalize_pair(left, right), data)
+    for ch, cw in ((24, 30), (12, 18)):
+        in1, in2, _, _ = test_transform(data, ch, cw)
+        l, r = IO.test_transform(data, ch, cw)
+        assert np.array_equal(l, in1.numpy()) and np.array_equal(r, in2.numpy())
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_DIR), reason="reference tree only exists in the build container")
 def test_oracle_against_live_reference():
     import sys
