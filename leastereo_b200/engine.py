@@ -30,6 +30,16 @@ from .structure import scale_dimension
 
 _LOCK = threading.Lock()
 
+# Bumped by anything that rewrites parameters behind autograd's back (``pipeline.FlatAdam.step`` updates the flat
+# buffer through a raw pointer, which changes neither ``data_ptr`` nor ``_version`` of the parameters): part of every
+# plan's parameter key, so packed weight images / BN vectors are rebuilt on the next eval-mode forward.
+_PARAM_GENERATION = [0]
+
+
+def bump_param_generation():
+    _PARAM_GENERATION[0] += 1
+
+
 
 @dataclass
 class Slice:
@@ -94,7 +104,6 @@ class MatchingPlan:
         self.volumes: List[PlanesVol] = []
         self._bn_users: List[Tuple[ConvBR3d, int]] = []     # (module, offset into the BN buffers)
         self._bn_channels = 0
-        self._eye: Dict[int, torch.Tensor] = {}
         self._resampled: Dict[tuple, Slice] = {}
         self.flat2d = False
         self._param_key = None
@@ -234,39 +243,32 @@ class MatchingPlan:
         return dst
 
     def _emit_conv(self, name: str, mods, src: Slice, dst: Optional[Slice], *, res: bool = False,
-                   dst_f32: Optional[torch.Tensor] = None, identity_c: int = 0, raw: bool = False,
+                   dst_f32: Optional[torch.Tensor] = None, raw: bool = False,
                    fused_cv: bool = False):
         """Append one ConvBR launch.
 
         ``mods``: a ConvBR3d, or a list of ConvBR3d reading the same input whose outputs are adjacent channel
-        slices (their weights / BN vectors are concatenated along c_out: one launch, one pass over the input);
-        ``None`` = identity 1x1x1 (``skip_connect`` / state copy).  ``raw`` drops BN+ReLU (applied later by the
-        up-sampling resample, see ``_resample``)."""
+        slices (their weights / BN vectors are concatenated along c_out: one launch, one pass over the input).
+        ``raw`` drops BN+ReLU (applied later by the up-sampling resample, see ``_resample``)."""
         wcat = None
-        if mods is None:
-            mods = ()
-            c_in = c_out = identity_c
-            k, relu, scale, shift = 1, False, None, None
-            weight = self._identity_weight(identity_c)
+        mods = tuple(mods) if isinstance(mods, (list, tuple)) else (mods,)
+        w0 = mods[0].conv.weight
+        c_in, k = w0.shape[1], w0.shape[2]
+        is2d = w0.dim() == 4                   # 2-D conv run as a k^3 conv on a depth-1 volume (zero kd != 1 taps)
+        c_out = sum(m.conv.out_channels for m in mods)
+        relu = mods[0].relu and not raw
+        use_bn = mods[0].use_bn and not raw
+        for m in mods[1:]:
+            if (m.conv.weight.shape[1], m.conv.weight.shape[2], m.relu, m.use_bn) != (c_in, k, mods[0].relu, mods[0].use_bn):
+                raise LeaError("%s: batched convs must agree on c_in, kernel size, bn and relu" % name)
+        scale = shift = None
+        if use_bn:
+            scale, shift = self._bn_slices(mods)
+        if len(mods) == 1 and not is2d:
+            weight = w0.detach()
         else:
-            mods = tuple(mods) if isinstance(mods, (list, tuple)) else (mods,)
-            w0 = mods[0].conv.weight
-            c_in, k = w0.shape[1], w0.shape[2]
-            is2d = w0.dim() == 4                   # 2-D conv run as a k^3 conv on a depth-1 volume (zero kd != 1 taps)
-            c_out = sum(m.conv.out_channels for m in mods)
-            relu = mods[0].relu and not raw
-            use_bn = mods[0].use_bn and not raw
-            for m in mods[1:]:
-                if (m.conv.weight.shape[1], m.conv.weight.shape[2], m.relu, m.use_bn) != (c_in, k, mods[0].relu, mods[0].use_bn):
-                    raise LeaError("%s: batched convs must agree on c_in, kernel size, bn and relu" % name)
-            scale = shift = None
-            if use_bn:
-                scale, shift = self._bn_slices(mods)
-            if len(mods) == 1 and not is2d:
-                weight = w0.detach()
-            else:
-                wcat = torch.zeros((c_out, c_in, k, k, k), dtype=torch.float32, device=self.device)
-                weight = wcat
+            wcat = torch.zeros((c_out, c_in, k, k, k), dtype=torch.float32, device=self.device)
+            weight = wcat
         if src.c != c_in:
             raise LeaError("%s: input has %d channels, conv expects %d" % (name, src.c, c_in))
         out_spatial = dst.spatial if (fused_cv and dst is not None) else src.spatial
@@ -283,7 +285,7 @@ class MatchingPlan:
             nbytes = 2.0 * self.P * m_vox * (c_in + c_out * (2 if res else 1))
         else:
             nbytes = 2.0 * self.P * m_vox * c_in + 4.0 * m_vox * c_out
-        use_tc = self.conv_mode == "tc" and len(mods) > 0 and \
+        use_tc = self.conv_mode == "tc" and \
             self.ops.tc_weight_image_bytes(c_in, c_out, k, self.P) > 0
         opts = None
         if use_tc:
@@ -304,6 +306,14 @@ class MatchingPlan:
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
                                weight=weight, wcat=wcat, opts=opts, ref=src.vol.t,
                                vols=(src.vol,) + ((dst.vol,) if dst is not None else ())))
+
+    def _emit_copy(self, name: str, src: Slice, dst: Slice, accumulate: bool):
+        """``Identity`` (``skip_connect``, operations_3d.py:84-90) inside a step sum, or a state copied into its concat
+        slot: ``dst (+)= src`` as one elementwise pass (``lea_affine_relu`` without scale / ReLU) - no weights, no MMA."""
+        if src.c != dst.c or src.spatial != dst.spatial:
+            raise LeaError("%s: identity needs matching shapes" % name)
+        nbytes = 2.0 * self.P * self.B * _prod(src.spatial) * src.c * (3 if accumulate else 2)
+        self.steps.append(Step("copy", name, 0.0, nbytes, rs=(src, dst, bool(accumulate)), vols=(src.vol, dst.vol)))
 
     def _emit_tap_projection(self, name: str, mod: ConvBR3d, src: Slice, dst: Slice):
         """1x1x1 conv C -> k^3 "tap" channels with weights W[t, c] = mod.weight[0, c, kd, kh, kw], t = kd*9+kh*3+kw:
@@ -395,11 +405,6 @@ class MatchingPlan:
         self.steps.append(Step("stem0_assemble", "stem0.collapsed.assemble", 0.0, nbytes,
                                rs=(lmap, abmap, v0, 0, c_out, scale, shift, st.relu), vols=(lmap, abmap, v0)))
 
-    def _identity_weight(self, c: int) -> torch.Tensor:
-        if c not in self._eye:
-            self._eye[c] = torch.eye(c, dtype=torch.float32, device=self.device).reshape(c, c, 1, 1, 1).contiguous()
-        return self._eye[c]
-
     def _max_batched_c_out(self) -> int:
         return 64
 
@@ -473,7 +478,7 @@ class MatchingPlan:
         else:
             r = s0 if s0.spatial == sp else self._resample(name + ".resample_s0", s0, sp)
             if first_in_concat <= 0:
-                self._emit_conv(name + ".s0_copy", None, r, state_slot(0), identity_c=c_out)
+                self._emit_copy(name + ".s0_copy", r, state_slot(0), accumulate=False)
             else:
                 slots[0] = r
         self._pre(name + ".preprocess", cell.preprocess, s1, sp, state_slot(1))
@@ -517,8 +522,8 @@ class MatchingPlan:
                 dst = Slice(first.vol, first.c0, c_out * len(group))
                 res = written.get(tgt, False)
                 if isinstance(op, _IDENTITY):
-                    self._emit_conv("%s._ops.%d(skip)" % (name, opi), None, state_slot(j), dst, res=res,
-                                    identity_c=c_out)
+                    # skip_connect (operations_3d.py:84-90): the state is added into (or copied to) the target slot
+                    self._emit_copy("%s._ops.%d(skip)" % (name, opi), state_slot(j), dst, accumulate=res)
                 else:
                     mods = [cell._ops[o] for (_, o) in group]
                     nm = "%s._ops.%s" % (name, "+".join(str(o) for (_, o) in group))
@@ -628,7 +633,7 @@ class MatchingPlan:
 
     # ---- parameters -----------------------------------------------------------------------------------
     def _current_param_key(self):
-        key = []
+        key = [_PARAM_GENERATION[0]]
         for mod, _ in self._bn_users:
             for t in (mod.bn.weight, mod.bn.bias, mod.bn.running_mean, mod.bn.running_var):
                 key.append((t.data_ptr(), t._version))
@@ -700,6 +705,9 @@ class MatchingPlan:
         elif s.kind == "head_taps":
             q, q_c0, mat, ws = s.rs
             self.ops.head_taps(q, q_c0, mat, ws)
+        elif s.kind == "copy":
+            src, dst, accumulate = s.rs
+            self.ops.affine_relu(src.vol, src.c0, dst.vol, dst.c0, src.c, None, None, False, accumulate)
         elif s.kind == "repack":
             src, dst, c = s.rs
             self.ops.affine_relu(src, 0, dst, 0, c, None, None, False, False)
@@ -895,6 +903,15 @@ def _require_inference(module):
             "through LEAStereo.forward (leastereo_b200/training.py) - there is deliberately no PyTorch fallback")
 
 
+def _no_eval_autograd(*inputs):
+    """The eval-mode path is inference-only (its result is detached).  Refuse silently wrong gradients: an input that
+    requires grad under ``enable_grad`` would get none.  (Train mode - ``model.train()`` - is differentiable.)"""
+    if torch.is_grad_enabled() and any(t.requires_grad for t in inputs):
+        raise RuntimeError("leastereo_b200: the eval-mode forward is not differentiable (inputs require grad); wrap the "
+                           "call in torch.no_grad() as predict.py / train.py's val() do, or switch the module to "
+                           "train() for the differentiable path")
+
+
 def hot_path_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optional[Ops] = None) -> torch.Tensor:
     """cost volume -> matching net -> disparity head on feature maps (B, C, H3, W3) -> (B, 3*H3, 3*W3)."""
     if model.training:
@@ -928,6 +945,7 @@ def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[O
     if model.training or opt.get("feature", "native") != "native" or opt["conv"] != "tc" or left.shape != right.shape:
         return None
     ops = ops or get_ops()
+    _no_eval_autograd(left, right)
     B, _, H, W = left.shape
     D3 = int(model.maxdisp / 3)
     h3, w3 = (H - 1) // 3 + 1, (W - 1) // 3 + 1

@@ -73,7 +73,9 @@ class LEAStereo(nn.Module):
             return self.feature(x), self.feature(y)
 
     def forward(self, x, y):
-        from .engine import full_forward, hot_path_forward
+        from .engine import full_forward, hot_path_forward, _no_eval_autograd
+        if not self.training:
+            _no_eval_autograd(x, y)         # eval mode is inference-only: never hand back silently detached results
         if not self.training and x.is_cuda:
             out = full_forward(self, x, y)          # native feature net + hot path (engine option feature="native")
             if out is not None:

@@ -171,6 +171,9 @@ class FlatAdam:
         self.t += 1
         self.ops.adam_step(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
                            self.eps, self.t)
+        # the kernel wrote the parameters through a raw pointer (no autograd version bump): tell the inference plans
+        from .engine import bump_param_generation
+        bump_param_generation()
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -41,6 +41,7 @@ class TrainPlan:
         self.grads: Dict[int, PlanesVol] = {}
         self.values: List[PlanesVol] = []
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self.generation = 0                        # forward counter: a backward must belong to the latest forward
         self._build()
 
     # ---- buffers ----------------------------------------------------------------------------------------
@@ -195,6 +196,7 @@ class TrainPlan:
 
     # ---- execution ----------------------------------------------------------------------------------------
     def forward(self, fx: torch.Tensor, fy: torch.Tensor) -> torch.Tensor:
+        self.generation += 1                       # the plan's buffers now hold THIS forward's activations
         self.ops.cost_volume_planes(fx, fy, self.maxdisp, self.P, out=self.cost)
         for n in self.nodes:
             n.forward()
@@ -364,11 +366,18 @@ class _HotPathTrainFn(torch.autograd.Function):
         ctx.params = params
         with torch.no_grad():
             disp = plan.forward(fx.detach().float().contiguous(), fy.detach().float().contiguous())
+        ctx.generation = plan.generation
         return disp
 
     @staticmethod
     def backward(ctx, gdisp):
         plan = ctx.plan
+        if ctx.generation != plan.generation:
+            # the single cached plan holds the saved activations (33 GB at 288x576 batch 4): a second train-mode
+            # forward has overwritten the ones this backward needs
+            raise RuntimeError("leastereo_b200: backward() of a train-mode forward whose saved activations were "
+                               "overwritten by a later forward through the same module (one forward may be "
+                               "outstanding per module; call backward() before the next train-mode forward)")
         with torch.no_grad():
             dfx, dfy, pg = plan.backward(gdisp)
         grads = []
@@ -392,6 +401,8 @@ def hot_path_train_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optio
     D3 = int(model.maxdisp / 3)
     key = (id(model.matching), str(fx.device), B, D3, H3, W3, planes, conv, id(ops))
     plan = _TRAIN_PLANS.get(key)
+    if plan is not None and plan.m is not model.matching:       # id() of a collected module re-used by a new one
+        plan = None
     if plan is None:
         _TRAIN_PLANS.clear()                       # one live training plan: buffers are large
         plan = TrainPlan(model.matching, ops, B, (D3, H3, W3), planes, fx.device, conv, model.maxdisp)

@@ -24,7 +24,14 @@ CASES = [
     ("cal_48x96_d48", 48, 96, 48, "calibrated"),
     ("cal_46x94_d50", 46, 94, 50, "calibrated"),     # ragged: H, W, maxdisp not multiples of 3 (H3=16, W3=32, D3=16)
     ("cal_b2_24x48_d24", 24, 48, 24, "calibrated"),  # batch 2, smallest volume (level-2 depth 2)
+    ("cal_skip_b2_24x48_d24", 24, 48, 24, "calibrated"),   # a 3D genotype with skip_connect ops (SKIP_GENOTYPE_3D)
 ]
+
+# models/genotypes_3d.py:5-8: op 0 = skip_connect (Identity), op 1 = 3d_conv_3x3.  The shipped matching genotype has no
+# op 0; this one exercises Identity inside a step sum (rows 0 and 3) and - through the row-order / branch-order quirk
+# of skip_model_3d.py:33-36 vs :58-68 - an Identity that is the first contribution of a state as well as one that is
+# added to a conv's output.
+SKIP_GENOTYPE_3D = np.array([[1, 0], [0, 1], [3, 1], [4, 0], [8, 1], [6, 1]], dtype=np.int64)
 
 
 def state_dict_sha256(sd) -> str:
@@ -35,13 +42,19 @@ def state_dict_sha256(sd) -> str:
     return h.hexdigest()
 
 
-def build_reference(maxdisp):
-    sys.path.insert(0, REF)
+def build_reference(maxdisp, matching_genotype=None):
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
     from config_utils.leastereo_args import LEAStereoArgs
     from retrain.LEAStereo import LEAStereo
     A = os.path.join(REF, "run/sceneflow/best/architecture/")
+    cell_arch_mat = A + "matching_genotype.npy"
+    if matching_genotype is not None:
+        import tempfile
+        cell_arch_mat = os.path.join(tempfile.mkdtemp(prefix="lea_genotype_"), "matching_genotype.npy")
+        np.save(cell_arch_mat, np.asarray(matching_genotype))
     args = LEAStereoArgs(net_arch_fea=A + "feature_network_path.npy", cell_arch_fea=A + "feature_genotype.npy",
-                         net_arch_mat=A + "matching_network_path.npy", cell_arch_mat=A + "matching_genotype.npy")
+                         net_arch_mat=A + "matching_network_path.npy", cell_arch_mat=cell_arch_mat)
     args.maxdisp = maxdisp
     args.cuda = False
     torch.manual_seed(0)
@@ -55,9 +68,13 @@ def make_inputs(B, H, W):
 
 def main():
     torch.set_num_threads(8)
+    want = set(sys.argv[1:])
     for name, H, W, maxdisp, regime in CASES:
+        if want and name not in want:
+            continue
         B = 2 if "_b2_" in name else 1
-        model = build_reference(maxdisp)
+        genotype = SKIP_GENOTYPE_3D if "_skip_" in name else None
+        model = build_reference(maxdisp, genotype)
         sha_init = state_dict_sha256(model.state_dict())
         left, right = make_inputs(B, H, W)
         bn = {}
@@ -89,6 +106,8 @@ def main():
             cost_shape=np.array(cost.shape), cost_sample=cost[:, ::7, ::3, ::5, ::3].copy(),
             state_sha256_init=np.array(sha_init), torch_version=np.array(torch.__version__),
         )
+        if genotype is not None:
+            out["matching_genotype"] = genotype
         for k, v in bn.items():
             out["bn/" + k] = v
         path = os.path.join(HERE, name + ".npz")

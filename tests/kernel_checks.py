@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from conftest import golden_state_dict, load_golden, seeded_model
+from conftest import golden_arch, golden_genotype, golden_model, golden_state_dict, load_golden, seeded_model
 from oracle import leastereo_oracle as O
 from leastereo_b200.kernels import PlanesVol
 from leastereo_b200 import engine
@@ -292,9 +292,7 @@ def check_disparity_regression(ops, device):
 def run_hot_path(ops, device, g, planes, conv="simt", mma_terms=0, extra=None):
     """Product engine on a golden case's feature maps; returns (mat, disp) on CPU."""
     maxdisp = int(g["maxdisp"])
-    model = seeded_model(maxdisp)
-    model.load_state_dict(golden_state_dict(g, model))
-    model = model.to(device).eval()
+    model = golden_model(g, device).eval()
     model.engine_options = {"planes": planes, "conv": conv, "mma_terms": mma_terms}
     model.engine_options.update(extra or {})
     fx, fy = torch.from_numpy(g["fx"]).to(device), torch.from_numpy(g["fy"]).to(device)

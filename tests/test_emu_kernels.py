@@ -89,6 +89,18 @@ def test_hot_path_golden_exact_planes(emu_ops):
     assert rep["max_abs"] <= 0.05, rep
 
 
+def test_hot_path_skip_connect_genotype(emu_ops):
+    """A 3D genotype with skip_connect ops (Identity inside the step sums) against the reference's own run of it; the
+    plan must execute them as copy/accumulate passes, not as convolutions."""
+    from conftest import load_golden
+    g = load_golden("cal_skip_b2_24x48_d24")
+    mat, disp, model, plan = K.run_hot_path(emu_ops, DEV, g, planes=3)
+    copies = [s for s in plan.steps if s.kind == "copy"]
+    assert len(copies) == 2 * 12, [s.name for s in copies]                 # two Identity ops in each of the 12 cells
+    rep = K.check_hot_path_golden(emu_ops, DEV, "cal_skip_b2_24x48_d24", planes=3, mat_rtol=2e-4)
+    print(rep)
+
+
 def test_hot_path_golden_two_planes(emu_ops):
     # 2 planes (the bf16x3 operand format): activations carry 16 significant bits between layers
     rep = K.check_hot_path_golden(emu_ops, DEV, "cal_b2_24x48_d24", planes=2, mat_rtol=5e-3)

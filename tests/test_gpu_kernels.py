@@ -72,7 +72,8 @@ def test_disparity_regression(ops):
     K.check_disparity_regression(ops, DEV)
 
 
-@pytest.mark.parametrize("name", ["raw_48x96_d48", "cal_48x96_d48", "cal_46x94_d50", "cal_b2_24x48_d24"])
+@pytest.mark.parametrize("name", ["raw_48x96_d48", "cal_48x96_d48", "cal_46x94_d50", "cal_b2_24x48_d24",
+                                  "cal_skip_b2_24x48_d24"])
 @pytest.mark.parametrize("planes", [3, 2])
 def test_hot_path_golden_simt(ops, name, planes):
     rep = K.check_hot_path_golden(ops, DEV, name, planes=planes, conv="simt", mat_rtol=None)
@@ -100,7 +101,8 @@ def test_conv_tc_single_pass(ops):
     K.check_conv_tc(ops, DEV, planes=2, mma_terms=1, verbose=True)
 
 
-@pytest.mark.parametrize("name", ["raw_48x96_d48", "cal_48x96_d48", "cal_46x94_d50", "cal_b2_24x48_d24"])
+@pytest.mark.parametrize("name", ["raw_48x96_d48", "cal_48x96_d48", "cal_46x94_d50", "cal_b2_24x48_d24",
+                                  "cal_skip_b2_24x48_d24"])
 @pytest.mark.parametrize("planes", [2, 3])
 def test_hot_path_golden_tc(ops, name, planes):
     rep = K.check_hot_path_golden(ops, DEV, name, planes=planes, conv="tc", mat_rtol=None)

@@ -27,6 +27,14 @@ def test_train_step_tensor_core(ops):
     print("tc/P=2 train step vs autograd:", check_train_step(ops, DEV, planes=2, conv="tc", tol=2e-2, grad_tol=1e-1))
 
 
+def test_train_step_skip_connect_genotype(ops):
+    """3D genotype with skip_connect ops (operations_3d.py:84-104): Identity forward/backward on the GPU kernels."""
+    print("skip genotype, simt/P=3:", check_train_step(ops, DEV, planes=3, conv="simt", tol=2e-3, grad_tol=3e-2,
+                                                       name="cal_skip_b2_24x48_d24"))
+    print("skip genotype, tc/P=2:", check_train_step(ops, DEV, planes=2, conv="tc", tol=2e-2, grad_tol=1e-1,
+                                                     name="cal_skip_b2_24x48_d24"))
+
+
 def test_module_train_mode_end_to_end(ops):
     """model.train(); loss.backward() through LEAStereo.forward (feature net by PyTorch autograd, hot path by ours)."""
     from conftest import seeded_model

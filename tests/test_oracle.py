@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_CASES, REFERENCE_DIR, golden_state_dict, load_golden
+from conftest import GOLDEN_CASES, REFERENCE_DIR, golden_arch, golden_state_dict, load_golden
 from oracle import leastereo_oracle as O
 
 
@@ -27,7 +27,7 @@ def test_hot_path_against_golden(name):
     maxdisp = int(g["maxdisp"])
     with torch.no_grad():
         cost = O.cost_volume(torch.from_numpy(g["fx"]), torch.from_numpy(g["fy"]), maxdisp)
-        mat = O.matching_forward(sd, cost)
+        mat = O.matching_forward(sd, cost, golden_arch(g))
         disp = O.disp_head(mat, maxdisp)
     ref_mat = torch.from_numpy(g["mat"])
     assert mat.shape == ref_mat.shape
