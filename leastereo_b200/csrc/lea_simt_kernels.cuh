@@ -540,8 +540,12 @@ lea_conv1_simt_kernel(lea_conv p, const float* __restrict__ weight) {
 // =========================================================================================================
 LEA_HD lea_axis_lerp lea_axis_half_pixel(int dst, int in_n, int out_n) {
     lea_axis_lerp r;
+    // ATen (UpSampleKernel.cpp, area_pixel_compute_source_index) evaluates scale * (dst + 0.5) - 0.5 as ONE fused
+    // multiply-add in fp32 (probed: F.interpolate's weights equal this formula bit for bit for every BASELINE size, and
+    // differ from the two-rounding form by up to 1.5e-5) - e.g. output 1 of an exact x3 up-sample gets l1 = 1.49e-8, not
+    // 0.  With un-normalised logits (~1e8) those weight bits decide the soft-argmin, so they are reproduced exactly.
     const float scale = (float)in_n / (float)out_n;
-    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    float src = fmaf(scale, (float)dst + 0.5f, -0.5f);
     if (src < 0.0f) src = 0.0f;
     int i0 = (int)floorf(src);
     if (i0 > in_n - 1) i0 = in_n - 1;
@@ -613,6 +617,7 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
     }
     // pass 1: per-pixel minimum of the blended column; this lane's quarter of the samples, then min over the 4 lanes
     float m[9];
+    float amax = 0.0f;                       // largest |logit| of the cell: decides whether the x3 shortcut below is safe
 #pragma unroll
     for (int q = 0; q < 9; ++q) m[q] = 3.0e38f;
     {
@@ -624,7 +629,11 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
             if (k + 1 < kb) LEA_DH_LOAD(nxt, k + 1);
             LEA_DH_COMBINE(u, cur);
 #pragma unroll
-            for (int q = 0; q < 9; ++q) { m[q] = u[q] < m[q] ? u[q] : m[q]; cur[q] = nxt[q]; }
+            for (int q = 0; q < 9; ++q) {
+                m[q] = u[q] < m[q] ? u[q] : m[q];
+                amax = fmaxf(amax, fabsf(u[q]));
+                cur[q] = nxt[q];
+            }
         }
 #pragma unroll
         for (int q = 0; q < 9; ++q) {
@@ -633,11 +642,19 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
             o = __shfl_xor_sync(0xffffffffu, m[q], 2);
             m[q] = o < m[q] ? o : m[q];
         }
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
     }
     float den[9], num[9], u0[9], u1[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) { den[q] = 0.0f; num[q] = 0.0f; u0[q] = 0.0f; u1[q] = 0.0f; }
-    if (maxdisp == 3 * D3) {
+    // The shortcut below replaces the reference's fp32 interpolation weights along disparity (lea_axis_half_pixel:
+    // 2/3 and 1/3 carry rounding errors up to ~2e-6, output 1 has l1 = 1.49e-8) by exact thirds.  That changes a logit
+    // by at most 2e-6 * |u_k+1 - u_k|: harmless for normalised logits, decisive for the soft-argmin of un-normalised ones
+    // (random-init weights with identity BN give |u| ~ 1e8; measured at 288x576: 0.2 % of pixels off by up to 0.4 px
+    // against the reference, all of them ties that the reference's weight bits break).  So it is taken only where every
+    // logit of the cell is below 64 (error <= 2.6e-4 in the exponent); other cells use the reference's own weights.
+    if (maxdisp == 3 * D3 && amax <= 64.0f) {
         // pass 2, exact x3 scale (every BASELINE config): output 0 is sample 0, 3k+1 is sample k, 3k+2 and 3k+3 blend
         // samples k and k+1 with weights (2/3, 1/3) and (1/3, 2/3) (sample D3 := sample D3-1).  With
         // T_k = exp((m - u_k) / 3) the three softmin terms are T_k^3, T_k^2 T_{k+1}, T_k T_{k+1}^2: ONE exp per sample

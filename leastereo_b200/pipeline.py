@@ -31,53 +31,63 @@ def preprocess_pair(left_u8: torch.Tensor, right_u8: torch.Tensor, crop_h: int, 
 
 
 class InputPipeline:
-    """Double-buffered host->device feed of 8-bit stereo pairs: while pair k is being normalised / run on the compute
-    stream, pair k+1 is copied from pinned memory on a side stream.  ``submit`` takes (H, W, 3) uint8 CPU tensors (or
-    numpy arrays); ``next`` returns the normalised (1, 3, crop_h, crop_w) pair for the oldest submitted pair."""
+    """Double-buffered host->device feed of 8-bit stereo pairs: while batch k is being normalised / run on the compute
+    stream, batch k+1 is copied from pinned memory on a side stream.  ``submit`` takes (H, W, 3) uint8 CPU tensors (or
+    numpy arrays) - or (batch, H, W, 3) stacks when ``batch > 1``; ``next`` returns the normalised
+    (batch, 3, crop_h, crop_w) left / right tensors of the oldest submitted batch (``predict.py:144-184`` per pair).
+    ``dst=(left, right)`` makes ``next`` write into caller-owned tensors (e.g. the static inputs of a CUDA graph).
 
-    def __init__(self, H: int, W: int, crop_h: int, crop_w: int, device, depth: int = 2, ops: Optional[Ops] = None):
+    Only the 8-bit images cross PCIe: 2*H*W*3 bytes per pair, a quarter of the fp32 tensors the reference uploads."""
+
+    def __init__(self, H: int, W: int, crop_h: int, crop_w: int, device, depth: int = 2, ops: Optional[Ops] = None,
+                 batch: int = 1):
         self.ops = ops or get_ops()
         self.device = torch.device(device)
         self.crop = (int(crop_h), int(crop_w))
-        self.depth = depth
-        self.host = [torch.empty((2, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(depth)]
-        self.dev = [torch.empty((2, H, W, 3), dtype=torch.uint8, device=self.device) for _ in range(depth)]
-        self.out = [torch.empty((2, 3, crop_h, crop_w), dtype=torch.float32, device=self.device) for _ in range(depth)]
-        self.sums = [torch.zeros((2, 6), dtype=torch.int64, device=self.device) for _ in range(depth)]
+        self.depth, self.batch = depth, int(batch)
+        B = self.batch
+        self.host = [torch.empty((2, B, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(depth)]
+        self.dev = [torch.empty((2, B, H, W, 3), dtype=torch.uint8, device=self.device) for _ in range(depth)]
+        self.out = [torch.empty((2, B, 3, crop_h, crop_w), dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.sums = [torch.zeros((2, B, 6), dtype=torch.int64, device=self.device) for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.ready = [torch.cuda.Event() for _ in range(depth)]
         self.consumed = [torch.cuda.Event() for _ in range(depth)]
         self._head = self._tail = 0
         self.h2d_bytes_per_pair = 2 * H * W * 3
+        self.h2d_bytes_per_batch = B * self.h2d_bytes_per_pair
 
     def submit(self, left_u8, right_u8):
         if self._head - self._tail >= self.depth:
-            raise RuntimeError("InputPipeline: %d pairs already in flight" % self.depth)
+            raise RuntimeError("InputPipeline: %d batches already in flight" % self.depth)
         s = self._head % self.depth
         if self._head >= self.depth:
             # the pinned slot still feeds the slot's previous (asynchronous) upload until ``ready[s]`` has completed:
             # wait for it on the HOST before overwriting the staging buffer (the caller need not synchronise)
             self.ready[s].synchronize()
-        self.host[s][0].copy_(torch.as_tensor(left_u8))
-        self.host[s][1].copy_(torch.as_tensor(right_u8))
+        self.host[s][0].copy_(torch.as_tensor(left_u8).reshape(self.host[s][0].shape))
+        self.host[s][1].copy_(torch.as_tensor(right_u8).reshape(self.host[s][1].shape))
         with torch.cuda.stream(self.copy_stream):
             if self._head >= self.depth:
-                self.copy_stream.wait_event(self.consumed[s])        # the slot's previous pair has been normalised
+                self.copy_stream.wait_event(self.consumed[s])        # the slot's previous batch has been normalised
             self.dev[s].copy_(self.host[s], non_blocking=True)
             self.ready[s].record(self.copy_stream)
         self._head += 1
 
-    def next(self) -> Tuple[torch.Tensor, torch.Tensor]:
+    def next(self, dst: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
         if self._tail >= self._head:
             raise RuntimeError("InputPipeline: nothing submitted")
         s = self._tail % self.depth
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.ready[s])
+        outs = dst if dst is not None else (self.out[s][0], self.out[s][1])
         for k in range(2):
-            self.ops.normalize_pad_u8(self.dev[s][k], self.crop[0], self.crop[1], out=self.out[s][k], sums=self.sums[s][k])
+            for b in range(self.batch):
+                self.ops.normalize_pad_u8(self.dev[s][k][b], self.crop[0], self.crop[1], out=outs[k][b],
+                                          sums=self.sums[s][k][b])
         self.consumed[s].record(cur)
         self._tail += 1
-        return self.out[s][0:1], self.out[s][1:2]
+        return outs[0], outs[1]
 
 
 # ---------------------------------------------------------------------------------------------------------

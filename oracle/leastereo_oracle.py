@@ -223,7 +223,7 @@ def disp_head(mat: torch.Tensor, maxdisp: int) -> torch.Tensor:
     x = F.interpolate(mat, [maxdisp, mat.shape[3] * 3, mat.shape[4] * 3], mode="trilinear", align_corners=False)
     x = torch.squeeze(x, 1)
     p = F.softmin(x, dim=1)
-    d = torch.arange(0, maxdisp, dtype=torch.float32).reshape(1, maxdisp, 1, 1)
+    d = torch.arange(0, maxdisp, dtype=torch.float32, device=mat.device).reshape(1, maxdisp, 1, 1)
     return torch.sum(p * d, 1)
 
 
@@ -300,7 +300,8 @@ def leastereo_forward(sd, left: torch.Tensor, right: torch.Tensor, maxdisp: int,
     with torch.no_grad():
         fx = feature_forward(sd, left, arch, training=training, batch_stats=batch_stats)
         fy = feature_forward(sd, right, arch, training=training, batch_stats=batch_stats)
-        cost = cost_volume(fx, fy, maxdisp)
+        # on a CUDA device (bench.py's gpu_baseline leg) the slice-assignment statement of LEAStereo.py:34-48 is used
+        cost = cost_volume(fx, fy, maxdisp) if not fx.is_cuda else cost_volume_torch(fx, fy, maxdisp)
         mat = matching_forward(sd, cost, arch, training=training, batch_stats=batch_stats)
         disp = disp_head(mat, maxdisp)
     if stages is not None:

@@ -170,6 +170,19 @@ def check_disp_head(ops, device):
     want = O.disp_head(mat.cpu(), 24)
     assert torch.isfinite(got).all()
     assert float(((got - want).abs() <= 0.1).float().mean()) >= 0.99
+    # un-normalised logits with a trend along disparity (what random-init weights produce, SURVEY App. C "raw" regime):
+    # the minimum sits at an end of the range, where outputs 0/1 (and maxdisp-2/-1) read the same sample and the
+    # reference's fp32 interpolation weights (l1 = 1.49e-8 at output 1) break the tie - the head must use those weights
+    for sign, seed in ((1.0, 21), (-1.0, 22)):
+        D3, H3, W3 = 16, 6, 40
+        ramp = torch.arange(D3, dtype=torch.float32).view(1, 1, D3, 1, 1) * 2.0e7 * sign
+        mat = (ramp + _rand((2, 1, D3, H3, W3), seed, "cpu", scale=3.0e6)).to(device)
+        got = ops.disp_head(mat, 3 * D3).cpu()
+        want = O.disp_head(mat.cpu(), 3 * D3)
+        diff = (got - want).abs()
+        assert float((diff <= 0.1).float().mean()) >= 0.999 and float(diff.mean()) <= 0.01, (sign, float(diff.max()))
+        if sign > 0:        # the tie is really broken by the weight bits: neither 0.5 (exact thirds) nor 0 or 1
+            assert 0.05 < float(want.median()) < 0.495, float(want.median())
 
 
 def check_head_taps(ops, device):

@@ -3,7 +3,7 @@ kernels, against the oracle's autograd gradients."""
 import pytest
 import torch
 
-from test_training_emu import check_train_step, _rel
+from test_training_emu import check_backward_kernels, check_train_step, _rel
 from oracle import leastereo_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -16,6 +16,11 @@ def ops():
     g.build()
     from leastereo_b200.kernels import get_ops
     return get_ops()
+
+
+def test_backward_kernels_individually(ops):
+    """lea_trilinear_ac_bwd, lea_cost_volume_bwd, lea_disp_head_bwd on the GPU against autograd."""
+    check_backward_kernels(ops, DEV)
 
 
 def test_train_step_fp32_simt(ops):

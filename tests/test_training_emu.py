@@ -96,27 +96,31 @@ def test_train_step_skip_connect_genotype(emu_ops):
 
 
 def test_backward_kernels_individually(emu_ops):
-    """Trilinear backward and cost-volume backward against autograd on random data."""
+    check_backward_kernels(emu_ops, DEV)
+
+
+def check_backward_kernels(ops, DEV):
+    """Trilinear backward, cost-volume backward and disparity-head backward against autograd on random data (run on the
+    CPU emulation here and on the GPU by tests/test_gpu_training.py)."""
     import torch.nn.functional as F
     from leastereo_b200.kernels import PlanesVol
-    ops = emu_ops
     for src_sp, dst_sp in [((4, 3, 6), (8, 6, 12)), ((8, 6, 12), (4, 3, 6)), ((3, 5, 4), (5, 9, 7)), ((2, 2, 2), (1, 1, 1))]:
         x = torch.randn(1, 8, *src_sp, requires_grad=True)
         y = F.interpolate(x, dst_sp, mode="trilinear", align_corners=True)
         gy = torch.randn_like(y)
         y.backward(gy)
-        ddst = ops.pack(gy, 3)
+        ddst = ops.pack(gy.to(DEV), 3)
         dsrc = PlanesVol.empty(1, 8, 3, *src_sp, DEV)
         dsrc.t.zero_()
         ops.trilinear_ac_bwd(ddst, 0, dsrc, 0, 8)
-        assert _rel(ops.unpack(dsrc), x.grad) <= 1e-5, (src_sp, dst_sp)
+        assert _rel(ops.unpack(dsrc).cpu(), x.grad) <= 1e-5, (src_sp, dst_sp)
     fx = torch.randn(2, 8, 5, 12, requires_grad=True)
     fy = torch.randn(2, 8, 5, 12, requires_grad=True)
     cost = O.cost_volume_torch(fx, fy, 15)
     gc = torch.randn_like(cost)
     cost.backward(gc)
-    dx, dy = ops.cost_volume_bwd(ops.pack(gc, 3), 8)
-    assert _rel(dx, fx.grad) <= 1e-5 and _rel(dy, fy.grad) <= 1e-5
+    dx, dy = ops.cost_volume_bwd(ops.pack(gc.to(DEV), 3), 8)
+    assert _rel(dx.cpu(), fx.grad) <= 1e-5 and _rel(dy.cpu(), fy.grad) <= 1e-5
     # disparity head backward
     mat = (torch.randn(1, 1, 8, 5, 7) * 2).requires_grad_(True)
     for maxdisp in (24, 25):
@@ -124,5 +128,5 @@ def test_backward_kernels_individually(emu_ops):
         d = O.disp_head(mat, maxdisp)
         go = torch.randn_like(d)
         d.backward(go)
-        dm = ops.disp_head_bwd(mat.detach(), go, maxdisp)
-        assert _rel(dm, mat.grad[:, 0]) <= 2e-4, maxdisp
+        dm = ops.disp_head_bwd(mat.detach().to(DEV), go.to(DEV), maxdisp)
+        assert _rel(dm.cpu(), mat.grad[:, 0]) <= 2e-4, maxdisp
