@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LEA_ABI_VERSION 1
+#define LEA_ABI_VERSION 2
 
 typedef struct lea_vol {
     void*   data;          /* bf16 planes volume, 16-byte aligned                                   */
@@ -106,11 +106,8 @@ typedef struct lea_tc_opts {
     int32_t acc_sets;      /* 0 = auto, 1 or 2 TMEM accumulator sets (2 = epilogue overlaps the next item's MMAs) */
     const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
     int32_t resident_weights;  /* 0 = auto (all channel groups' weights stay in shared memory when they fit), 2 = never */
-    int32_t early_drain;       /* k = 3: 1 = one accumulator set, depths go to the epilogue one by one while the last channel
-                                  group accumulates; 0 = default schedule (measured faster, see lea_tc_conv.cu) */
     int32_t cv_skip;           /* fused_cv only: 1 = leave the voxels lea_stem0_assemble writes (collapsed stem0) untouched */
-    int32_t debug;             /* development switches of the rolling kernel's epilogue; 0 in production */
-    int32_t rolling;           /* k = 3: 1 = rolling accumulator ring (needs <= 85 TMEM columns per depth), 0 = chunked kernel (default) */
+    int32_t debug;             /* timing-ablation switches, only in -DLEA_TC_ABLATION builds; 0 in production */
     int32_t depth_chunk;       /* 0 = auto, n = depth slices per work item, clamped to what the schedule allows (test knob) */
     int32_t tile_w_log2;       /* 1x1x1 convs only: 0 = auto, 3..7 = tile of 2^n voxels along w by 128/2^n along h */
 } lea_tc_opts;

@@ -44,13 +44,11 @@ namespace {
 // sub-partition (16 K registers), capping the kernel at 168 registers per thread.
 __host__ __device__ constexpr int epi_warps(int planes) { return planes == 3 ? 4 : 4; }
 __host__ __device__ constexpr int tc_threads(int planes) { return 64 + 32 * epi_warps(planes); }
-constexpr int kThreads = 192;       // rolling kernel: 4 epilogue warps
 constexpr int kMaxTerms = 6;
 constexpr int kMaxStages = 24;   // deep enough that 8 KB 1x1x1 stages keep ~1.5 us of HBM latency covered
 constexpr int kSmemBudget = 227 * 1024;
-constexpr int kMaxRing = 32;       // rolling schedule: depth accumulators in flight (TMEM ring entries)
 constexpr int kHeaderBytes = 2048;
-static_assert(8 * (2 * kMaxStages + 8 + 2 * kMaxRing) <= 1024, "barriers must fit below the BN vectors at byte 1024");
+static_assert(8 * (2 * kMaxStages + 8) <= 1024, "barriers must fit below the BN vectors at byte 1024");
 #ifdef LEA_TC_SOFT_TIMEOUT
 constexpr unsigned long long kWaitTimeoutCycles = 100000000ull;
 #else
@@ -81,11 +79,9 @@ struct TcParams {
     int slab_vox, pitch_vox, blk_bytes, stage_bytes, stage_stride;   // stride = bytes rounded up to 128 (TMA alignment)
     int nstages, nwbuf;
     int tw_log2;              // tile = (1 << tw_log2) voxels along w x (128 >> tw_log2) along h  (3 for k = 3)
-    int early;                // one accumulator set, depths handed to the epilogue one by one while the last channel group runs
     int cv_skip;              // collapsed stem0: skip the voxels lea_stem0_assemble writes (lea_cv_interior)
     int dbg;                  // development switches (bit 0: epilogue skips its stores, bit 1: skips the TMEM loads, bit 2: skips the
                               // residual reads, bit 3: the issuer issues no MMAs) - timing ablations only, results are wrong
-    int roll, R;              // rolling schedule (see lea_conv_tc_roll_kernel): R home accumulator blocks + 2 alias blocks
     int wres;                 // 1 = the weight parts of ALL channel groups stay resident in shared memory (loaded once per CTA)
     int fused_cv, ncg_half;   // fused cost volume: channel groups [0,ncg_half) come from x, the rest from y(w-d)
     const CUtensorMap* cvmaps; // [2*D]: x maps for d = 0..D-1, then y maps
@@ -380,7 +376,6 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint64_t* wempty = wfull + 2;                   // [2]
     uint64_t* accfull = wempty + 2;                 // [2]
     uint64_t* accempty = accfull + 2;               // [2]
-    uint64_t* dready = accempty + 2;                // [kMaxRing] early drain: depth slot j of the item is final
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1536);
     float* s_scale = reinterpret_cast<float*>(smem + 1024);     // [64]  (barriers occupy the first KB)
     float* s_shift = s_scale + 64;                              // [64]
@@ -401,7 +396,6 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1);
             mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 32 * epi_warps(PL));
         }
-        for (int i = 0; i < kMaxRing; ++i) mbar_init(smem_u32(dready + i), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -559,23 +553,13 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     }
                     tc_commit_if(elected, smem_u32(empty + stage));
                     if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
-                    if (p.early && cg + 1 == p.ncg) {
-                        // last channel group: slab d_in was the last contribution to depth d_in-1 (and to its own depth
-                        // when it is the final slab of a chunk that ends with the volume) - hand them to the epilogue
-                        if (d_in - 1 >= g.d0) tc_commit_if(elected, smem_u32(dready + (d_in - 1 - g.d0)));
-                        if (d_in == g.dhi && g.dhi == g.d_hi - 1) tc_commit_if(elected, smem_u32(dready + (g.d_hi - 1 - g.d0)));
-                    }
                 }
                 if (!p.wres) {
                     tc_commit_if(elected, smem_u32(wempty + wb));
                     if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
                 }
             }
-            if (p.early) {          // unused depth slots of a short chunk: keep every slot's barrier in step with the items
-                for (int j = g.d_hi - g.d0; j < p.Dc; ++j) tc_commit_if(elected, smem_u32(dready + j));
-            } else {
-                tc_commit_if(elected, smem_u32(accfull + set));
-            }
+            tc_commit_if(elected, smem_u32(accfull + set));
         }
     } else {
         // ================= epilogue warps 2..5 =================
@@ -599,8 +583,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const int h = g.h0 + lh, w = g.w0 + lw;
             const bool valid = (h < p.H) && (w < p.W);
             const int nd = g.d_hi - g.d0;
-            bool waited = p.early != 0;
-            int ready_upto = 0;                      // early drain: depth slots [0, ready_upto) are known to be final
+            bool waited = false;
             for (int j0 = ((warp - 2) >> 2) * kJB; j0 < nd; j0 += (epi_warps(PL) / 4) * kJB) {
                 for (int c16 = 0; c16 < p.c_out; c16 += 16) {
                     const bool two = (c16 + 8 < p.c_out);
@@ -621,7 +604,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         tc_fence_after();
                         waited = true;
                     }
-                    if (E8 != 0 && !two && !p.early) {
+                    if (E8 != 0 && !two) {
                         // The group holds ONE 8-channel block (8-channel convs, the tail of 24): read only its 8 columns,
                         // and the whole depth batch with one tcgen05.wait::ld so that the TMEM latencies overlap.
                         // Measured: the epilogue-bound 8-channel convs 640 -> 456 us.  Compiled only into the instances
@@ -634,7 +617,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                                         s_scale, s_shift, rq);
                         continue;
                     }
-                    if (E8 != 1 && two && !p.early) {
+                    if (E8 != 1 && two) {
                         // full 16-channel group: 2 depths per tcgen05.wait::ld.  Measured (KITTI, 4 pairs): 16-channel
                         // cell ops 125 -> 106 us, batched ones 240 -> 211, conv1/conv2 -3 %; 199.8 -> 209.2 pairs/s.
                         const bool two_regions = (p.ngroups == 2) || p.fold;
@@ -649,11 +632,6 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     for (int jj = 0; jj < kJB; ++jj) {
                         if (j0 + jj >= nd) break;
                         const int d = g.d0 + j0 + jj;
-                        if (p.early && j0 + jj >= ready_upto) {
-                            mbar_wait(smem_u32(dready + j0 + jj), aphase, 303);
-                            tc_fence_after();
-                            ready_upto = j0 + jj + 1;
-                        }
                         // depth d of region r: column set*ngroups*Dc*NP + r*Dc*NP + (d_hi-1-d)*NP
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
@@ -714,367 +692,6 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Rolling schedule (k = 3).  The chunked kernel above keeps the accumulators of a whole depth chunk in TMEM, so a
-// chunk is at most 512 / (columns per depth) slices long and pays two halo slabs - full-price MMAs that feed one
-// or two output depths instead of three - per chunk (x1.25 .. x1.5 tensor time), and its epilogue only overlaps
-// the next item with half of TMEM.  Here a work item is a depth range of ANY length.  The loops are slab-major
-// (for d_in: for channel group: 27 taps), so output depth d is complete as soon as slab d+1 has been issued, is
-// drained by the epilogue while the issuer continues with the next slabs, and its accumulator is reused R slabs
-// later: TMEM is a ring of R "home" blocks.  One tcgen05.mma still spans the three kd taps, i.e. three
-// ADJACENT blocks (depths d_in+1, d_in, d_in-1 in that order); at the ring's wrap this is kept contiguous by two
-// alias blocks: block 0 takes the part that belongs to home block R, block R+1 the part of home block 1, and the
-// epilogue adds an alias to its home.  With h(s) = home of slab s's centre depth (R, R-1, .., 1, R, ..):
-//     blocks h-1, h, h+1  <-  depths s+1, s, s-1;   h == 1: block 0 is the alias of depth s+1 (home R),
-//                                                    h == R: block R+1 is the alias of depth s-1 (home 1).
-// First writes (accumulate = 0): the kd=0 part always; all three parts when h == R (depth s's earlier part went to
-// alias 0, depth s-1's part goes to alias R+1); depth 0 at slab 0.  No extra MMAs, no halo except 2 slabs per ITEM.
-// ---------------------------------------------------------------------------------------------------------
-template <int NTERM, int PL>
-__global__ void __launch_bounds__(kThreads, 1)
-lea_conv_tc_roll_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
-    extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* full = bars;                          // [kMaxStages]
-    uint64_t* empty = bars + kMaxStages;            // [kMaxStages]
-    uint64_t* wfull = bars + 2 * kMaxStages;        // [2]
-    uint64_t* wempty = wfull + 2;                   // [2]
-    uint64_t* dfull = wempty + 6;                   // [kMaxRing]  depth complete (tcgen05.commit)
-    uint64_t* dempty = dfull + kMaxRing;            // [kMaxRing]  depth drained by the 128 epilogue threads
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1536);
-    float* s_scale = reinterpret_cast<float*>(smem + 1024);
-    float* s_shift = s_scale + 64;
-    uint8_t* wbuf = smem + kHeaderBytes;
-    const int wbuf_stride = (p.wpart_bytes + 127) & ~127;
-    uint8_t* stages = wbuf + (size_t)p.nwbuf * wbuf_stride;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int R = p.R;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1); }
-        for (int i = 0; i < R; ++i) { mbar_init(smem_u32(dfull + i), 1); mbar_init(smem_u32(dempty + i), 128); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (threadIdx.x >= 64 && threadIdx.x < 128) {
-        const int n = threadIdx.x - 64;
-        s_scale[n] = (p.bn_scale && n < p.c_out) ? __ldg(p.bn_scale + n) : 1.0f;
-        s_shift[n] = (p.bn_shift && n < p.c_out) ? __ldg(p.bn_shift + n) : 0.0f;
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                     ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    constexpr int kHalo = 1;
-    constexpr int kPitch = LEA_TC_TW + 2;
-
-    if (warp == 0) {
-        // ================= TMA producer: slab-major order =================
-        if (lane == 0) {
-            int stage = 0, sphase = 0, wb = 0, wphase = 0;
-            if (p.wres) {
-                mbar_arrive_expect_tx(smem_u32(wfull), (uint32_t)(p.ncg * p.wpart_bytes));
-                for (int cg = 0; cg < p.ncg; ++cg)
-                    bulk_load(smem_u32(wbuf + (size_t)cg * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
-                              (uint32_t)p.wpart_bytes, smem_u32(wfull));
-            }
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const ItemGeom g = decode_item(p, item);
-                const int gbase = g.b * p.g0_stride_b + p.g0_first;
-                for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
-                    for (int cg = 0; cg < p.ncg; ++cg) {
-                        if (!p.wres) {
-                            mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101);
-                            mbar_arrive_expect_tx(smem_u32(wfull + wb), (uint32_t)p.wpart_bytes);
-                            bulk_load(smem_u32(wbuf + (size_t)wb * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
-                                      (uint32_t)p.wpart_bytes, smem_u32(wfull + wb));
-                            if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
-                        }
-                        mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102);
-                        mbar_arrive_expect_tx(smem_u32(full + stage), (uint32_t)p.stage_bytes);
-                        if (p.fused_cv) {
-                            const bool left = cg < p.ncg_half;
-                            const CUtensorMap* m = p.cvmaps + (left ? 0 : p.D) + d_in;
-                            tma_load_3d(smem_u32(stages + (size_t)stage * p.stage_stride), m, smem_u32(full + stage),
-                                        (g.w0 - kHalo - d_in) * 8, g.h0 - kHalo,
-                                        gbase + (left ? cg : cg - p.ncg_half) * p.blocks_per_cg);
-                        } else {
-                            tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_stride), &tmap, smem_u32(full + stage),
-                                        (g.w0 - kHalo) * 8, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
-                        }
-                        if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        const uint32_t elected = elect_one();
-        const int nblk = R + 2;
-        uint32_t a_term16[NTERM], a_lbo_field[NTERM], b_term16[NTERM], reg_col[NTERM];
-        bool t_first[NTERM];
-#pragma unroll
-        for (int t = 0; t < NTERM; ++t) {
-            a_term16[t] = (uint32_t)(p.term_aoff[t] * p.blk_bytes) >> 4;
-            a_lbo_field[t] = ((uint32_t)(p.term_lbo_blocks[t] * p.blk_bytes) >> 4) << 16;
-            b_term16[t] = (uint32_t)(p.term_btile[t] * p.btile_bytes) >> 4;
-            reg_col[t] = (uint32_t)(p.term_region[t] * nblk * p.NP);
-            t_first[t] = p.term_first[t] != 0;
-        }
-        const uint32_t idesc1 = make_idesc(p.NP), idesc2 = make_idesc(2 * p.NP), idesc3 = make_idesc(3 * p.NP);
-        const uint32_t a_hi = (uint32_t)kPitch | (1u << 14);
-        const uint32_t b_hi = 8u | (1u << 14);
-        const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;
-        const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;
-        int stage = 0, sphase = 0, wb = 0, wphase = 0;
-        // tcgen05.mma issue is synchronous with the tensor pipe (DESIGN.md 4.1 law ii): every instruction this warp
-        // executes between the last MMA of a slab and the first MMA of the next one is a pipe bubble.  All per-slab
-        // bookkeeping - kd range, ring entry and block, first-write count, the barriers to acquire / commit, and at an
-        // item boundary the decode of the next item - is therefore computed for the NEXT slab in the shadow of the
-        // current slab's MMAs (the ~20 spare cycles between two MMA issues), and the barriers the next slab needs are
-        // probed there with mbarrier.test_wait.
-        // Ring: depth number q = R + (depths of earlier items) + (d - d0) lives in entry q % R, generation q / R - 1;
-        // (e, par) = (q % R, (q / R) & 1), advanced without divisions.
-        struct Slab {
-            int valid, item, d_in, e, par, e0, par0;
-            ItemGeom g;
-            int nkd, nfresh;
-            uint32_t col0, brow16, idesc_all, open1, open1_par, open2, open2_par, done1, done2;
-        };
-        const uint32_t dempty0 = smem_u32(dempty), dfull0 = smem_u32(dfull);
-        auto derive = [&](Slab& c) {
-            const ItemGeom& g = c.g;
-            const int d_in = c.d_in, e = c.e, par = c.par;
-            const int kd_a = (d_in + 1 <= g.d_hi - 1) ? 0 : ((d_in <= g.d_hi - 1) ? 1 : 2);
-            const int kd_b = (d_in - 1 >= g.d0) ? 2 : ((d_in >= g.d0) ? 1 : 0);
-            c.nkd = kd_b - kd_a + 1;
-            const int h = R - e;
-            const int e_up = (e + 1 == R) ? 0 : e + 1, par_up = (e + 1 == R) ? par ^ 1 : par;   // depth d_in+1
-            const int e_dn = (e == 0) ? R - 1 : e - 1;                                           // depth d_in-1
-            // first writes (accumulate = 0) are a prefix of [kd_a, kd_b]: kd 0 always; everything when h == R; depth 0
-            const bool fr1 = (h == R) || (d_in == 0), fr2 = (h == R);
-            int nf;
-            if (kd_a == 0)      nf = 1 + ((kd_b >= 1 && fr1) ? 1 + ((kd_b >= 2 && fr2) ? 1 : 0) : 0);
-            else if (kd_a == 1) nf = fr1 ? 1 + ((kd_b >= 2 && fr2) ? 1 : 0) : 0;
-            else                nf = fr2 ? 1 : 0;
-            c.nfresh = nf;
-            c.col0 = (uint32_t)((h - 1 + kd_a) * p.NP);
-            c.brow16 = (uint32_t)(kd_a * p.NP);
-            c.idesc_all = c.nkd == 3 ? idesc3 : (c.nkd == 2 ? idesc2 : idesc1);
-            c.open1 = (kd_a == 0) ? dempty0 + 8u * (uint32_t)e_up : 0u;            c.open1_par = (uint32_t)par_up;
-            c.open2 = (d_in == 0 && kd_a <= 1 && kd_b >= 1) ? dempty0 + 8u * (uint32_t)e : 0u;   c.open2_par = (uint32_t)par;
-            c.done1 = (d_in - 1 >= g.d0) ? dfull0 + 8u * (uint32_t)e_dn : 0u;
-            c.done2 = (d_in == p.D - 1 && d_in < g.d_hi) ? dfull0 + 8u * (uint32_t)e : 0u;
-        };
-        auto first_of_item = [&](Slab& c, int item, int e0, int par0) {
-            c.item = item; c.e0 = e0; c.par0 = par0;
-            c.valid = item < p.total_items;
-            if (!c.valid) return;
-            c.g = decode_item(p, item);
-            c.d_in = c.g.dlo;
-            c.e = e0; c.par = par0;
-            if (c.g.dlo < c.g.d0) { if (c.e == 0) { c.e = R - 1; c.par ^= 1; } else --c.e; }   // leading halo slab
-            derive(c);
-        };
-        auto next_slab = [&](const Slab& c, Slab& n) {
-            if (c.d_in < c.g.dhi) {
-                n = c;
-                n.d_in = c.d_in + 1;
-                if (c.e + 1 == R) { n.e = 0; n.par = c.par ^ 1; } else n.e = c.e + 1;
-                derive(n);
-            } else {
-                int e0 = c.e0 + (c.g.d_hi - c.g.d0), par0 = c.par0;
-                while (e0 >= R) { e0 -= R; par0 ^= 1; }
-                first_of_item(n, c.item + (int)gridDim.x, e0, par0);
-            }
-        };
-        uint32_t probed = 0, opened = 0;
-        if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
-        Slab cur, nxt;
-        first_of_item(cur, (int)blockIdx.x, 0, 1);
-        nxt.valid = 0;
-        while (cur.valid) {
-            // acquire the ring entries of the depths this slab opens (drained one generation ago)
-            if (!opened) {
-                if (cur.open1) mbar_wait(cur.open1, cur.open1_par, 204);
-                if (cur.open2) mbar_wait(cur.open2, cur.open2_par, 205);
-            }
-            const uint32_t col0 = cur.col0, brow16 = cur.brow16, idesc_all = cur.idesc_all;
-            const int nkd = cur.nkd;
-            for (int cg = 0; cg < p.ncg; ++cg) {
-                if (!p.wres) mbar_wait(smem_u32(wfull + wb), wphase, 202);
-                const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
-                if (!probed) mbar_wait(smem_u32(full + stage), sphase, 203);
-                tc_fence_after();
-                const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
-                const int nf = (cg == 0) ? cur.nfresh : 0;
-                const uint32_t idesc_fresh = nf == 3 ? idesc3 : (nf == 2 ? idesc2 : idesc1);
-                const int nrest = nkd - nf;
-                const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
-                const bool last_cg = (cg + 1 == p.ncg);
-#pragma unroll
-                for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
-                        const uint32_t b_tap = w16 + (uint32_t)(kh * 3 + kw) * tap16 + brow16;
-#pragma unroll
-                        for (int t = 0; t < NTERM; ++t) {
-                            const uint32_t a_lo = (a_tap + a_term16[t]) | a_lbo_field[t];
-                            const uint32_t b_lo = b_tap + b_term16[t];
-                            const uint32_t dcol = tmem_base + reg_col[t] + col0;
-                            if (kh == 0 && kw == 0 && t_first[t] && nf > 0) {
-                                tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
-                                if (nrest > 0)
-                                    tc_mma_issue(elected, dcol + (uint32_t)(nf * p.NP), a_lo, a_hi,
-                                                 b_lo + (uint32_t)(nf * p.NP), b_hi, idesc_rest, 1u);
-                            } else {
-                                tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_all, 1u);
-                            }
-                        }
-                        // ---- work done in the MMA shadow ----
-                        if (kh == 0 && kw == 0) {
-                            const bool wrap = (stage + 1 == p.nstages);
-                            probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
-                        }
-                        if (kh == 1 && kw == 0 && last_cg) next_slab(cur, nxt);
-                        if (kh == 2 && kw == 1 && last_cg) {
-                            opened = 0;
-                            if (nxt.valid) {
-                                uint32_t ok = 1;
-                                if (nxt.open1) ok &= mbar_test(nxt.open1, nxt.open1_par);
-                                if (nxt.open2) ok &= mbar_test(nxt.open2, nxt.open2_par);
-                                opened = ok;
-                            }
-                        }
-                    }
-                }
-                tc_commit_if(elected, smem_u32(empty + stage));
-                if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
-                if (!p.wres) {
-                    tc_commit_if(elected, smem_u32(wempty + wb));
-                    if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
-                }
-            }
-            // depths completed by this slab
-            if (cur.done1) tc_commit_if(elected, cur.done1);
-            if (cur.done2) tc_commit_if(elected, cur.done2);
-            cur = nxt;
-        }
-    } else if (warp < 6) {
-        // ================= epilogue warps 2..5: one depth at a time, as they complete =================
-        const int qd = warp & 3;
-        const int m = qd * 32 + lane;
-        const int lh = m >> 3, lw = m & 7;
-        const int64_t sp = (int64_t)p.D * p.H * p.W;
-        const int nblk = R + 2;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(qd * 32) << 16);
-        const uint32_t region1 = (uint32_t)(p.fold ? (p.NP >> 1) : nblk * p.NP);
-        const bool two_regions = (p.ngroups == 2) || p.fold;
-        int e = 0, par = 1;                            // entry / parity of the next depth (see the issuer)
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const ItemGeom g = decode_item(p, item);
-            const int h_out = g.h0 + lh, w_out = g.w0 + lw;
-            const bool valid = (h_out < p.H) && (w_out < p.W);
-            for (int d = g.d0; d < g.d_hi; ++d) {
-                const int hb = R - e;
-                // residual operands do not depend on the MMAs: fetch them before waiting for the depth
-                uint4 rq[4][2][PL];
-                if (p.has_res && valid) {
-#pragma unroll
-                    for (int ci = 0; ci < 4; ++ci) {
-                        const int c16 = ci * 16;
-                        if (c16 < p.c_out) {
-                            ep_load_raw8<PL>(p.res, g.b, (p.res_c0 + c16) >> 3, d, h_out, w_out, rq[ci][0]);
-                            if (c16 + 8 < p.c_out)
-                                ep_load_raw8<PL>(p.res, g.b, ((p.res_c0 + c16) >> 3) + 1, d, h_out, w_out, rq[ci][1]);
-                        }
-                    }
-                }
-                mbar_wait(smem_u32(dfull + e), par ^ 1, 301);
-                tc_fence_after();
-                const bool alias_lo = (hb == R) && (d >= 1);           // part written into block 0 by slab d-1
-                const bool alias_hi = (hb == 1) && (d <= p.D - 2);     // part written into block R+1 by slab d+1
-                const uint32_t home = lane_base + (uint32_t)(hb * p.NP);
-                const uint32_t alias = lane_base + (uint32_t)((alias_lo ? 0 : R + 1) * p.NP);
-                const bool has_alias = alias_lo || alias_hi;
-#pragma unroll
-                for (int ci = 0; ci < 4; ++ci) {
-                    const int c16 = ci * 16;
-                    if (c16 >= p.c_out) break;
-                    const bool two = (c16 + 8 < p.c_out);
-                    float acc[16];
-                    {
-                        uint32_t ra[16], rb[16], rc[16], rd[16];
-                        if (p.dbg & 2) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) { ra[i] = 0; rb[i] = 0; rc[i] = 0; rd[i] = 0; }
-                        } else {
-                        tc_ld16_nowait(home + (uint32_t)c16, ra);
-                        if (two_regions) tc_ld16_nowait(home + region1 + (uint32_t)c16, rb);
-                        }
-                        if (has_alias && !(p.dbg & 2)) {
-                            tc_ld16_nowait(alias + (uint32_t)c16, rc);
-                            if (two_regions) tc_ld16_nowait(alias + region1 + (uint32_t)c16, rd);
-                        }
-                        tc_wait_ld();
-                        tc_touch16(ra);
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
-                        if (has_alias) {
-                            tc_touch16(rc);
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(rc[i]);
-                        }
-                        if (two_regions) {
-                            tc_touch16(rb);
-                            if (has_alias) {
-                                tc_touch16(rd);
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(rb[i]) + __uint_as_float(rd[i]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) acc[i] += __uint_as_float(rb[i]);
-                            }
-                        }
-                    }
-                    if (!valid || (p.dbg & 1)) continue;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
-                        if (p.relu) v = fmaxf(v, 0.0f);
-                        acc[i] = v;
-                    }
-                    if (p.dst_f32) {
-                        float* o = p.dst_f32 + (int64_t)g.b * p.c_out * sp + ((int64_t)d * p.H + h_out) * p.W + w_out;
-                        for (int n = 0; n < 16 && c16 + n < p.c_out; ++n) o[(c16 + n) * sp] = acc[n];
-                    } else {
-                        if (p.has_res) {
-                            ep_add_raw8<PL>(rq[ci][0], acc);
-                            if (two) ep_add_raw8<PL>(rq[ci][1], acc + 8);
-                        }
-                        ep_store8<PL>(p.dst, g.b, (p.dst_c0 + c16) >> 3, d, h_out, w_out, acc);
-                        if (two) ep_store8<PL>(p.dst, g.b, ((p.dst_c0 + c16) >> 3) + 1, d, h_out, w_out, acc + 8);
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(smem_u32(dempty + e));
-                if (++e == R) { e = 0; par ^= 1; }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-    }
-}
-
 typedef void (*TcKernelFn)(const CUtensorMap, const TcParams);
 template <int KS, int E8>
 static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
@@ -1087,17 +704,6 @@ static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
     if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 3, E8>;
     if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3, E8>;      // 8-channel layout, 3 planes
     return lea_conv_tc_kernel<KS, 6, 3, E8>;                       // bf16x6
-}
-static TcKernelFn tc_roll_kernel_for(int nterm, int planes) {
-    if (planes == 1) return lea_conv_tc_roll_kernel<1, 1>;
-    if (planes == 2) {
-        if (nterm == 1) return lea_conv_tc_roll_kernel<1, 2>;
-        if (nterm == 2) return lea_conv_tc_roll_kernel<2, 2>;
-        return lea_conv_tc_roll_kernel<3, 2>;
-    }
-    if (nterm == 1) return lea_conv_tc_roll_kernel<1, 3>;
-    if (nterm == 3) return lea_conv_tc_roll_kernel<3, 3>;
-    return lea_conv_tc_roll_kernel<6, 3>;
 }
 static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, int e8) {
     if (e8 == 1) return ks == 3 ? tc_kernel_for_ks<3, 1>(nterm, planes) : tc_kernel_for_ks<1, 1>(nterm, planes);
@@ -1324,13 +930,11 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // depth per item (more halo slabs); when that leaves fewer than 4 depths a measured cycle model decides: a slab
     // costs M = groups * taps * terms * max(64, N/2) cycles of tensor pipe, the epilogue E ~ 650 cycles per 16 output
     // channels and depth.
-    // "Early drain" (opts->early_drain == 1, k = 3): one set with twice the depth, the depths handed to the epilogue one
-    // by one while the LAST channel group is still being accumulated (depth d is final once slab d+1 of that group is
-    // issued).  Measured: it saves 17 % of stem1's MMAs and gains nothing (521 vs 515-523 us; 8-ch, batched and 32-ch
-    // level-2 convs lose 3-12 %) - like the rolling kernel, an epilogue interleaved with the MMAs of its own item costs
-    // about what the saved halo is worth (cause not identified; concurrent tcgen05.ld alone is free, see
-    // lea_tc_microbench), while the default two-set schedule runs at exactly #MMAs x 64 cycles.
-    const bool want_early = (p.ks == 3) && opts && opts->early_drain == 1;
+    // (Round 1 also carried two schedules that drain depths while their item is still accumulating - a rolling TMEM
+    // ring and an "early drain" single set.  Both saved halo slabs and measured slower; removed in round 2.
+    // Round 2 measured a shared-memory-staged TMA-store epilogue - cp.async.bulk.tensor stores of each warp's 32-voxel box
+    // per depth and 8-channel block, then one proxy fence per 4 boxes: the epilogue-bound convs lose 12-20 % against the
+    // per-thread 16-byte stores below (8 -> 8 at 64x128x416, 4 pairs: 450 us -> 565 / 517 us); not kept.)
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
     if (p.nsets == 1 && 512 / (2 * accw) >= 2) {
         const int halo = (p.ks == 3) ? 2 : 0;
@@ -1343,7 +947,6 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         const double t2 = (me > ee ? me : ee) / d2;
         if (t2 < t1) p.nsets = 2;
     }
-    if (want_early) p.nsets = 1;
     if (opts && (opts->acc_sets == 1 || opts->acc_sets == 2)) p.nsets = opts->acc_sets;
     // tile shape: 8 x 16 for k = 3 (the tap windows need the 8-row core-matrix groups to be rows of the slab); a
     // 1x1x1 conv has no halo, its slab is 128 consecutive rows whatever the shape, so it takes the widest tile the
@@ -1366,22 +969,10 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.stage_stride = (p.stage_bytes + 127) & ~127;
     p.tiles_w = (p.W + tile_w - 1) / tile_w;
     p.tiles_h = (p.H + tile_h - 1) / tile_h;
-    // rolling schedule (k = 3): ring of R home blocks + 2 alias blocks; needs some slack between the issuer and the
-    // epilogue (R >= 4), i.e. at most 85 accumulator columns per depth
-    p.R = 512 / accw - 2;
-    if (p.R > kMaxRing) p.R = kMaxRing;
-    // Opt-in (opts->rolling == 1).  Measured on B200 (tools/roll_perf.py, KITTI shapes, 4 pairs): the rolling kernel
-    // issues 28 % fewer MMAs for stem1 but its per-slab time is ~35 % longer: stem1 526 vs 516 us, 16-ch ops 38 vs 35,
-    // 8-ch ops 205 vs 158, 32-ch level-2 ops 14.5 vs 12.9.  Ablations: epilogue doing no work -12 %, no ring barriers
-    // a further -7 %; moving all per-slab bookkeeping into the MMA shadow (this version) changed nothing, so the loss
-    // is not issuer arithmetic - the suspects left are the per-slab tcgen05.commit and TMEM reads next to the columns
-    // being accumulated.  Kept for the next round; the chunked kernel is the default.
-    p.roll = (p.ks == 3 && p.R >= 4 && opts && opts->rolling == 1) ? 1 : 0;
     p.dbg = opts ? opts->debug : 0;
-    p.cv_skip = (fused && opts->cv_skip == 1 && !p.roll) ? 1 : 0;
-    p.early = (want_early && p.nsets == 1 && !p.roll) ? 1 : 0;
-    int dc_max = p.roll ? p.D : 512 / (p.nsets * accw);
-    if (!p.roll && dc_max > (p.early ? kMaxRing : 16)) dc_max = p.early ? kMaxRing : 16;
+    p.cv_skip = (fused && opts->cv_skip == 1) ? 1 : 0;
+    int dc_max = 512 / (p.nsets * accw);
+    if (dc_max > 16) dc_max = 16;
     if (dc_max > p.D) dc_max = p.D;
     const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
     // Depth slices per work item: an item of Dc slices streams Dc + 2*halo slabs at a fixed MMA cost per slab, and the
@@ -1437,7 +1028,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    TcKernelFn kernel = p.roll ? tc_roll_kernel_for(p.nterm, P) : tc_kernel_for(p.ks, p.nterm, P, (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0);
+    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm, P, (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
@@ -1446,12 +1037,12 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // graph of the KITTI step: 196.0 pairs/s with, 196.1 without - launch gaps are not what the step loses.
     static const int use_pdl = [] { const char* v = getenv("LEA_TC_PDL"); return (v && v[0] == '1') ? 1 : 0; }();
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)(p.roll ? kThreads : tc_threads(P)));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)tc_threads(P));
     cfg.dynamicSmemBytes = kSmemBudget; cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = (use_pdl && !p.roll) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl ? 1 : 0;
     e = cudaLaunchKernelEx(&cfg, kernel, tmap, p);
     (void)smem;
     if (e == cudaSuccess) e = cudaGetLastError();

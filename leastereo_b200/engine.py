@@ -98,8 +98,6 @@ class MatchingPlan:
         self.tile_w_log2 = int(tc_knobs.get("tile_w_log2", 0))
         self.resident_weights = int(tc_knobs.get("resident_weights", 0))
         self.depth_chunk = int(tc_knobs.get("depth_chunk", 0))
-        self.rolling = int(tc_knobs.get("rolling", 0))
-        self.early_drain = int(tc_knobs.get("early_drain", 0))
         self.steps: List[Step] = []
         self.volumes: List[PlanesVol] = []
         self._bn_users: List[Tuple[ConvBR3d, int]] = []     # (module, offset into the BN buffers)
@@ -301,8 +299,6 @@ class MatchingPlan:
             opts.tile_w_log2 = self.tile_w_log2
             opts.resident_weights = self.resident_weights
             opts.depth_chunk = self.depth_chunk
-            opts.rolling = self.rolling
-            opts.early_drain = self.early_drain
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, flops, nbytes, p=p, mods=mods,
                                weight=weight, wcat=wcat, opts=opts, ref=src.vol.t,
                                vols=(src.vol,) + ((dst.vol,) if dst is not None else ())))
@@ -340,8 +336,6 @@ class MatchingPlan:
             opts.tile_w_log2 = self.tile_w_log2
             opts.resident_weights = self.resident_weights
             opts.depth_chunk = self.depth_chunk
-            opts.rolling = self.rolling
-            opts.early_drain = self.early_drain
         self.steps.append(Step("conv_tc" if use_tc else "conv_simt", name, 2.0 * m_vox * taps * c_in,
                                2.0 * self.P * m_vox * (c_in + dst.c), p=p, mods=(mod,), weight=wcat, wcat=wcat, opts=opts,
                                ref=src.vol.t, wfn=fill, vols=(src.vol, dst.vol)))
@@ -858,7 +852,7 @@ DEFAULT_OPTIONS = {"planes": 2, "conv": "tc", "mma_terms": 0, "fuse": True, "fus
 
 # tensor-core kernel / plan-rewrite knobs an ``engine_options`` dict may carry (defaults = what the product runs)
 _TC_KNOBS = {"accum_split": 0, "acc_sets": 0, "fuse_cv": True, "fuse_head": True, "collapse_stem0": True, "tile_w_log2": 0,
-             "resident_weights": 0, "depth_chunk": 0, "rolling": 0, "early_drain": 0, "reuse_buffers": True,
+             "resident_weights": 0, "depth_chunk": 0, "reuse_buffers": True,
              "fuse_resample_conv": False}
 
 

@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libleastereo_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class lea_vol(C.Structure):
@@ -38,7 +38,7 @@ class lea_rc_out(C.Structure):
 class lea_tc_opts(C.Structure):
     _fields_ = [("mma_terms", C.c_int32), ("fused_cv", C.c_int32), ("fx", lea_vol), ("fy", lea_vol),
                 ("d3", C.c_int32), ("num_sms", C.c_int32), ("accum_split", C.c_int32), ("acc_sets", C.c_int32), ("cv_maps", C.c_void_p),
-                ("resident_weights", C.c_int32), ("early_drain", C.c_int32), ("cv_skip", C.c_int32), ("debug", C.c_int32), ("rolling", C.c_int32), ("depth_chunk", C.c_int32),
+                ("resident_weights", C.c_int32), ("cv_skip", C.c_int32), ("debug", C.c_int32), ("depth_chunk", C.c_int32),
                 ("tile_w_log2", C.c_int32)]
 
 

@@ -351,22 +351,21 @@ TC_CASES = [
 ]
 
 
-# rolling schedule (k = 3): long work items so that the TMEM ring wraps and both alias blocks are used; the last
-# field forces the depth-chunk length (ring sizes: 32 -> 32 ch: 6 blocks, 16 -> 16: 14, 8 -> 8: 30)
-TC_ROLL_CASES = [
+# forced depth-chunk lengths (last field): several work items per tile column, short last chunks, chunks longer than
+# the volume, one and two accumulator sets
+TC_CHUNK_CASES = [
     (1, 32, 0, 32, 32, 3, (19, 20, 12), True, True, False, 19),
-    (1, 32, 0, 32, 32, 3, (19, 20, 12), True, True, True, 7),       # chunks 7+7+5: sequence numbers carry across items
+    (1, 32, 0, 32, 32, 3, (19, 20, 12), True, True, True, 7),       # chunks 7+7+5
     (2, 16, 0, 16, 16, 3, (40, 16, 8), True, True, True, 40),
     (1, 16, 0, 16, 16, 3, (33, 16, 8), False, False, False, 15),
     (1, 8, 0, 8, 8, 3, (70, 16, 8), True, True, True, 70),
     (1, 64, 0, 64, 32, 3, (13, 16, 8), True, True, False, 13),      # weights streamed per slab and channel group
-    (1, 32, 0, 32, 1, 3, (21, 16, 8), False, False, False, 21),     # fp32 output
-    (1, 16, 0, 16, 48, 3, (6, 16, 8), True, True, False, 6),        # 96 columns per depth: chunked kernel, two sets
-    # early-drain schedule (one accumulator set, per-depth hand-over): negative chunk length
-    (1, 32, 0, 32, 32, 3, (19, 20, 12), True, True, True, -7),      # short last chunk: unused depth slots
-    (2, 16, 0, 16, 16, 3, (40, 16, 8), True, True, True, -16),
-    (1, 128, 0, 128, 64, 3, (9, 16, 16), True, True, False, -4),    # streamed weights, 8 channel groups
-    (1, 8, 0, 8, 8, 3, (33, 16, 8), True, True, True, -32),
+    (1, 32, 0, 32, 1, 3, (21, 16, 8), False, False, False, 21),     # fp32 output (per-thread stores)
+    (1, 16, 0, 16, 48, 3, (6, 16, 8), True, True, False, 6),        # 96 columns per depth, two sets
+    (1, 128, 0, 128, 64, 3, (9, 16, 16), True, True, False, 4),     # streamed weights, 8 channel groups
+    (1, 16, 0, 16, 24, 3, (9, 21, 13), True, True, True, 4),        # 16-channel group + 8-channel tail, ragged tiles
+    (2, 64, 16, 32, 16, 1, (5, 9, 70), True, True, True, 3),        # 1x1x1, wide tile (32 x 4), clipped rows and columns
+    (1, 32, 0, 32, 8, 1, (3, 20, 24), True, False, False, 2),       # 1x1x1, 16 x 8 tile
 ]
 
 
@@ -383,8 +382,6 @@ def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False)
             opts = lea_tc_opts()
             opts.mma_terms = mma_terms
             opts.depth_chunk = abs(chunk)
-            opts.rolling = 1 if chunk > 0 else 0      # the TC_ROLL_CASES exercise the rolling-schedule kernel
-            opts.early_drain = 1 if chunk < 0 else 0  # negative chunk: the early-drain single-set schedule
             ops.conv3d_tc(p, img, opts, x)
 
         got, ref = _conv_case(ops, device, B, ct, c0, ci, co, k, sp, bn, relu, res, planes, 300 + 10 * i, fn)

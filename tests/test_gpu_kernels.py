@@ -92,9 +92,10 @@ def test_conv_tc(ops, planes):
 
 
 @pytest.mark.parametrize("planes", [2, 3])
-def test_conv_tc_rolling_schedule(ops, planes):
-    worst = K.check_conv_tc(ops, DEV, planes=planes, cases=K.TC_ROLL_CASES, verbose=True)
-    print("worst relative error (rolling), planes", planes, worst)
+def test_conv_tc_depth_chunks(ops, planes):
+    """Forced depth-chunk lengths, ragged tiles, 16+8 channel groups and wide 1x1x1 tiles."""
+    worst = K.check_conv_tc(ops, DEV, planes=planes, cases=K.TC_CHUNK_CASES, verbose=True)
+    print("worst relative error, planes", planes, worst)
 
 
 def test_conv_tc_single_pass(ops):
