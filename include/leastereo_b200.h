@@ -92,7 +92,9 @@ int lea_conv3d_simt(const lea_conv* p, const float* weight, void* stream);
 int64_t lea_tc_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t ksize, int32_t planes);
 int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
                         int32_t planes, void* stream);
-/* mma_terms: 1 = single-pass bf16 (hi*hi), 0 = full triangular split for the volume's P (P=2: bf16x3, P=3: bf16x6).
+/* mma_terms: 1 = single-pass bf16 (hi*hi), 0 = full triangular split for the volume's P (P=2: bf16x3, P=3: bf16x6),
+ * 2 (P = 3 volumes with c_in %% 16 == 0) = only the product terms of order < 2 (a0 w0, a1 w0, a0 w1): bf16x3 products on
+ * 3-plane (exactly stored) operands.
  * fused_cv: when non-zero, src is ignored and the operand loader builds the cost volume on the fly from the two
  * 2-D planes volumes fx/fy (retrain/LEAStereo.py:34-48 fused into stem0; the volume is never materialised). */
 typedef struct lea_tc_opts {
@@ -177,6 +179,15 @@ int lea_bn_relu_bwd(const lea_vol* x, int32_t x_c0, const lea_vol* dy, int32_t d
 /* dw[c_out][c_in][k^3] += sum_voxels dout * in(shifted)   (fp32, atomically accumulated: zero dw first). */
 int lea_conv3d_wgrad(const lea_vol* in, int32_t in_c0, int32_t c_in, const lea_vol* dout, int32_t dout_c0, int32_t c_out,
                      int32_t ksize, float* dw, void* stream);
+/* The same weight gradient on the tensor cores for the shapes that carry the training step (k = 3, two-plane volumes,
+ * channel counts tiling by 8, 16 or 32): warp-level mma.sync.m16n8k16 on bf16 planes with the bf16x3 split product
+ * (hi*hi + hi*lo + lo*hi, fp32 accumulate), operands straight from the planes layout via TMA + ldmatrix.trans.  The
+ * contraction runs over voxels and the output is tiny per tap, which fits 16 x 8 warp tiles and not tcgen05's
+ * 128 x N x 16 instruction (lea_wgrad_mma.cu).  dw is accumulated atomically (zero it first).
+ * lea_conv3d_wgrad_tc_supported returns 1 for the shapes taken; others go through lea_conv3d_wgrad. */
+int lea_conv3d_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t ksize, int32_t planes);
+int lea_conv3d_wgrad_tc(const lea_vol* in, int32_t in_c0, int32_t c_in, const lea_vol* dout, int32_t dout_c0,
+                        int32_t c_out, int32_t ksize, float* dw, void* stream);
 /* dsrc += transpose of the align_corners=True trilinear resample applied to ddst. */
 int lea_trilinear_ac_bwd(const lea_vol* ddst, int32_t ddst_c0, const lea_vol* dsrc, int32_t dsrc_c0, int32_t c,
                          void* stream);

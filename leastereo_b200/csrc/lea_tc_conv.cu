@@ -912,8 +912,11 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
             if (opts && opts->accum_split == 3) split = (s.ncg * s.taps2d > 9);
             if (opts && opts->accum_split == 4) split = (s.ncg * s.taps2d > 18);      // ... more than two groups
             p.ngroups = (P > 1 && split) ? 2 : 1;
-            for (int pw = 0; pw < P; ++pw)                     // weight plane pw = weight tile pw
-                for (int t = 0; t + pw < P; ++t) {             // activation plane t (plane t of cb 0; cb 1 is P blocks on)
+            // mma_terms = 2 on 3-plane volumes: only the terms of order < 2 (a0 w0, a1 w0, a0 w1) - bf16x3 products on
+            // exactly stored operands, half the MMAs of the full 6-term product
+            const int order = (opts && opts->mma_terms >= 2 && opts->mma_terms < P) ? opts->mma_terms : P;
+            for (int pw = 0; pw < order; ++pw)                 // weight plane pw = weight tile pw
+                for (int t = 0; t + pw < order; ++t) {         // activation plane t (plane t of cb 0; cb 1 is P blocks on)
                     const bool main_term = (pw == 0 && t == 0);
                     const bool first_small = (pw == 0 && t == 1);
                     add_term(t, P, pw, (main_term || p.ngroups == 1) ? 0 : 1,

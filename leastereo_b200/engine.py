@@ -948,14 +948,15 @@ def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[O
     plan = get_plan(model.matching, B, (D3, h3, w3), left.device, opt, ops)
     if plan.fxy is None:
         return None
-    key = ("feature", str(left.device), B, H, W, int(opt.get("feature_planes", 3)), opt["mma_terms"], id(ops), id(plan))
+    fterms = int(opt.get("feature_terms", opt["mma_terms"]))
+    key = ("feature", str(left.device), B, H, W, int(opt.get("feature_planes", 3)), fterms, id(ops), id(plan))
     with _LOCK:
         plans = _plans(model.feature)
         fplan = plans.get(key)
         if fplan is None:
             try:
                 fplan = FeaturePlan(model.feature, ops, 2 * B, H, W, int(opt.get("feature_planes", 3)), left.device, plan.fxy,
-                                    opt["mma_terms"], bool(opt.get("fuse", True)),
+                                    fterms, bool(opt.get("fuse", True)),
                                     {k: opt.get(k, d) for k, d in _TC_KNOBS.items()}, out3=plan.fxy3)
             except LeaError:
                 fplan = False

@@ -72,6 +72,8 @@ SYMBOLS = {
     "lea_affine_relu": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp, _vp, _i32, _i32, _vp]),
     "lea_bn_relu_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lea_conv3d_wgrad": (C.c_int, [_VOLP, _i32, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp]),
+    "lea_conv3d_wgrad_tc_supported": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "lea_conv3d_wgrad_tc": (C.c_int, [_VOLP, _i32, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp]),
     "lea_trilinear_ac_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp]),
     "lea_cost_volume_bwd": (C.c_int, [_VOLP, _i32, _vp, _vp, _vp]),
     "lea_disp_head_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
@@ -84,7 +86,7 @@ SYMBOLS = {
 }
 # symbols only the CUDA build has (tcgen05 path); the CPU emulation used by the no-GPU tests lacks them
 DEVICE_ONLY = {"lea_tc_weight_image_bytes", "lea_pack_weights_tc", "lea_conv3d_tc", "lea_tc_selftest",
-               "lea_fused_cv_maps_bytes", "lea_build_fused_cv_maps"}
+               "lea_fused_cv_maps_bytes", "lea_build_fused_cv_maps", "lea_conv3d_wgrad_tc_supported", "lea_conv3d_wgrad_tc"}
 
 
 class LeaError(RuntimeError):
@@ -412,11 +414,18 @@ class Ops:
                                                  self._stream(x.t)))
 
     def conv3d_wgrad(self, src: PlanesVol, src_c0: int, c_in: int, dout: PlanesVol, dout_c0: int, c_out: int,
-                     ksize: int, dw: torch.Tensor):
+                     ksize: int, dw: torch.Tensor, tensor_cores: bool = False):
+        """dw += weight gradient.  ``tensor_cores``: take ``lea_conv3d_wgrad_tc`` (mma.sync on the bf16 planes) for the
+        shapes it supports (device build only); everything else runs the fp32 FMA kernel."""
         self._dev(src.t, dout.t, dw)
         assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == c_out * c_in * ksize ** 3
         a, b = src.struct(), dout.struct()
         with self._dev_ctx(src.t):
+            if (tensor_cores and self.device_build and src.P == 2 and dout.P == 2 and
+                    self.lib.lea_conv3d_wgrad_tc_supported(c_in, c_out, ksize, src.P)):
+                self._check(self.lib.lea_conv3d_wgrad_tc(C.byref(a), src_c0, c_in, C.byref(b), dout_c0, c_out, ksize,
+                                                         dw.data_ptr(), self._stream(src.t)))
+                return
             self._check(self.lib.lea_conv3d_wgrad(C.byref(a), src_c0, c_in, C.byref(b), dout_c0, c_out, ksize,
                                                   dw.data_ptr(), self._stream(src.t)))
 

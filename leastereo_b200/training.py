@@ -274,7 +274,8 @@ class _ConvBRNode(_Node):
         w = mod.conv.weight.detach()
         if mod.conv.weight.requires_grad:
             dw = torch.zeros_like(w, dtype=torch.float32)
-            ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dx.vol, 0, c, k, dw)
+            ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dx.vol, 0, c, k, dw,
+                             tensor_cores=(plan.conv_mode == "tc"))
             plan.add_param_grad(mod.conv.weight, dw)
         # data gradient: conv with transposed, tap-flipped weights, accumulated into the input's gradient
         wt = w.flip(2, 3, 4).transpose(0, 1).contiguous()

@@ -397,6 +397,50 @@ def check_conv_tc(ops, device, planes=2, mma_terms=0, cases=None, verbose=False)
     return worst
 
 
+def check_wgrad_tc(ops, device, verbose=False):
+    """lea_conv3d_wgrad_tc (mma.sync on the two bf16 planes, bf16x3 products) against the weight gradient of F.conv3d
+    computed in fp64 on the SAME 2-plane-rounded operands; ragged tiles, channel slices, every channel tiling
+    (8 / 16 / 32), several depth chunks, and against the fp32 FMA kernel it replaces.
+    Tolerance 3e-5 of the gradient's max: the dropped lo*lo products (2^-16 per product, random sign)."""
+    worst = 0.0
+    cases = [  # (B, c_in_total, c0, c_in, c_out_total, o0, c_out, spatial[, ksize])
+        (2, 64, 0, 64, 16, 0, 16, (5, 19, 13), 1),       # 1x1x1: cells' pre-processing layers
+        (1, 128, 0, 128, 32, 0, 32, (3, 16, 24), 1),
+        (1, 64, 0, 64, 8, 0, 8, (4, 9, 30), 1),
+        (2, 48, 16, 32, 24, 8, 16, (6, 17, 8), 1),
+        (1, 8, 0, 8, 8, 0, 8, (5, 16, 8)),
+        (2, 16, 0, 16, 16, 0, 16, (7, 19, 13)),
+        (1, 32, 0, 32, 32, 0, 32, (9, 33, 17)),
+        (1, 64, 0, 64, 32, 0, 32, (4, 16, 24)),          # two ci tiles (stem0-like)
+        (1, 96, 32, 64, 72, 8, 64, (3, 20, 9)),          # channel slices, 2 x 2 tiles of 32
+        (2, 16, 8, 8, 24, 16, 8, (6, 9, 30)),            # 8-channel tiles inside wider volumes
+        (1, 48, 0, 48, 16, 0, 16, (3, 16, 16)),          # 3 ci tiles of 16
+        (1, 16, 0, 16, 16, 0, 16, (70, 16, 8)),          # long column: several depth chunks / ring wraps
+    ]
+    for i, case in enumerate(cases):
+        (B, cit, c0, ci, cot, o0, co, sp), k = case[:8], (case[8] if len(case) > 8 else 3)
+        assert ops.lib.lea_conv3d_wgrad_tc_supported(ci, co, k, 2)
+        x = _rand((B, cit) + sp, 500 + i, device)
+        dy = _rand((B, cot) + sp, 600 + i, device)
+        xv, dyv = ops.pack(x, 2), ops.pack(dy, 2)
+        dw = torch.zeros((co, ci, k, k, k), dtype=torch.float32, device=device)
+        ops.conv3d_wgrad(xv, c0, ci, dyv, o0, co, k, dw, tensor_cores=True)
+        dw_fma = torch.zeros_like(dw)
+        ops.conv3d_wgrad(xv, c0, ci, dyv, o0, co, k, dw_fma, tensor_cores=False)
+        xr = ops.unpack(xv).cpu().double()[:, c0:c0 + ci]                 # the operands the kernels actually see
+        dr = ops.unpack(dyv).cpu().double()[:, o0:o0 + co]
+        w = torch.zeros((co, ci, k, k, k), dtype=torch.float64, requires_grad=True)
+        (F.conv3d(xr, w, None, 1, (k - 1) // 2) * dr).sum().backward()
+        scale = float(w.grad.abs().max())
+        err = float((dw.cpu().double() - w.grad).abs().max()) / scale
+        err_fma = float((dw_fma.cpu().double() - w.grad).abs().max()) / scale
+        if verbose:
+            print("wgrad_tc case %d: rel err %.3g (fma kernel %.3g)" % (i, err, err_fma))
+        assert err <= 3e-5, (i, err)
+        worst = max(worst, err)
+    return worst
+
+
 # ---------------------------------------------------------------------------------------------------------
 # native feature net (2D net on depth-1 planes volumes + fused stems) against the stock-PyTorch module
 # ---------------------------------------------------------------------------------------------------------

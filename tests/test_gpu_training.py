@@ -23,6 +23,11 @@ def test_backward_kernels_individually(ops):
     check_backward_kernels(ops, DEV)
 
 
+def test_wgrad_tensor_cores(ops):
+    import kernel_checks as K
+    print("lea_conv3d_wgrad_tc worst rel err:", K.check_wgrad_tc(ops, DEV, verbose=True))
+
+
 def test_train_step_fp32_simt(ops):
     print("simt/P=3 train step vs autograd:", check_train_step(ops, DEV, planes=3, conv="simt", tol=2e-3, grad_tol=3e-2))
 

@@ -23,6 +23,7 @@ MODES = {
     "tc_p2_no_head_taps": {"fuse_head": False},
     "tc_p2_one_region": {"accum_split": 2},
     "tc_p2_feature_p2": {"feature_planes": 2},
+    "tc_p2_feature_terms2": {"feature_terms": 2},
     "tc_p3": {"planes": 3},
     "simt_p2": {"conv": "simt", "planes": 2},
     "simt_p3": {"conv": "simt", "planes": 3},
