@@ -22,6 +22,8 @@ MODES = {
     "tc_p2_plain_stem0": {"collapse_stem0": False},
     "tc_p2_no_head_taps": {"fuse_head": False},
     "tc_p2_one_region": {"accum_split": 2},
+    "tc_p2_split3": {"accum_split": 3},
+    "tc_p2_split4": {"accum_split": 4},
     "tc_p2_feature_p2": {"feature_planes": 2},
     "tc_p2_feature_terms2": {"feature_terms": 2},
     "tc_p3": {"planes": 3},
