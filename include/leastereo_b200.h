@@ -169,6 +169,16 @@ int lea_feature_stem(const float* img, int32_t B, int32_t H, int32_t W, const fl
 int lea_channel_reduce(const lea_vol* x, int32_t x_c0, const lea_vol* dy, int32_t dy_c0, int32_t c, int32_t mode,
                        int32_t relu, const float* scale, const float* shift, const float* mean, const float* invstd,
                        float* partial, int32_t chunks, void* stream);
+/* BatchNorm3d train-mode glue on the device (operations_3d.py:38,44), one launch each instead of dozens of tiny host
+ * tensor ops per ConvBR.  lea_bn_finalize: chunk partials of (sum x, sum x^2) over n voxels -> mean, invstd, scale =
+ * gamma*invstd, shift = beta - mean*scale, running statistics updated in place with `momentum` (unbiased variance),
+ * *num_batches_tracked += 1 (gamma/beta/running/num_batches_tracked may be NULL).  lea_bn_bwd_coeffs: chunk partials of
+ * (sum g, sum g*xh) -> the coefficients ka, kb, kc of lea_bn_relu_bwd and dgamma = sum g*xh, dbeta = sum g. */
+int lea_bn_finalize(const float* partial, int32_t chunks, int32_t c, double n, const float* gamma, const float* beta,
+                    double eps, double momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                    float* mean, float* invstd, float* scale, float* shift, void* stream);
+int lea_bn_bwd_coeffs(const float* partial, int32_t chunks, int32_t c, double n, const float* gamma, const float* invstd,
+                      float* ka, float* kb, float* kc, float* dgamma, float* dbeta, void* stream);
 /* dst = [dst +] relu?(x*scale[ch] + shift[ch])  - BN apply in train mode and the state sums (skip_model_3d.py:70). */
 int lea_affine_relu(const lea_vol* x, int32_t x_c0, const lea_vol* dst, int32_t dst_c0, int32_t c, const float* scale,
                     const float* shift, int32_t relu, int32_t accumulate, void* stream);

@@ -17,6 +17,26 @@ extern "C" int lea_channel_reduce(const lea_vol* x, int32_t x_c0, const lea_vol*
     return LEA_POST_LAUNCH();
 }
 
+extern "C" int lea_bn_finalize(const float* partial, int32_t chunks, int32_t c, double n, const float* gamma,
+                               const float* beta, double eps, double momentum, float* running_mean, float* running_var,
+                               int64_t* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift,
+                               void* stream) {
+    LEA_CHECK(partial && mean && invstd && scale && shift && chunks >= 1 && c >= 1 && n >= 1.0, "bn_finalize: bad argument");
+    LEA_CHECK((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running statistics must come together");
+    LEA_LAUNCH(lea_bn_finalize_kernel, dim3((c + 63) / 64), dim3(64), 0, stream, partial, chunks, c, n, gamma, beta, eps,
+               momentum, running_mean, running_var, (long long*)num_batches_tracked, mean, invstd, scale, shift);
+    return LEA_POST_LAUNCH();
+}
+
+extern "C" int lea_bn_bwd_coeffs(const float* partial, int32_t chunks, int32_t c, double n, const float* gamma,
+                                 const float* invstd, float* ka, float* kb, float* kc, float* dgamma, float* dbeta,
+                                 void* stream) {
+    LEA_CHECK(partial && invstd && ka && kb && kc && chunks >= 1 && c >= 1 && n >= 1.0, "bn_bwd_coeffs: bad argument");
+    LEA_LAUNCH(lea_bn_bwd_coeffs_kernel, dim3((c + 63) / 64), dim3(64), 0, stream, partial, chunks, c, n, gamma, invstd,
+               ka, kb, kc, dgamma, dbeta);
+    return LEA_POST_LAUNCH();
+}
+
 extern "C" int lea_affine_relu(const lea_vol* x, int32_t x_c0, const lea_vol* dst, int32_t dst_c0, int32_t c,
                                const float* scale, const float* shift, int32_t relu, int32_t accumulate, void* stream) {
     if (lea_check_vol(x, "affine_relu") || lea_check_slice(x, x_c0, c, "affine_relu")) return 1;

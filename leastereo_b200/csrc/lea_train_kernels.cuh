@@ -330,6 +330,64 @@ lea_conv1_wgrad_kernel(lea_vol in, int in_c0, int c_in, lea_vol dout, int dout_c
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// BatchNorm3d (train mode) per-channel glue, one thread per channel - what the host did with ~35 tiny tensor ops per
+// ConvBR (operations_3d.py:38,44; F.batch_norm semantics):
+//   finalize:  from the chunk partials of (sum x, sum x^2): mean, invstd = 1/sqrt(var_biased + eps),
+//              scale = gamma*invstd, shift = beta - mean*scale, and the running statistics
+//              r = (1-momentum)*r + momentum*{mean, var_unbiased} (fp32 like torch), num_batches_tracked += 1;
+//   bwd coeffs: from the partials of (sum g, sum g*xh): ka = gamma*invstd, kb = ka*sum_g/n, kc = ka*sum_gx/n
+//              (the coefficients of lea_bn_relu_bwd) and the parameter gradients dgamma = sum g*xh, dbeta = sum g.
+// Chunk partials are added in fp64.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+lea_bn_finalize_kernel(const float* __restrict__ partial, int chunks, int c, double n, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, double eps, double momentum, float* __restrict__ running_mean,
+                       float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
+                       float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
+                       float* __restrict__ shift) {
+    const int ch = blockIdx.x * 64 + threadIdx.x;
+    if (ch >= c) return;
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        s += (double)partial[((int64_t)k * 2 + 0) * c + ch];
+        q += (double)partial[((int64_t)k * 2 + 1) * c + ch];
+    }
+    const double m = s / n;
+    double var = q / n - m * m;
+    var = var > 0.0 ? var : 0.0;
+    const double is = 1.0 / sqrt(var + eps);
+    const double g = gamma ? (double)gamma[ch] : 1.0, bt = beta ? (double)beta[ch] : 0.0;
+    mean[ch] = (float)m; invstd[ch] = (float)is;
+    scale[ch] = (float)(g * is); shift[ch] = (float)(bt - m * g * is);
+    if (running_mean) {
+        const float keep = (float)(1.0 - momentum), mom = (float)momentum;
+        const float unb = (float)(var * (n / (n - 1.0 > 1.0 ? n - 1.0 : 1.0)));
+        const float rm = running_mean[ch] * keep, rv = running_var[ch] * keep;      // separately rounded, as the two
+        const float am = mom * (float)m, av = mom * unb;                            // tensor ops of torch would
+        running_mean[ch] = rm + am;
+        running_var[ch] = rv + av;
+    }
+    if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
+}
+
+__global__ void __launch_bounds__(64)
+lea_bn_bwd_coeffs_kernel(const float* __restrict__ partial, int chunks, int c, double n, const float* __restrict__ gamma,
+                         const float* __restrict__ invstd, float* __restrict__ ka, float* __restrict__ kb,
+                         float* __restrict__ kc, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int ch = blockIdx.x * 64 + threadIdx.x;
+    if (ch >= c) return;
+    double sg = 0.0, sgx = 0.0;
+    for (int k = 0; k < chunks; ++k) {
+        sg += (double)partial[((int64_t)k * 2 + 0) * c + ch];
+        sgx += (double)partial[((int64_t)k * 2 + 1) * c + ch];
+    }
+    const double a = (gamma ? (double)gamma[ch] : 1.0) * (double)invstd[ch];
+    ka[ch] = (float)a; kb[ch] = (float)(a * sg / n); kc[ch] = (float)(a * sgx / n);
+    if (dgamma) dgamma[ch] = (float)sgx;
+    if (dbeta) dbeta[ch] = (float)sg;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // trilinear (align_corners=True) backward, gather form: every SOURCE voxel sums the destination gradients that
 // referenced it, dsrc += up^T(ddst).  Destination index j touches source i iff floor(j*s) is i-1 or i
 // (s = (in-1)/(out-1)), i.e. j in [(i-1)/s, (i+1)/s): a short range per axis, scanned with one step of margin.

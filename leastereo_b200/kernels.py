@@ -69,6 +69,9 @@ SYMBOLS = {
     "lea_disparity_regression": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "lea_feature_stem": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _VOLP, _i32, _vp]),
     "lea_channel_reduce": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "lea_bn_finalize": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp,
+                                  _vp, _vp, _vp]),
+    "lea_bn_bwd_coeffs": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lea_affine_relu": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp, _vp, _i32, _i32, _vp]),
     "lea_bn_relu_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lea_conv3d_wgrad": (C.c_int, [_VOLP, _i32, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp]),
@@ -393,6 +396,45 @@ class Ops:
                                                     self._ptr(scale), self._ptr(shift), self._ptr(mean),
                                                     self._ptr(invstd), partial.data_ptr(), chunks, self._stream(x.t)))
         return partial.double().sum(dim=0)
+
+    def channel_reduce_partial(self, x: PlanesVol, x_c0: int, c: int, partial: torch.Tensor, mode: int = 0,
+                               dy: Optional[PlanesVol] = None, dy_c0: int = 0, relu: bool = False, scale=None,
+                               shift=None, mean=None, invstd=None) -> int:
+        """``lea_channel_reduce`` into the caller's (chunks, 2, c) fp32 buffer; returns the number of chunk rows written
+        (the rows are added on the device by ``bn_finalize`` / ``bn_bwd_coeffs``)."""
+        self._dev(x.t, partial)
+        chunks = max(64, 1184 // max(1, c >> 3))
+        chunks = max(1, min(chunks, ((x.D * x.H * x.W) + 255) // 256, partial.shape[0]))
+        assert partial.dtype == torch.float32 and partial.is_contiguous() and partial.shape[1:] == (2, c)
+        xs = x.struct()
+        ds = dy.struct() if dy is not None else xs
+        with self._dev_ctx(x.t):
+            self._check(self.lib.lea_channel_reduce(C.byref(xs), x_c0, C.byref(ds), dy_c0, c, mode, int(bool(relu)),
+                                                    self._ptr(scale), self._ptr(shift), self._ptr(mean),
+                                                    self._ptr(invstd), partial.data_ptr(), chunks, self._stream(x.t)))
+        return chunks
+
+    def bn_finalize(self, partial: torch.Tensor, chunks: int, c: int, n: float, gamma, beta, eps: float, momentum: float,
+                    running_mean, running_var, num_batches_tracked, mean, invstd, scale, shift):
+        self._dev(partial, mean, invstd, scale, shift)
+        for t in (gamma, beta, running_mean, running_var, mean, invstd, scale, shift):
+            assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() >= c)
+        assert num_batches_tracked is None or num_batches_tracked.dtype == torch.int64
+        with self._dev_ctx(partial):
+            self._check(self.lib.lea_bn_finalize(partial.data_ptr(), chunks, c, float(n), self._ptr(gamma), self._ptr(beta),
+                                                 float(eps), float(momentum), self._ptr(running_mean),
+                                                 self._ptr(running_var), self._ptr(num_batches_tracked), mean.data_ptr(),
+                                                 invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
+                                                 self._stream(partial)))
+
+    def bn_bwd_coeffs(self, partial: torch.Tensor, chunks: int, c: int, n: float, gamma, invstd, ka, kb, kc, dgamma, dbeta):
+        self._dev(partial, invstd, ka, kb, kc)
+        for t in (gamma, invstd, ka, kb, kc, dgamma, dbeta):
+            assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() >= c)
+        with self._dev_ctx(partial):
+            self._check(self.lib.lea_bn_bwd_coeffs(partial.data_ptr(), chunks, c, float(n), self._ptr(gamma),
+                                                   invstd.data_ptr(), ka.data_ptr(), kb.data_ptr(), kc.data_ptr(),
+                                                   self._ptr(dgamma), self._ptr(dbeta), self._stream(partial)))
 
     def affine_relu(self, x: PlanesVol, x_c0: int, dst: PlanesVol, dst_c0: int, c: int, scale=None, shift=None,
                     relu: bool = False, accumulate: bool = False):

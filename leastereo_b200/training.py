@@ -226,28 +226,28 @@ class _ConvBRNode(_Node):
             raise LeaError("%s: ConvBR without BN is only supported as the last_3 head" % name)
         self.x = Slice(plan.vol(c_out, src.spatial), 0, c_out)        # raw conv output, kept for the backward
         self.dx = None
+        # per-channel BN vectors and the chunk partials of the reductions: allocated once, filled by kernels
+        dev = plan.device
+        self.partial = torch.empty((max(64, 1184 // max(1, c_out >> 3)), 2, c_out), dtype=torch.float32, device=dev)
+        self.mean, self.invstd, self.scale, self.shift, self.ka, self.kb, self.kc = (
+            torch.empty(c_out, dtype=torch.float32, device=dev) for _ in range(7))
 
     def forward(self):
         plan, mod, ops = self.plan, self.mod, self.plan.ops
         c = mod.conv.out_channels
         plan.conv_raw(self.src, mod.conv.weight.detach(), self.x)
         n = float(self.x.vol.B * _prod(self.x.spatial))
-        sums = ops.channel_reduce(self.x.vol, self.x.c0, c, mode=0)
-        mean = sums[0] / n
-        var = (sums[1] / n - mean * mean).clamp_min(0.0)
         bn = mod.bn
-        invstd = 1.0 / torch.sqrt(var + bn.eps)
-        gamma, beta = bn.weight.detach().double(), bn.bias.detach().double()
-        self.mean, self.invstd = mean.float().contiguous(), invstd.float().contiguous()
-        self.scale = (gamma * invstd).float().contiguous()
-        self.shift = (beta - mean * gamma * invstd).float().contiguous()
+        # batch statistics: chunked per-channel sums, then ONE kernel for mean / invstd / scale / shift and the running
+        # statistics (momentum, unbiased variance, num_batches_tracked) - no host arithmetic, no tiny tensor ops
+        chunks = ops.channel_reduce_partial(self.x.vol, self.x.c0, c, self.partial, mode=0)
+        track = bn.track_running_stats and bn.running_mean is not None
+        ops.bn_finalize(self.partial, chunks, c, n, bn.weight.detach(), bn.bias.detach(), bn.eps,
+                        bn.momentum if bn.momentum is not None else 0.1,
+                        bn.running_mean if track else None, bn.running_var if track else None,
+                        bn.num_batches_tracked if track else None, self.mean, self.invstd, self.scale, self.shift)
         ops.affine_relu(self.x.vol, self.x.c0, self.dst.vol, self.dst.c0, c, self.scale, self.shift, mod.relu,
                         self.accumulate)
-        with torch.no_grad():                       # running statistics (momentum, unbiased variance)
-            mom = bn.momentum if bn.momentum is not None else 0.1
-            bn.running_mean.mul_(1 - mom).add_(mom * mean.to(bn.running_mean.dtype))
-            bn.running_var.mul_(1 - mom).add_(mom * (var * (n / max(n - 1.0, 1.0))).to(bn.running_var.dtype))
-            bn.num_batches_tracked += 1
 
     def backward(self):
         plan, mod, ops = self.plan, self.mod, self.plan.ops
@@ -255,22 +255,21 @@ class _ConvBRNode(_Node):
         k = mod.conv.weight.shape[2]
         dy = plan.grad_of(self.dst.vol)
         n = float(self.x.vol.B * _prod(self.x.spatial))
-        sums = ops.channel_reduce(self.x.vol, self.x.c0, c, mode=1, dy=dy, dy_c0=self.dst.c0, relu=mod.relu,
-                                  scale=self.scale, shift=self.shift, mean=self.mean, invstd=self.invstd)
-        sum_g, sum_gx = sums[0], sums[1]
-        gamma = mod.bn.weight.detach().double()
-        ka = gamma * self.invstd.double()
-        kb = ka * sum_g / n
-        kc = ka * sum_gx / n
-        if mod.bn.weight.requires_grad:
-            plan.add_param_grad(mod.bn.weight, sum_gx.float())
-        if mod.bn.bias.requires_grad:
-            plan.add_param_grad(mod.bn.bias, sum_g.float())
+        chunks = ops.channel_reduce_partial(self.x.vol, self.x.c0, c, self.partial, mode=1, dy=dy, dy_c0=self.dst.c0,
+                                            relu=mod.relu, scale=self.scale, shift=self.shift, mean=self.mean,
+                                            invstd=self.invstd)
+        dgamma = torch.empty(c, dtype=torch.float32, device=plan.device) if mod.bn.weight.requires_grad else None
+        dbeta = torch.empty(c, dtype=torch.float32, device=plan.device) if mod.bn.bias.requires_grad else None
+        ops.bn_bwd_coeffs(self.partial, chunks, c, n, mod.bn.weight.detach(), self.invstd, self.ka, self.kb, self.kc,
+                          dgamma, dbeta)
+        if dgamma is not None:
+            plan.add_param_grad(mod.bn.weight, dgamma)
+        if dbeta is not None:
+            plan.add_param_grad(mod.bn.bias, dbeta)
         if self.dx is None:
             self.dx = Slice(PlanesVol.empty(self.x.vol.B, c, plan.P, *self.x.spatial, plan.device), 0, c)
         ops.bn_relu_bwd(self.x.vol, self.x.c0, dy, self.dst.c0, self.dx.vol, 0, c, mod.relu, self.scale, self.shift,
-                        self.mean, self.invstd, ka.float().contiguous(), kb.float().contiguous(),
-                        kc.float().contiguous())
+                        self.mean, self.invstd, self.ka, self.kb, self.kc)
         w = mod.conv.weight.detach()
         if mod.conv.weight.requires_grad:
             dw = torch.zeros_like(w, dtype=torch.float32)
@@ -409,4 +408,8 @@ def hot_path_train_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optio
         plan = TrainPlan(model.matching, ops, B, (D3, H3, W3), planes, fx.device, conv, model.maxdisp)
         _TRAIN_PLANS[key] = plan
     params = used_parameters(plan)
+    # the BN kernels update running_mean / running_var / num_batches_tracked through raw pointers (no autograd version
+    # bump): tell the eval-mode plans that parameters changed
+    from .engine import bump_param_generation
+    bump_param_generation()
     return _HotPathTrainFn.apply(plan, fx, fy, *params)
