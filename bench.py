@@ -688,7 +688,7 @@ def main():
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
-            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_conv_tc_traffic.json (%s)" % tj.get("captured", "ncu")
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r02_conv_tc_traffic.json: " + tj.get("captured", "ncu")
         except Exception:  # noqa: BLE001
             traffic = None
     roofline = {"bound": "tensor", "kernel": "lea_conv_tc_kernel" if args.conv == "tc" else "lea_conv3_simt_kernel",
@@ -697,6 +697,8 @@ def main():
                 "achieved_as_launched": round(launched_tflops, 2),
                 "frac_as_launched": round(launched_tflops / peaks["bf16_tflops_sustained"], 4),
                 "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch_1pair": int(sum(agg[k]["bytes"] for k in conv_kinds) / max(1, B) /
+                                                          max(1, sum(agg[k]["launches"] for k in conv_kinds))),
                 "peak_source": "%s bf16 dense, sustained (kernel timed inside a long step)" % peak_src,
                 "algorithmic_flops_per_step": ref_conv_flops, "conv_launches_per_step": sum(agg[k]["launches"] for k in conv_kinds),
                 "launched_flops_per_step": conv_flops, "conv_ms_per_step": round(conv_ms, 4),

@@ -1,5 +1,5 @@
 """Turns the CSV of `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none
--k regex:lea_ --csv --log-file X python bench.py --batch 1 --steps 1 --warmup 3 --no-graph --no-cpu-baseline` into the
+-k regex:lea_ --csv --log-file X python bench.py --batch 1 --steps 1 --warmup 3 --no-graph --quick` into the
 per-launch / per-kernel summary kept under profiles/ (the LAST forward of the run: from the last feature-stem launch to
 the disparity head).  Usage: python tools/ncu_summarize.py launches.csv out.json [conv_tc_traffic.json [n_matching_conv_launches]]"""
 import csv
@@ -33,7 +33,7 @@ def main():
     starts = [i for i in ids if rows[i]["kernel"].startswith("lea_feature_stem_kernel")]
     first = starts[-1] if starts else ids[0]
     ends = [i for i in ids if i >= first and rows[i]["kernel"].startswith("lea_disp_head")]
-    last = ends[-1] if ends else ids[-1]
+    last = ends[0] if ends else ids[-1]          # the forward's own head (bench.py times stand-alone kernels after it)
     sel = [rows[i] for i in ids if first <= i <= last]
     per = [{"kernel": e["kernel"], "grid": e["grid"], "us": round(e["gpu__time_duration.sum"] / 1e3, 2),
             "dram_read_MB": round(e.get("dram__bytes_read.sum", 0.0) / 1e6, 2),
@@ -56,7 +56,7 @@ def main():
     nbytes = sum((p["dram_read_MB"] + p["dram_write_MB"]) * 1e6 for p in convs)
     summary = {
         "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none "
-                   "-k regex:lea_ --csv python bench.py --batch 1 --steps 1 --warmup 3 --no-graph --no-cpu-baseline",
+                   "-k regex:lea_ --csv python bench.py --batch 1 --steps 1 --warmup 3 --no-graph --quick",
         "note": "one eager forward (1 KITTI pair) late in the run; per-launch times are cold-cache and serialised - "
                 "compare shares, not absolutes",
         "launches_in_forward": len(per), "total_us": round(total, 1), "by_kernel": by,

@@ -12,7 +12,7 @@ from leastereo_b200.kernels import get_ops, PlanesVol, lea_tc_opts  # noqa: E402
 
 def main():
     which = sys.argv[1:] or ["stem0", "l1res", "l1batched", "conv1", "l0res", "cv", "disp", "resample", "headtaps", "pp64",
-                             "assemble"]
+                             "assemble", "wgrad"]
     ops = get_ops()
     dev = torch.device("cuda:0")
     B, C, H3, W3, D3, maxdisp = 1, 32, 128, 416, 64, 192
@@ -43,6 +43,16 @@ def main():
         conv(8, 8, 3, (64, 128, 416), True)
     if "pp64" in which:
         conv(64, 16, 1, (32, 64, 208), False)
+    if "wgrad" in which:
+        # weight gradients at the training shapes (288x576, one sample): stem1-like 32 -> 32 at level 0, a level-1 cell op
+        # 16 -> 16, and the 1x1x1 pre-processing conv 64 -> 16
+        for (ci, co, k, sp) in [(32, 32, 3, (64, 96, 192)), (16, 16, 3, (32, 48, 96)), (64, 16, 1, (32, 48, 96))]:
+            x = PlanesVol.empty(B, ci, 2, *sp, dev); x.t.copy_(torch.randn(x.t.shape, device=dev).bfloat16() * 0.1)
+            dy = PlanesVol.empty(B, co, 2, *sp, dev); dy.t.copy_(torch.randn(dy.t.shape, device=dev).bfloat16() * 0.1)
+            dw = torch.zeros(co, ci, k, k, k, device=dev)
+            for _ in range(2):
+                ops.conv3d_wgrad(x, 0, ci, dy, 0, co, k, dw, tensor_cores=True)
+            del x, dy
     if "cv" in which:
         x = torch.randn(B, C, H3, W3, device=dev); y = torch.randn(B, C, H3, W3, device=dev)
         for _ in range(2):
