@@ -350,7 +350,7 @@ def gpu_baseline_leg(device, B, steps=3, warmup=2):
     return out
 
 
-def train_leg(device, rank, world, dist, steps=4, warmup=2, batch=4, H=288, W=576, maxdisp=192):
+def train_leg(device, rank, world, dist, steps=4, warmup=5, batch=4, H=288, W=576, maxdisp=192):
     """BASELINE configs[4]: fwd + bwd + gradient all-reduce (ONE NCCL all-reduce of the flat fp32 bucket over NVLink)
     + Adam at 288x576, batch 4 per GPU, every rank; device time, max over ranks (train.py:153-160)."""
     from leastereo_b200 import LEAStereo, default_args

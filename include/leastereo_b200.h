@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define LEA_ABI_VERSION 2
+#define LEA_ABI_VERSION 3
 
 typedef struct lea_vol {
     void*   data;          /* bf16 planes volume, 16-byte aligned                                   */
@@ -92,6 +92,11 @@ int lea_conv3d_simt(const lea_conv* p, const float* weight, void* stream);
 int64_t lea_tc_weight_image_bytes(int32_t c_in, int32_t c_out, int32_t ksize, int32_t planes);
 int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
                         int32_t planes, void* stream);
+/* Image of the DATA-GRADIENT conv of a forward weight (fwd_c_out = c_in here, fwd_c_in >= c_out), read in place:
+ * transposed in the channel pair and tap-flipped, W'[co][ci][tap] = weight[ci][fwd_ci0 + co][k^3-1-tap]
+ * (the slice [fwd_ci0, fwd_ci0 + c_out) of the forward input channels: a launch takes at most 64; train.py:156-160). */
+int lea_pack_weights_tc_dgrad(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
+                              int32_t planes, int32_t fwd_c_in, int32_t fwd_ci0, void* stream);
 /* mma_terms: 1 = single-pass bf16 (hi*hi), 0 = full triangular split for the volume's P (P=2: bf16x3, P=3: bf16x6),
  * 2 (P = 3 volumes with c_in %% 16 == 0) = only the product terms of order < 2 (a0 w0, a1 w0, a0 w1): bf16x3 products on
  * 3-plane (exactly stored) operands.
@@ -173,12 +178,13 @@ int lea_channel_reduce(const lea_vol* x, int32_t x_c0, const lea_vol* dy, int32_
  * tensor ops per ConvBR.  lea_bn_finalize: chunk partials of (sum x, sum x^2) over n voxels -> mean, invstd, scale =
  * gamma*invstd, shift = beta - mean*scale, running statistics updated in place with `momentum` (unbiased variance),
  * *num_batches_tracked += 1 (gamma/beta/running/num_batches_tracked may be NULL).  lea_bn_bwd_coeffs: chunk partials of
- * (sum g, sum g*xh) -> the coefficients ka, kb, kc of lea_bn_relu_bwd and dgamma = sum g*xh, dbeta = sum g. */
+ * (sum g, sum g*xh) -> the coefficients ka, kb, kc of lea_bn_relu_bwd and dgamma = sum g*xh, dbeta = sum g
+ * (written, or added to what the vectors hold when accumulate != 0). */
 int lea_bn_finalize(const float* partial, int32_t chunks, int32_t c, double n, const float* gamma, const float* beta,
                     double eps, double momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
                     float* mean, float* invstd, float* scale, float* shift, void* stream);
 int lea_bn_bwd_coeffs(const float* partial, int32_t chunks, int32_t c, double n, const float* gamma, const float* invstd,
-                      float* ka, float* kb, float* kc, float* dgamma, float* dbeta, void* stream);
+                      float* ka, float* kb, float* kc, float* dgamma, float* dbeta, int32_t accumulate, void* stream);
 /* dst = [dst +] relu?(x*scale[ch] + shift[ch])  - BN apply in train mode and the state sums (skip_model_3d.py:70). */
 int lea_affine_relu(const lea_vol* x, int32_t x_c0, const lea_vol* dst, int32_t dst_c0, int32_t c, const float* scale,
                     const float* shift, int32_t relu, int32_t accumulate, void* stream);
@@ -198,9 +204,9 @@ int lea_conv3d_wgrad(const lea_vol* in, int32_t in_c0, int32_t c_in, const lea_v
 int lea_conv3d_wgrad_tc_supported(int32_t c_in, int32_t c_out, int32_t ksize, int32_t planes);
 int lea_conv3d_wgrad_tc(const lea_vol* in, int32_t in_c0, int32_t c_in, const lea_vol* dout, int32_t dout_c0,
                         int32_t c_out, int32_t ksize, float* dw, void* stream);
-/* dsrc += transpose of the align_corners=True trilinear resample applied to ddst. */
+/* dsrc (+)= transpose of the align_corners=True trilinear resample applied to ddst (accumulate == 0 overwrites). */
 int lea_trilinear_ac_bwd(const lea_vol* ddst, int32_t ddst_c0, const lea_vol* dsrc, int32_t dsrc_c0, int32_t c,
-                         void* stream);
+                         int32_t accumulate, void* stream);
 /* transpose of the cost-volume construction (LEAStereo.py:42-48): dcost (2C channels) -> dx, dy (B, C, H, W) fp32. */
 int lea_cost_volume_bwd(const lea_vol* dcost, int32_t C, float* dx, float* dy, void* stream);
 /* backward of lea_disp_head: dmat (B, D3, H3, W3) += J^T gout; dmat must be zero-initialised by the caller. */

@@ -23,17 +23,17 @@ extern "C" int lea_bn_finalize(const float* partial, int32_t chunks, int32_t c, 
                                void* stream) {
     LEA_CHECK(partial && mean && invstd && scale && shift && chunks >= 1 && c >= 1 && n >= 1.0, "bn_finalize: bad argument");
     LEA_CHECK((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running statistics must come together");
-    LEA_LAUNCH(lea_bn_finalize_kernel, dim3((c + 63) / 64), dim3(64), 0, stream, partial, chunks, c, n, gamma, beta, eps,
+    LEA_LAUNCH(lea_bn_finalize_kernel, dim3((c + 7) / 8), dim3(256), 0, stream, partial, chunks, c, n, gamma, beta, eps,
                momentum, running_mean, running_var, (long long*)num_batches_tracked, mean, invstd, scale, shift);
     return LEA_POST_LAUNCH();
 }
 
 extern "C" int lea_bn_bwd_coeffs(const float* partial, int32_t chunks, int32_t c, double n, const float* gamma,
                                  const float* invstd, float* ka, float* kb, float* kc, float* dgamma, float* dbeta,
-                                 void* stream) {
+                                 int32_t accumulate, void* stream) {
     LEA_CHECK(partial && invstd && ka && kb && kc && chunks >= 1 && c >= 1 && n >= 1.0, "bn_bwd_coeffs: bad argument");
-    LEA_LAUNCH(lea_bn_bwd_coeffs_kernel, dim3((c + 63) / 64), dim3(64), 0, stream, partial, chunks, c, n, gamma, invstd,
-               ka, kb, kc, dgamma, dbeta);
+    LEA_LAUNCH(lea_bn_bwd_coeffs_kernel, dim3((c + 7) / 8), dim3(256), 0, stream, partial, chunks, c, n, gamma, invstd,
+               ka, kb, kc, dgamma, dbeta, accumulate);
     return LEA_POST_LAUNCH();
 }
 
@@ -102,13 +102,13 @@ extern "C" int lea_conv3d_wgrad(const lea_vol* in, int32_t in_c0, int32_t c_in, 
 }
 
 extern "C" int lea_trilinear_ac_bwd(const lea_vol* ddst, int32_t ddst_c0, const lea_vol* dsrc, int32_t dsrc_c0,
-                                    int32_t c, void* stream) {
+                                    int32_t c, int32_t accumulate, void* stream) {
     if (lea_check_vol(ddst, "trilinear_ac_bwd ddst") || lea_check_vol(dsrc, "trilinear_ac_bwd dsrc")) return 1;
     if (lea_check_slice(ddst, ddst_c0, c, "trilinear_ac_bwd ddst") || lea_check_slice(dsrc, dsrc_c0, c, "trilinear_ac_bwd dsrc"))
         return 1;
     LEA_CHECK(ddst->B == dsrc->B && (int64_t)dsrc->B * (c >> 3) <= 65535, "trilinear_ac_bwd: bad batch");
     LEA_LAUNCH(lea_trilinear_ac_bwd_kernel, dim3((dsrc->W + 127) / 128, dsrc->D * dsrc->H, dsrc->B * (c >> 3)), dim3(128),
-               0, stream, *ddst, ddst_c0, *dsrc, dsrc_c0, c);
+               0, stream, *ddst, ddst_c0, *dsrc, dsrc_c0, c, accumulate);
     return LEA_POST_LAUNCH();
 }
 

@@ -749,7 +749,8 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P, 
 }
 
 __global__ void lea_pack_weights_tc_kernel(const float* __restrict__ w, lea_u4* __restrict__ img,
-                                           int c_in, int c_out, int ks, int P, int total_groups, int allow_fold) {
+                                           int c_in, int c_out, int ks, int P, int total_groups, int allow_fold,
+                                           int dgrad) {
     const int gidx = blockIdx.x * blockDim.x + threadIdx.x;
     if (gidx >= total_groups) return;
     const TcShape s = tc_shape(c_in, c_out, ks, P, allow_fold);
@@ -789,8 +790,14 @@ __global__ void lea_pack_weights_tc_kernel(const float* __restrict__ w, lea_u4* 
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint16_t a[3], b[3];
-            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i) * ntaps + tap], P, a);
-            lea_split_planes(w[((int64_t)co * c_in + ci0 + 2 * i + 1) * ntaps + tap], P, b);
+            // dgrad: the image of the data-gradient conv W'[co][ci][tap] = w[ci][co][flipped tap], read in place from
+            // the forward weight (c_in, c_out here are the data-gradient conv's: c_in = the forward c_out)
+            const int ca = ci0 + 2 * i, cb = ci0 + 2 * i + 1;
+            // (dgrad = row length of the forward weight in channels, >= c_out: a launch may take a slice of them)
+            const int64_t ia = dgrad ? ((int64_t)ca * dgrad + co) * ntaps + (ntaps - 1 - tap) : ((int64_t)co * c_in + ca) * ntaps + tap;
+            const int64_t ib = dgrad ? ((int64_t)cb * dgrad + co) * ntaps + (ntaps - 1 - tap) : ((int64_t)co * c_in + cb) * ntaps + tap;
+            lea_split_planes(w[ia], P, a);
+            lea_split_planes(w[ib], P, b);
             q[i] = (uint32_t)a[plane] | ((uint32_t)b[plane] << 16);
         }
     }
@@ -1061,17 +1068,30 @@ extern "C" int64_t lea_tc_weight_image_bytes(int32_t c_in, int32_t c_out, int32_
     return (int64_t)s.ncg * s.wpart_bytes;
 }
 
-extern "C" int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
-                                   int32_t planes, void* stream) {
+static int pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
+                           int32_t planes, void* stream, int dgrad) {
     const TcShape s = tc_shape(c_in, c_out, ksize, planes, tc_fold_enabled());
     LEA_CHECK(s.ok, "pack_weights_tc: unsupported shape c_in=%d c_out=%d k=%d planes=%d", c_in, c_out, ksize, planes);
     LEA_CHECK(weight && wimg && ((((uintptr_t)wimg) & 15) == 0), "pack_weights_tc: bad pointer");
     const int total = (int)((int64_t)s.ncg * s.wpart_bytes / 16);
     lea_pack_weights_tc_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-        weight, reinterpret_cast<lea_u4*>(wimg), c_in, c_out, ksize, planes, total, tc_fold_enabled());
+        weight, reinterpret_cast<lea_u4*>(wimg), c_in, c_out, ksize, planes, total, tc_fold_enabled(), dgrad);
     cudaError_t e = cudaGetLastError();
     LEA_CHECK(e == cudaSuccess, "pack_weights_tc: launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+extern "C" int lea_pack_weights_tc(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
+                                   int32_t planes, void* stream) {
+    return pack_weights_tc(weight, wimg, c_in, c_out, ksize, planes, stream, 0);
+}
+
+extern "C" int lea_pack_weights_tc_dgrad(const float* weight, void* wimg, int32_t c_in, int32_t c_out, int32_t ksize,
+                                         int32_t planes, int32_t fwd_c_in, int32_t fwd_ci0, void* stream) {
+    LEA_CHECK(fwd_ci0 >= 0 && fwd_ci0 + c_out <= fwd_c_in, "pack_weights_tc_dgrad: channel slice outside the forward weight");
+    const int64_t ntaps = (int64_t)ksize * ksize * ksize;
+    return pack_weights_tc(weight ? weight + (int64_t)fwd_ci0 * ntaps : weight, wimg, c_in, c_out, ksize, planes, stream,
+                           fwd_c_in);
 }
 
 extern "C" int lea_conv3d_tc(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void* stream) {

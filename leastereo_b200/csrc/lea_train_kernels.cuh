@@ -339,19 +339,38 @@ lea_conv1_wgrad_kernel(lea_vol in, int in_c0, int c_in, lea_vol dout, int dout_c
 //              (the coefficients of lea_bn_relu_bwd) and the parameter gradients dgamma = sum g*xh, dbeta = sum g.
 // Chunk partials are added in fp64.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+// Chunk partials of channel ch are added by the 32 threads that share threadIdx.x / 32 (lane l takes chunks l, l+32, ...)
+// and then in a fixed order by lane 0 - deterministic, and ~300 dependent fp64 adds per channel become ~10.
+// block 256 = 8 channels x 32 lanes, grid ceil(c / 8).
+LEA_D void lea_bn_chunk_sums(const float* __restrict__ partial, int chunks, int c, int ch, double (*red)[8][32],
+                               double& s0, double& s1) {
+    const int slot = threadIdx.x >> 5, l = threadIdx.x & 31;
+    double a = 0.0, b = 0.0;
+    if (ch < c) {
+        for (int k = l; k < chunks; k += 32) {
+            a += (double)partial[((int64_t)k * 2 + 0) * c + ch];
+            b += (double)partial[((int64_t)k * 2 + 1) * c + ch];
+        }
+    }
+    red[0][slot][l] = a; red[1][slot][l] = b;
+    __syncthreads();
+    s0 = 0.0; s1 = 0.0;
+    if (l == 0) {
+        for (int k = 0; k < 32; ++k) { s0 += red[0][slot][k]; s1 += red[1][slot][k]; }
+    }
+}
+
+__global__ void __launch_bounds__(256)
 lea_bn_finalize_kernel(const float* __restrict__ partial, int chunks, int c, double n, const float* __restrict__ gamma,
                        const float* __restrict__ beta, double eps, double momentum, float* __restrict__ running_mean,
                        float* __restrict__ running_var, long long* __restrict__ num_batches_tracked,
                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
                        float* __restrict__ shift) {
-    const int ch = blockIdx.x * 64 + threadIdx.x;
-    if (ch >= c) return;
-    double s = 0.0, q = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-        s += (double)partial[((int64_t)k * 2 + 0) * c + ch];
-        q += (double)partial[((int64_t)k * 2 + 1) * c + ch];
-    }
+    __shared__ double red[2][8][32];
+    const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+    double s, q;
+    lea_bn_chunk_sums(partial, chunks, c, ch, red, s, q);
+    if (ch >= c || (threadIdx.x & 31) != 0) return;
     const double m = s / n;
     double var = q / n - m * m;
     var = var > 0.0 ? var : 0.0;
@@ -370,21 +389,20 @@ lea_bn_finalize_kernel(const float* __restrict__ partial, int chunks, int c, dou
     if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
 
-__global__ void __launch_bounds__(64)
+// dgamma / dbeta: written, or ADDED when accumulate != 0 (the flat gradient bucket, zeroed once per step)
+__global__ void __launch_bounds__(256)
 lea_bn_bwd_coeffs_kernel(const float* __restrict__ partial, int chunks, int c, double n, const float* __restrict__ gamma,
                          const float* __restrict__ invstd, float* __restrict__ ka, float* __restrict__ kb,
-                         float* __restrict__ kc, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int ch = blockIdx.x * 64 + threadIdx.x;
-    if (ch >= c) return;
-    double sg = 0.0, sgx = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-        sg += (double)partial[((int64_t)k * 2 + 0) * c + ch];
-        sgx += (double)partial[((int64_t)k * 2 + 1) * c + ch];
-    }
+                         float* __restrict__ kc, float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+    __shared__ double red[2][8][32];
+    const int ch = blockIdx.x * 8 + (threadIdx.x >> 5);
+    double sg, sgx;
+    lea_bn_chunk_sums(partial, chunks, c, ch, red, sg, sgx);
+    if (ch >= c || (threadIdx.x & 31) != 0) return;
     const double a = (gamma ? (double)gamma[ch] : 1.0) * (double)invstd[ch];
     ka[ch] = (float)a; kb[ch] = (float)(a * sg / n); kc[ch] = (float)(a * sgx / n);
-    if (dgamma) dgamma[ch] = (float)sgx;
-    if (dbeta) dbeta[ch] = (float)sg;
+    if (dgamma) dgamma[ch] = (accumulate ? dgamma[ch] : 0.0f) + (float)sgx;
+    if (dbeta) dbeta[ch] = (accumulate ? dbeta[ch] : 0.0f) + (float)sg;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -409,8 +427,13 @@ LEA_HD float lea_axis_ac_weight(int j, int i, int in_n, int out_n) {
     return (a.i0 == i ? a.l0 : 0.0f) + (a.i1 == i ? a.l1 : 0.0f);
 }
 
+// Along w (the per-thread axis) the destinations with a non-zero weight are compacted into registers once
+// (LEA_TB_TAPS entries: enough for up-sampling factors up to ~3; longer ranges fall back to the scanning loop), so the
+// inner loop is loads + FMAs only: the first version evaluated a weight - a float division - for every candidate of
+// a 7 x 7 x 7 range and was 10x off the traffic it needs.  accumulate == 0 overwrites dsrc (first writer).
+#define LEA_TB_TAPS 6
 __global__ void __launch_bounds__(128)
-lea_trilinear_ac_bwd_kernel(lea_vol ddst, int ddst_c0, lea_vol dsrc, int dsrc_c0, int c) {
+lea_trilinear_ac_bwd_kernel(lea_vol ddst, int ddst_c0, lea_vol dsrc, int dsrc_c0, int c, int accumulate) {
     const int w = blockIdx.x * 128 + threadIdx.x;
     if (w >= dsrc.W) return;
     const int h = blockIdx.y % dsrc.H, d = blockIdx.y / dsrc.H;
@@ -420,21 +443,57 @@ lea_trilinear_ac_bwd_kernel(lea_vol ddst, int ddst_c0, lea_vol dsrc, int dsrc_c0
     const lea_axis_range rh = lea_axis_ac_sources(h, dsrc.H, ddst.H);
     const lea_axis_range rw = lea_axis_ac_sources(w, dsrc.W, ddst.W);
     float acc[8];
-    lea_vol_load8(dsrc, b, (dsrc_c0 >> 3) + cb, d, h, w, acc);         // gradients accumulate
+    if (accumulate) lea_vol_load8(dsrc, b, (dsrc_c0 >> 3) + cb, d, h, w, acc);
+    else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    }
+    int tj[LEA_TB_TAPS];
+    float tw[LEA_TB_TAPS];
+    int nt = 0;
+    bool compact = true;
+#pragma unroll
+    for (int q = 0; q < LEA_TB_TAPS; ++q) { tj[q] = 0; tw[q] = 0.0f; }
+    for (int jw = rw.lo; jw <= rw.hi; ++jw) {
+        const float ww = lea_axis_ac_weight(jw, w, dsrc.W, ddst.W);
+        if (ww == 0.0f) continue;
+        if (nt >= LEA_TB_TAPS) { compact = false; break; }
+#pragma unroll
+        for (int q = 0; q < LEA_TB_TAPS; ++q)
+            if (q == nt) { tj[q] = jw; tw[q] = ww; }
+        ++nt;
+    }
+    const int64_t dHW = (int64_t)ddst.H * ddst.W, dPS = dHW * ddst.D;
+    const lea_u4* gbase = (const lea_u4*)ddst.data + ((int64_t)b * (ddst.C >> 3) + (ddst_c0 >> 3) + cb) * ddst.P * dPS;
     for (int jd = rd.lo; jd <= rd.hi; ++jd) {
         const float wd = lea_axis_ac_weight(jd, d, dsrc.D, ddst.D);
         if (wd == 0.0f) continue;
         for (int jh = rh.lo; jh <= rh.hi; ++jh) {
             const float wh = lea_axis_ac_weight(jh, h, dsrc.H, ddst.H);
             if (wh == 0.0f) continue;
-            for (int jw = rw.lo; jw <= rw.hi; ++jw) {
-                const float ww = lea_axis_ac_weight(jw, w, dsrc.W, ddst.W);
-                if (ww == 0.0f) continue;
-                float g[8];
-                lea_vol_load8(ddst, b, (ddst_c0 >> 3) + cb, jd, jh, jw, g);
-                const float k = wd * wh * ww;
+            const float wdh = wd * wh;
+            const lea_u4* grow = gbase + (int64_t)jd * dHW + (int64_t)jh * ddst.W;
+            if (compact) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += k * g[j];
+                for (int q = 0; q < LEA_TB_TAPS; ++q) {
+                    if (q < nt) {
+                        float g[8];
+                        lea_load8_at(grow + tj[q], dPS, ddst.P, g);
+                        const float k = wdh * tw[q];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] += k * g[j];
+                    }
+                }
+            } else {
+                for (int jw = rw.lo; jw <= rw.hi; ++jw) {
+                    const float ww = lea_axis_ac_weight(jw, w, dsrc.W, ddst.W);
+                    if (ww == 0.0f) continue;
+                    float g[8];
+                    lea_load8_at(grow + jw, dPS, ddst.P, g);
+                    const float k = wdh * ww;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] += k * g[j];
+                }
             }
         }
     }

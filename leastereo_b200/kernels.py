@@ -14,7 +14,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libleastereo_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class lea_vol(C.Structure):
@@ -58,6 +58,7 @@ SYMBOLS = {
     "lea_conv3d_simt": (C.c_int, [_CONVP, _vp, _vp]),
     "lea_tc_weight_image_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "lea_pack_weights_tc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "lea_pack_weights_tc_dgrad": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "lea_conv3d_tc": (C.c_int, [_CONVP, _vp, _TCP, _vp]),
     "lea_tc_selftest": (C.c_int, [_i32, _vp]),
     "lea_fused_cv_maps_bytes": (_i64, [_i32]),
@@ -71,13 +72,13 @@ SYMBOLS = {
     "lea_channel_reduce": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "lea_bn_finalize": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp, _vp, C.c_double, C.c_double, _vp, _vp, _vp, _vp, _vp,
                                   _vp, _vp, _vp]),
-    "lea_bn_bwd_coeffs": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "lea_bn_bwd_coeffs": (C.c_int, [_vp, _i32, _i32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "lea_affine_relu": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp, _vp, _i32, _i32, _vp]),
     "lea_bn_relu_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "lea_conv3d_wgrad": (C.c_int, [_VOLP, _i32, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp]),
     "lea_conv3d_wgrad_tc_supported": (C.c_int, [_i32, _i32, _i32, _i32]),
     "lea_conv3d_wgrad_tc": (C.c_int, [_VOLP, _i32, _i32, _VOLP, _i32, _i32, _i32, _vp, _vp]),
-    "lea_trilinear_ac_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _vp]),
+    "lea_trilinear_ac_bwd": (C.c_int, [_VOLP, _i32, _VOLP, _i32, _i32, _i32, _vp]),
     "lea_cost_volume_bwd": (C.c_int, [_VOLP, _i32, _vp, _vp, _vp]),
     "lea_disp_head_bwd": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "lea_image_stats_u8": (C.c_int, [_vp, _i32, _i32, _vp, _vp]),
@@ -88,7 +89,7 @@ SYMBOLS = {
     "lea_disparity_metrics": (C.c_int, [_vp, _vp, _i64, C.c_float, _vp, C.c_int32, _vp, _vp]),
 }
 # symbols only the CUDA build has (tcgen05 path); the CPU emulation used by the no-GPU tests lacks them
-DEVICE_ONLY = {"lea_tc_weight_image_bytes", "lea_pack_weights_tc", "lea_conv3d_tc", "lea_tc_selftest",
+DEVICE_ONLY = {"lea_tc_weight_image_bytes", "lea_pack_weights_tc", "lea_pack_weights_tc_dgrad", "lea_conv3d_tc", "lea_tc_selftest",
                "lea_fused_cv_maps_bytes", "lea_build_fused_cv_maps", "lea_conv3d_wgrad_tc_supported", "lea_conv3d_wgrad_tc"}
 
 
@@ -298,6 +299,25 @@ class Ops:
                                                      self._stream(weight)))
         return img
 
+    def pack_weights_tc_dgrad(self, weight: torch.Tensor, planes: int, ci0: int = 0, ci: Optional[int] = None,
+                              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Image of the data-gradient conv (channels transposed, taps flipped) straight from the forward weight
+        (c_out_fwd, c_in_fwd, k, k, k); ``[ci0, ci0 + ci)`` = the forward input channels this launch produces."""
+        self._dev(weight)
+        assert weight.dtype == torch.float32 and weight.is_contiguous()
+        fwd_c_in = weight.shape[1]
+        c_in, k = weight.shape[0], weight.shape[2]                               # of the data-gradient conv
+        c_out = fwd_c_in - ci0 if ci is None else ci
+        nbytes = self.tc_weight_image_bytes(c_in, c_out, k, planes)
+        if nbytes <= 0:
+            raise LeaError("tcgen05 conv does not take c_in=%d c_out=%d k=%d" % (c_in, c_out, k))
+        img = out if out is not None else torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+        assert img.numel() == nbytes
+        with torch.cuda.device(weight.device):
+            self._check(self.lib.lea_pack_weights_tc_dgrad(weight.data_ptr(), img.data_ptr(), c_in, c_out, k, planes,
+                                                           fwd_c_in, ci0, self._stream(weight)))
+        return img
+
     def conv3d_tc(self, p: lea_conv, wimg: torch.Tensor, opts: lea_tc_opts, ref: torch.Tensor):
         self._dev(wimg, ref)
         with torch.cuda.device(ref.device):
@@ -427,14 +447,16 @@ class Ops:
                                                  invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(),
                                                  self._stream(partial)))
 
-    def bn_bwd_coeffs(self, partial: torch.Tensor, chunks: int, c: int, n: float, gamma, invstd, ka, kb, kc, dgamma, dbeta):
+    def bn_bwd_coeffs(self, partial: torch.Tensor, chunks: int, c: int, n: float, gamma, invstd, ka, kb, kc, dgamma, dbeta,
+                      accumulate: bool = False):
         self._dev(partial, invstd, ka, kb, kc)
         for t in (gamma, invstd, ka, kb, kc, dgamma, dbeta):
             assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.numel() >= c)
         with self._dev_ctx(partial):
             self._check(self.lib.lea_bn_bwd_coeffs(partial.data_ptr(), chunks, c, float(n), self._ptr(gamma),
                                                    invstd.data_ptr(), ka.data_ptr(), kb.data_ptr(), kc.data_ptr(),
-                                                   self._ptr(dgamma), self._ptr(dbeta), self._stream(partial)))
+                                                   self._ptr(dgamma), self._ptr(dbeta), int(bool(accumulate)),
+                                                   self._stream(partial)))
 
     def affine_relu(self, x: PlanesVol, x_c0: int, dst: PlanesVol, dst_c0: int, c: int, scale=None, shift=None,
                     relu: bool = False, accumulate: bool = False):
@@ -471,11 +493,13 @@ class Ops:
             self._check(self.lib.lea_conv3d_wgrad(C.byref(a), src_c0, c_in, C.byref(b), dout_c0, c_out, ksize,
                                                   dw.data_ptr(), self._stream(src.t)))
 
-    def trilinear_ac_bwd(self, ddst: PlanesVol, ddst_c0: int, dsrc: PlanesVol, dsrc_c0: int, c: int):
+    def trilinear_ac_bwd(self, ddst: PlanesVol, ddst_c0: int, dsrc: PlanesVol, dsrc_c0: int, c: int,
+                         accumulate: bool = True):
         self._dev(ddst.t, dsrc.t)
         a, b = ddst.struct(), dsrc.struct()
         with self._dev_ctx(ddst.t):
-            self._check(self.lib.lea_trilinear_ac_bwd(C.byref(a), ddst_c0, C.byref(b), dsrc_c0, c, self._stream(ddst.t)))
+            self._check(self.lib.lea_trilinear_ac_bwd(C.byref(a), ddst_c0, C.byref(b), dsrc_c0, c,
+                                                      int(bool(accumulate)), self._stream(ddst.t)))
 
     def cost_volume_bwd(self, dcost: PlanesVol, Cn: int):
         self._dev(dcost.t)

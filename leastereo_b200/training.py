@@ -30,6 +30,55 @@ class _Node:
     def backward(self):
         raise NotImplementedError
 
+    def plan_backward(self, cover: "_Coverage"):
+        """Declares, in backward order, which gradient slices this node reads and writes (``TrainPlan._finalize``)."""
+        raise NotImplementedError
+
+
+class _Coverage:
+    """Which channel ranges of every gradient volume have been written so far while the backward order is walked.
+    The first writer of a range overwrites (no zero fill of the volume, no read-modify-write); a volume whose writes
+    overlap only partially, or that is read before it is completely written, is zero-filled at the start of the
+    backward instead and all its writers accumulate."""
+
+    def __init__(self, zero_vols):
+        self.zero_vols = zero_vols                # ids of the volumes that are zero-filled: everything accumulates
+        self.ranges: Dict[int, List[Tuple[int, int]]] = {}
+        self.retry = False
+
+    def _covered(self, vid, c0, c) -> Tuple[bool, bool]:
+        """(any overlap, fully covered) of [c0, c0 + c) against the ranges written so far."""
+        rs = sorted(self.ranges.get(vid, []))
+        overlap = any(r0 < c0 + c and c0 < r0 + rc for r0, rc in rs)
+        pos = c0
+        for r0, rc in rs:
+            if r0 <= pos < r0 + rc:
+                pos = r0 + rc
+        return overlap, pos >= c0 + c
+
+    def write(self, sl: Slice) -> bool:
+        """Registers a write of the gradient slice; returns True when the writer has to accumulate."""
+        vid = id(sl.vol)
+        if vid in self.zero_vols:
+            return True
+        overlap, full = self._covered(vid, sl.c0, sl.c)
+        if not overlap:
+            self.ranges.setdefault(vid, []).append((sl.c0, sl.c))
+            return False
+        if full:
+            return True
+        self.zero_vols.add(vid)
+        self.retry = True
+        return True
+
+    def read(self, sl: Slice):
+        vid = id(sl.vol)
+        if vid in self.zero_vols:
+            return
+        if not self._covered(vid, sl.c0, sl.c)[1]:
+            self.zero_vols.add(vid)
+            self.retry = True
+
 
 class TrainPlan:
     def __init__(self, matching: newMatching, ops: Ops, B: int, spatial, planes: int, device, conv_mode: str, maxdisp):
@@ -41,8 +90,17 @@ class TrainPlan:
         self.grads: Dict[int, PlanesVol] = {}
         self.values: List[PlanesVol] = []
         self.param_grads: Dict[torch.nn.Parameter, torch.Tensor] = {}
+        self._resampled: Dict[tuple, Slice] = {}
         self.generation = 0                        # forward counter: a backward must belong to the latest forward
+        # CUDA graphs of the two launch lists (~1100 + ~1600 launches through ctypes: the eager step is host-bound).
+        # Two eager steps first (they create the per-node weight-image buffers), then capture; the graphs are dropped
+        # when a parameter moves to other storage (e.g. an optimizer that re-points them into a flat buffer).
+        self.use_graph = False
+        self._eager_calls = [0, 0]
+        self._graphs = [None, None]
+        self._graph_key = None
         self._build()
+        self._finalize()
 
     # ---- buffers ----------------------------------------------------------------------------------------
     def vol(self, c, spatial) -> PlanesVol:
@@ -57,42 +115,96 @@ class TrainPlan:
             self.grads[id(v)] = g
         return g
 
-    def add_param_grad(self, p: torch.nn.Parameter, g: torch.Tensor):
-        if p in self.param_grads:
-            self.param_grads[p] = self.param_grads[p] + g
+    def _finalize(self):
+        """Parameter-gradient bucket (one flat fp32 buffer, zeroed by ONE memset per backward; the weight-gradient and
+        BN kernels add into views of it) and the first-writer analysis of the activation gradients."""
+        params = used_parameters(self)
+        total = sum(p.numel() for p in params)
+        self.pflat = torch.zeros(max(1, total), dtype=torch.float32, device=self.device)
+        off = 0
+        self.param_grads = {}
+        for p in params:
+            self.param_grads[p] = self.pflat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        for v in self.values:
+            self.grad_of(v)
+        zero_vols: set = set()
+        for _ in range(len(self.values) + 2):
+            cover = _Coverage(zero_vols)
+            for n in reversed(self.nodes):
+                n.plan_backward(cover)
+            cover.read(Slice(self.cost, 0, self.cost.C))
+            if not cover.retry:
+                break
         else:
-            self.param_grads[p] = g
+            raise LeaError("training plan: gradient coverage analysis did not converge")
+        self.zero_grads = [self.grads[id(v)] for v in self.values if id(v) in zero_vols]
 
     # ---- conv launch helper (raw conv: no BN, no ReLU) ----------------------------------------------------
     def conv_raw(self, src: Slice, weight: torch.Tensor, dst: Optional[Slice], accumulate: bool = False,
-                 dst_f32: Optional[torch.Tensor] = None):
-        c_out, c_in, k = weight.shape[0], weight.shape[1], weight.shape[2]
+                 dst_f32: Optional[torch.Tensor] = None, dgrad_of: Optional[torch.Tensor] = None, images=None):
+        """``weight`` (c_out, c_in, k, k, k), or - ``dgrad_of`` = a FORWARD weight (c_in, c_out, k, k, k) - the data-gradient
+        conv of that layer (channels transposed, taps flipped; packed in place on the tensor-core path).  ``images`` = the
+        caller's list of packed-weight buffers, one per 64-channel output chunk (created on first use)."""
+        if dgrad_of is not None:
+            c_in, c_out, k = dgrad_of.shape[0], dgrad_of.shape[1], dgrad_of.shape[2]
+        else:
+            c_out, c_in, k = weight.shape[0], weight.shape[1], weight.shape[2]
+            weight = weight.contiguous()
         if src.c != c_in:
             raise LeaError("conv_raw: %d input channels, weight expects %d" % (src.c, c_in))
-        weight = weight.contiguous()
         # the kernels take at most 64 output channels per launch
-        for o0 in range(0, c_out, 64):
+        for n, o0 in enumerate(range(0, c_out, 64)):
             oc = min(64, c_out - o0)
-            w = weight[o0:o0 + oc].contiguous() if (o0 > 0 or oc < c_out) else weight
             d = None if dst is None else Slice(dst.vol, dst.c0 + o0, oc)
             p = self.ops.make_conv(src.vol, src.c0, c_in, oc, k, None, None, False,
                                    dst=None if d is None else d.vol, dst_c0=0 if d is None else d.c0,
                                    res=d.vol if (accumulate and d is not None) else None,
                                    res_c0=d.c0 if (accumulate and d is not None) else 0, dst_f32=dst_f32)
-            if self.conv_mode == "tc" and self.ops.tc_weight_image_bytes(c_in, oc, k, self.P) > 0:
-                img = self.ops.pack_weights_tc(w, self.P)
+            tc = self.conv_mode == "tc" and self.ops.tc_weight_image_bytes(c_in, oc, k, self.P) > 0
+            if images is not None and len(images) <= n:
+                images.append(None)
+            out = images[n] if images is not None else None
+            if tc and dgrad_of is not None:
+                img = self.ops.pack_weights_tc_dgrad(dgrad_of, self.P, o0, oc, out=out)
+            else:
+                if weight is None:               # SIMT path of a data gradient: materialise the transposed weight once
+                    weight = dgrad_of.flip(2, 3, 4).transpose(0, 1).contiguous()
+                w = weight[o0:o0 + oc].contiguous() if (o0 > 0 or oc < c_out) else weight
+                img = self.ops.pack_weights_tc(w, self.P, out=out) if tc else None
+            if tc:
+                if images is not None:
+                    images[n] = img
                 self.ops.conv3d_tc(p, img, lea_tc_opts(), src.vol.t)
             else:
                 self.ops.conv3d_simt(p, w, src.vol.t)
 
     # ---- graph construction (unfused mirror of retrain/skip_model_3d.py) -----------------------------------
-    def _convbr(self, name, mod: ConvBR3d, src: Slice, dst: Slice, accumulate=False):
-        self.nodes.append(_ConvBRNode(self, name, mod, src, dst, accumulate))
+    def _convbr(self, name, mod: ConvBR3d, src: Slice, dst: Slice, accumulate=False, upsample_to=None):
+        self.nodes.append(_ConvBRNode(self, name, mod, src, dst, accumulate, upsample_to))
 
     def _resample(self, name, src: Slice, spatial) -> Slice:
-        dst = Slice(self.vol(src.c, spatial), 0, src.c)
-        self.nodes.append(_ResampleNode(self, name, src, dst))
+        """One resample per distinct (tensor, size): s1 of cell i is s0 of cell i+1 (skip_model_3d.py:44-51)."""
+        key = (id(src.vol), src.c0, src.c, tuple(spatial))
+        dst = self._resampled.get(key)
+        if dst is None:
+            dst = Slice(self.vol(src.c, spatial), 0, src.c)
+            self.nodes.append(_ResampleNode(self, name, src, dst))
+            self._resampled[key] = dst
         return dst
+
+    def _pre(self, name, mod: ConvBR3d, src: Slice, spatial, dst: Slice):
+        """Cell input path [resample ->] 1x1x1 ConvBR (skip_model_3d.py:44-53).  When the resample ENLARGES the volume
+        the conv runs first on the small volume - a 1x1x1 conv commutes with the interpolation - and its raw output is
+        up-sampled before the batch statistics: c_out instead of c_in channels at the high resolution (8 instead of 64
+        for cell 10), in the forward and in every backward kernel."""
+        k = mod.conv.weight.shape[2]
+        if src.spatial == tuple(spatial):
+            self._convbr(name, mod, src, dst)
+        elif k == 1 and _prod(src.spatial) < _prod(spatial):
+            self._convbr(name, mod, src, dst, upsample_to=tuple(spatial))
+        else:
+            self._convbr(name, mod, self._resample(name + ".resample", src, spatial), dst)
 
     def _cell(self, i, s0: Slice, s1: Slice, out: Optional[Slice] = None):
         cell = self.m.cells[i]
@@ -100,12 +212,9 @@ class TrainPlan:
         name = "cells.%d" % i
         prev_input = s1
         c_out = spec.c_out
+        sp = s1.spatial
         if spec.downup_sample != 0:
             sp = tuple(scale_dimension(n, spec.scale) for n in s1.spatial)
-            s1 = self._resample(name + ".resample_s1", s1, sp)
-        if s0.spatial != s1.spatial:
-            s0 = self._resample(name + ".resample_s0", s0, s1.spatial)
-        sp = s1.spatial
         bm = self.m._block_multiplier
         n_states = 2 + len(spec.steps)
         first = n_states - bm
@@ -120,14 +229,17 @@ class TrainPlan:
 
         if s0.c != c_out:
             d0 = slot(0)
-            self._convbr(name + ".pre_preprocess", cell.pre_preprocess, s0, d0)
+            self._pre(name + ".pre_preprocess", cell.pre_preprocess, s0, sp, d0)
             s0 = d0
-        elif first <= 0:
-            d0 = slot(0)
-            self.nodes.append(_CopyNode(self, name + ".s0_copy", s0, d0, False))
-            s0 = d0
+        else:
+            if s0.spatial != sp:
+                s0 = self._resample(name + ".resample_s0", s0, sp)
+            if first <= 0:
+                d0 = slot(0)
+                self.nodes.append(_CopyNode(self, name + ".s0_copy", s0, d0, False))
+                s0 = d0
         d1 = slot(1)
-        self._convbr(name + ".preprocess", cell.preprocess, s1, d1)
+        self._pre(name + ".preprocess", cell.preprocess, s1, sp, d1)
         states = [s0, d1]
         for k, step in enumerate(spec.steps):
             dst = slot(2 + k)
@@ -202,13 +314,59 @@ class TrainPlan:
             n.forward()
         return self.ops.disp_head(self.mat, self.maxdisp)
 
+    def _storage_key(self):
+        return tuple(p.data_ptr() for p in self.param_grads) + tuple(
+            t.data_ptr() for n in self.nodes if isinstance(n, _ConvBRNode) and n.mod.bn.running_mean is not None
+            for t in (n.mod.bn.running_mean, n.mod.bn.running_var, n.mod.bn.num_batches_tracked))
+
+    def run_forward(self, fx: torch.Tensor, fy: torch.Tensor) -> torch.Tensor:
+        """``forward`` - eagerly, or (``use_graph``) as a replay of its captured launch list."""
+        if not self.use_graph:
+            return self.forward(fx, fy)
+        key = self._storage_key()
+        if self._graph_key != key:
+            self._graphs = [None, None]
+            self._eager_calls = [0, 0]
+            self._graph_key = key
+        if self._graphs[0] is None:
+            if self._eager_calls[0] < 2:
+                self._eager_calls[0] += 1
+                return self.forward(fx, fy)
+            self._fx_in, self._fy_in = fx.clone(), fy.clone()
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            gen = self.generation
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._disp_out = self.forward(self._fx_in, self._fy_in)
+            self.generation = gen
+            self._graphs[0] = g
+        self.generation += 1
+        self._fx_in.copy_(fx)
+        self._fy_in.copy_(fy)
+        self._graphs[0].replay()
+        return self._disp_out.clone()
+
+    def run_backward(self, gdisp: torch.Tensor):
+        if not self.use_graph or self._graphs[0] is None:
+            return self.backward(gdisp)
+        if self._graphs[1] is None:
+            if self._eager_calls[1] < 1:
+                self._eager_calls[1] += 1
+                return self.backward(gdisp)
+            self._gdisp_in = gdisp.contiguous().float().clone()
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._bwd_out = self.backward(self._gdisp_in)
+            self._graphs[1] = g
+        self._gdisp_in.copy_(gdisp)
+        self._graphs[1].replay()
+        return self._bwd_out
+
     def backward(self, gdisp: torch.Tensor):
-        self.param_grads = {}
-        for g in self.grads.values():
+        self.pflat.zero_()
+        for g in self.zero_grads:                  # only the volumes the first-writer analysis could not cover
             g.t.zero_()
-        for v in self.values:                      # make sure every value buffer has a (zeroed) gradient buffer
-            if id(v) not in self.grads:
-                self.grad_of(v).t.zero_()
         self.dmat = self.ops.disp_head_bwd(self.mat, gdisp.contiguous().float(), self.maxdisp)
         for n in reversed(self.nodes):
             n.backward()
@@ -217,25 +375,41 @@ class TrainPlan:
 
 
 class _ConvBRNode(_Node):
-    """Conv3d -> BatchNorm3d(train) -> ReLU (flags per module), output optionally accumulated (state sums)."""
+    """Conv3d -> BatchNorm3d(train) -> ReLU (flags per module), output optionally accumulated (state sums).
+    ``upsample_to``: the (1x1x1) conv runs on the low-resolution input and its raw output is interpolated to that size
+    before the batch statistics (TrainPlan._pre)."""
 
-    def __init__(self, plan: TrainPlan, name, mod: ConvBR3d, src: Slice, dst: Slice, accumulate: bool):
+    def __init__(self, plan: TrainPlan, name, mod: ConvBR3d, src: Slice, dst: Slice, accumulate: bool, upsample_to=None):
         self.plan, self.name, self.mod, self.src, self.dst, self.accumulate = plan, name, mod, src, dst, accumulate
         c_out = mod.conv.out_channels
         if not mod.use_bn:
             raise LeaError("%s: ConvBR without BN is only supported as the last_3 head" % name)
-        self.x = Slice(plan.vol(c_out, src.spatial), 0, c_out)        # raw conv output, kept for the backward
-        self.dx = None
-        # per-channel BN vectors and the chunk partials of the reductions: allocated once, filled by kernels
+        self.up = upsample_to is not None
+        self.xl = Slice(plan.vol(c_out, src.spatial), 0, c_out) if self.up else None      # raw conv output, low-res
+        self.x = Slice(plan.vol(c_out, upsample_to if self.up else src.spatial), 0, c_out)  # raw output BN sees (kept)
         dev = plan.device
+        self.dx = Slice(PlanesVol.empty(self.x.vol.B, c_out, plan.P, *self.x.spatial, dev), 0, c_out)
+        self.dxl = Slice(PlanesVol.empty(self.x.vol.B, c_out, plan.P, *src.spatial, dev), 0, c_out) if self.up else None
+        self.dgrad_accumulate = True
+        self.img_f: list = []
+        self.img_b: list = []
+        # per-channel BN vectors and the chunk partials of the reductions: allocated once, filled by kernels
         self.partial = torch.empty((max(64, 1184 // max(1, c_out >> 3)), 2, c_out), dtype=torch.float32, device=dev)
         self.mean, self.invstd, self.scale, self.shift, self.ka, self.kb, self.kc = (
             torch.empty(c_out, dtype=torch.float32, device=dev) for _ in range(7))
 
+    def plan_backward(self, cover: _Coverage):
+        cover.read(self.dst)
+        self.dgrad_accumulate = cover.write(self.src)
+
     def forward(self):
         plan, mod, ops = self.plan, self.mod, self.plan.ops
         c = mod.conv.out_channels
-        plan.conv_raw(self.src, mod.conv.weight.detach(), self.x)
+        if self.up:
+            plan.conv_raw(self.src, mod.conv.weight.detach(), self.xl, images=self.img_f)
+            ops.trilinear_ac(self.xl.vol, 0, c, self.x.vol, 0)
+        else:
+            plan.conv_raw(self.src, mod.conv.weight.detach(), self.x, images=self.img_f)
         n = float(self.x.vol.B * _prod(self.x.spatial))
         bn = mod.bn
         # batch statistics: chunked per-channel sums, then ONE kernel for mean / invstd / scale / shift and the running
@@ -258,28 +432,23 @@ class _ConvBRNode(_Node):
         chunks = ops.channel_reduce_partial(self.x.vol, self.x.c0, c, self.partial, mode=1, dy=dy, dy_c0=self.dst.c0,
                                             relu=mod.relu, scale=self.scale, shift=self.shift, mean=self.mean,
                                             invstd=self.invstd)
-        dgamma = torch.empty(c, dtype=torch.float32, device=plan.device) if mod.bn.weight.requires_grad else None
-        dbeta = torch.empty(c, dtype=torch.float32, device=plan.device) if mod.bn.bias.requires_grad else None
         ops.bn_bwd_coeffs(self.partial, chunks, c, n, mod.bn.weight.detach(), self.invstd, self.ka, self.kb, self.kc,
-                          dgamma, dbeta)
-        if dgamma is not None:
-            plan.add_param_grad(mod.bn.weight, dgamma)
-        if dbeta is not None:
-            plan.add_param_grad(mod.bn.bias, dbeta)
-        if self.dx is None:
-            self.dx = Slice(PlanesVol.empty(self.x.vol.B, c, plan.P, *self.x.spatial, plan.device), 0, c)
+                          plan.param_grads.get(mod.bn.weight), plan.param_grads.get(mod.bn.bias), accumulate=True)
         ops.bn_relu_bwd(self.x.vol, self.x.c0, dy, self.dst.c0, self.dx.vol, 0, c, mod.relu, self.scale, self.shift,
                         self.mean, self.invstd, self.ka, self.kb, self.kc)
+        dconv = self.dx
+        if self.up:                                # through the interpolation: gradient of the low-res raw output
+            ops.trilinear_ac_bwd(self.dx.vol, 0, self.dxl.vol, 0, c, accumulate=False)
+            dconv = self.dxl
         w = mod.conv.weight.detach()
-        if mod.conv.weight.requires_grad:
-            dw = torch.zeros_like(w, dtype=torch.float32)
-            ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dx.vol, 0, c, k, dw,
+        dw = plan.param_grads.get(mod.conv.weight)
+        if dw is not None:
+            ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, dconv.vol, 0, c, k, dw,
                              tensor_cores=(plan.conv_mode == "tc"))
-            plan.add_param_grad(mod.conv.weight, dw)
-        # data gradient: conv with transposed, tap-flipped weights, accumulated into the input's gradient
-        wt = w.flip(2, 3, 4).transpose(0, 1).contiguous()
+        # data gradient: conv with transposed, tap-flipped weights into the input's gradient (first writer overwrites)
         dsrc = plan.grad_of(self.src.vol)
-        plan.conv_raw(self.dx, wt, Slice(dsrc, self.src.c0, self.src.c), accumulate=True)
+        plan.conv_raw(dconv, None, Slice(dsrc, self.src.c0, self.src.c), accumulate=self.dgrad_accumulate,
+                      dgrad_of=w.contiguous(), images=self.img_b)
 
 
 class _Last3Node(_Node):
@@ -288,6 +457,14 @@ class _Last3Node(_Node):
     def __init__(self, plan: TrainPlan, name, mod: ConvBR3d, src: Slice):
         self.plan, self.name, self.mod, self.src = plan, name, mod, src
         self.dpad = None
+        self.dgrad_accumulate = True
+        B, (D, H, W) = plan.B, plan.spatial
+        self.dm8 = torch.zeros((B, 8, D, H, W), dtype=torch.float32, device=plan.device)   # channel 0 = dmat, rest 0
+        w = mod.conv.weight
+        self.wt = torch.zeros((w.shape[1], 8, 3, 3, 3), dtype=torch.float32, device=plan.device)
+
+    def plan_backward(self, cover: _Coverage):
+        self.dgrad_accumulate = cover.write(self.src)
 
     def forward(self):
         self.plan.conv_raw(self.src, self.mod.conv.weight.detach(), None, dst_f32=self.plan.mat)
@@ -295,23 +472,25 @@ class _Last3Node(_Node):
     def backward(self):
         plan, mod, ops = self.plan, self.mod, self.plan.ops
         w = mod.conv.weight.detach()                                  # (1, C, 3, 3, 3)
-        B, _, D, H, W = plan.mat.shape
-        dm8 = torch.zeros((B, 8, D, H, W), dtype=torch.float32, device=plan.device)
-        dm8[:, 0] = plan.dmat
-        self.dpad = ops.pack(dm8, plan.P, out=self.dpad)
-        if mod.conv.weight.requires_grad:
-            dw = torch.zeros_like(w, dtype=torch.float32)
+        self.dm8[:, 0].copy_(plan.dmat.reshape(self.dm8[:, 0].shape))
+        self.dpad = ops.pack(self.dm8, plan.P, out=self.dpad)
+        dw = plan.param_grads.get(mod.conv.weight)
+        if dw is not None:
             ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dpad, 0, 1, 3, dw)
-            plan.add_param_grad(mod.conv.weight, dw)
-        wt = torch.zeros((w.shape[1], 8, 3, 3, 3), dtype=torch.float32, device=plan.device)
-        wt[:, 0] = w.flip(2, 3, 4)[0]
+        self.wt[:, 0].copy_(w.flip(2, 3, 4)[0])
         dsrc = plan.grad_of(self.src.vol)
-        plan.conv_raw(Slice(self.dpad, 0, 8), wt, Slice(dsrc, self.src.c0, self.src.c), accumulate=True)
+        plan.conv_raw(Slice(self.dpad, 0, 8), self.wt, Slice(dsrc, self.src.c0, self.src.c),
+                      accumulate=self.dgrad_accumulate)
 
 
 class _ResampleNode(_Node):
     def __init__(self, plan: TrainPlan, name, src: Slice, dst: Slice):
         self.plan, self.name, self.src, self.dst = plan, name, src, dst
+        self.accumulate = True
+
+    def plan_backward(self, cover: _Coverage):
+        cover.read(self.dst)
+        self.accumulate = cover.write(self.src)
 
     def forward(self):
         self.plan.ops.trilinear_ac(self.src.vol, self.src.c0, self.src.c, self.dst.vol, self.dst.c0)
@@ -319,7 +498,7 @@ class _ResampleNode(_Node):
     def backward(self):
         plan = self.plan
         plan.ops.trilinear_ac_bwd(plan.grad_of(self.dst.vol), self.dst.c0, plan.grad_of(self.src.vol), self.src.c0,
-                                  self.src.c)
+                                  self.src.c, accumulate=self.accumulate)
 
 
 class _CopyNode(_Node):
@@ -327,6 +506,11 @@ class _CopyNode(_Node):
 
     def __init__(self, plan: TrainPlan, name, src: Slice, dst: Slice, accumulate: bool):
         self.plan, self.name, self.src, self.dst, self.accumulate = plan, name, src, dst, accumulate
+        self.bwd_accumulate = True
+
+    def plan_backward(self, cover: _Coverage):
+        cover.read(self.dst)
+        self.bwd_accumulate = cover.write(self.src)
 
     def forward(self):
         self.plan.ops.affine_relu(self.src.vol, self.src.c0, self.dst.vol, self.dst.c0, self.src.c, None, None, False,
@@ -335,7 +519,7 @@ class _CopyNode(_Node):
     def backward(self):
         plan = self.plan
         plan.ops.affine_relu(plan.grad_of(self.dst.vol), self.dst.c0, plan.grad_of(self.src.vol), self.src.c0,
-                             self.src.c, None, None, False, True)
+                             self.src.c, None, None, False, self.bwd_accumulate)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -365,7 +549,7 @@ class _HotPathTrainFn(torch.autograd.Function):
         ctx.plan = plan
         ctx.params = params
         with torch.no_grad():
-            disp = plan.forward(fx.detach().float().contiguous(), fy.detach().float().contiguous())
+            disp = plan.run_forward(fx.detach().float().contiguous(), fy.detach().float().contiguous())
         ctx.generation = plan.generation
         return disp
 
@@ -379,7 +563,7 @@ class _HotPathTrainFn(torch.autograd.Function):
                                "overwritten by a later forward through the same module (one forward may be "
                                "outstanding per module; call backward() before the next train-mode forward)")
         with torch.no_grad():
-            dfx, dfy, pg = plan.backward(gdisp)
+            dfx, dfy, pg = plan.run_backward(gdisp)
         grads = []
         for p in ctx.params:
             g = pg.get(p)
@@ -407,6 +591,7 @@ def hot_path_train_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optio
         _TRAIN_PLANS.clear()                       # one live training plan: buffers are large
         plan = TrainPlan(model.matching, ops, B, (D3, H3, W3), planes, fx.device, conv, model.maxdisp)
         _TRAIN_PLANS[key] = plan
+    plan.use_graph = bool(opt.get("train_graph", True)) and ops.device_build and fx.is_cuda
     params = used_parameters(plan)
     # the BN kernels update running_mean / running_var / num_batches_tracked through raw pointers (no autograd version
     # bump): tell the eval-mode plans that parameters changed

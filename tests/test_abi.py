@@ -31,7 +31,7 @@ def test_header_symbols_exported(lib_path):
 
 def test_library_identity(lib_path):
     lib = ctypes.CDLL(lib_path)
-    assert lib.lea_abi_version() == 2
+    assert lib.lea_abi_version() == 3
     assert lib.lea_is_device_build() == 1
 
 

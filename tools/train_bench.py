@@ -11,7 +11,7 @@ from leastereo_b200.pipeline import FlatAdam, masked_smooth_l1_loss
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4); ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=1); ap.add_argument("--h", type=int, default=288)
+    ap.add_argument("--warmup", type=int, default=5); ap.add_argument("--h", type=int, default=288)
     ap.add_argument("--w", type=int, default=576); ap.add_argument("--conv", default="tc")
     ap.add_argument("--torch-optim", action="store_true", help="torch smooth_l1 + torch.optim.Adam instead of our kernels")
     a = ap.parse_args()

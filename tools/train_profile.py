@@ -23,7 +23,9 @@ def step():
     loss = torch.nn.functional.smooth_l1_loss(disp[mask], target[mask])
     loss.backward()
 
-step(); torch.cuda.synchronize()
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step(); torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=70))
