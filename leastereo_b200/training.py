@@ -462,6 +462,10 @@ class _Last3Node(_Node):
         self.dm8 = torch.zeros((B, 8, D, H, W), dtype=torch.float32, device=plan.device)   # channel 0 = dmat, rest 0
         w = mod.conv.weight
         self.wt = torch.zeros((w.shape[1], 8, 3, 3, 3), dtype=torch.float32, device=plan.device)
+        # weight gradient on the tensor-core kernel with the output gradient padded to 8 channels (row 0 is last_3's)
+        self.wg_tc = (plan.conv_mode == "tc" and plan.ops.device_build and plan.P == 2 and
+                      bool(plan.ops.lib.lea_conv3d_wgrad_tc_supported(int(w.shape[1]), 8, 3, plan.P)))
+        self.dw8 = torch.zeros((8,) + tuple(w.shape[1:]), dtype=torch.float32, device=plan.device) if self.wg_tc else None
 
     def plan_backward(self, cover: _Coverage):
         self.dgrad_accumulate = cover.write(self.src)
@@ -475,7 +479,11 @@ class _Last3Node(_Node):
         self.dm8[:, 0].copy_(plan.dmat.reshape(self.dm8[:, 0].shape))
         self.dpad = ops.pack(self.dm8, plan.P, out=self.dpad)
         dw = plan.param_grads.get(mod.conv.weight)
-        if dw is not None:
+        if dw is not None and self.wg_tc:
+            self.dw8.zero_()
+            ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dpad, 0, 8, 3, self.dw8, tensor_cores=True)
+            dw.add_(self.dw8[0:1])
+        elif dw is not None:
             ops.conv3d_wgrad(self.src.vol, self.src.c0, self.src.c, self.dpad, 0, 1, 3, dw)
         self.wt[:, 0].copy_(w.flip(2, 3, 4)[0])
         dsrc = plan.grad_of(self.src.vol)

@@ -33,15 +33,17 @@ def test_train_step_fp32_simt(ops):
 
 
 def test_train_step_tensor_core(ops):
-    # tensor-core forward + data-gradient convs on 2-plane storage: gradients agree to the bf16x3 noise level
-    print("tc/P=2 train step vs autograd:", check_train_step(ops, DEV, planes=2, conv="tc", tol=2e-2, grad_tol=1e-1))
+    # tensor-core forward + data-gradient + weight-gradient kernels on 2-plane storage.  Measured (B200): relative L2
+    # error of d/dfx 0.019, median over the parameter tensors 0.017, worst tensor 0.049 - the fp32 SIMT path shows the
+    # same worst tensor at the same 0.049 (a BN bias whose gradient nearly cancels; ReLU-mask flips), cosine 0.9998.
+    print("tc/P=2 train step vs autograd:", check_train_step(ops, DEV, planes=2, conv="tc", tol=2e-2, grad_tol=3e-2))
 
 
 def test_train_step_skip_connect_genotype(ops):
     """3D genotype with skip_connect ops (operations_3d.py:84-104): Identity forward/backward on the GPU kernels."""
     print("skip genotype, simt/P=3:", check_train_step(ops, DEV, planes=3, conv="simt", tol=2e-3, grad_tol=3e-2,
                                                        name="cal_skip_b2_24x48_d24"))
-    print("skip genotype, tc/P=2:", check_train_step(ops, DEV, planes=2, conv="tc", tol=2e-2, grad_tol=1e-1,
+    print("skip genotype, tc/P=2:", check_train_step(ops, DEV, planes=2, conv="tc", tol=2e-2, grad_tol=3e-2,
                                                      name="cal_skip_b2_24x48_d24"))
 
 
