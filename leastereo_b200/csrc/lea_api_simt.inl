@@ -249,7 +249,7 @@ extern "C" int lea_feature_stem(const float* img, int32_t B, int32_t H, int32_t 
     LEA_CHECK(dst->B == B && dst->D == 1 && dst->H == (H - 1) / 3 + 1 && dst->W == (W - 1) / 3 + 1,
               "feature_stem: output volume must be (B, c, 1, ceil(H/3), ceil(W/3))");
     LEA_CHECK(dst->H <= 65535 && B <= 65535, "feature_stem: grid too large");
-    LEA_LAUNCH(lea_feature_stem_kernel, dim3((dst->W + 127) / 128, dst->H, B), dim3(128), 0, stream,
+    LEA_LAUNCH(lea_feature_stem_kernel, dim3((dst->W + 255) / 256, dst->H, B), dim3(128), 0, stream,
                img, H, W, w0, scale0, shift0, c_mid, w1, scale1, shift1, c_out, *dst, dst_c0);
     return LEA_POST_LAUNCH();
 }

@@ -1008,68 +1008,88 @@ lea_feature_stem_kernel(const float* __restrict__ img, int H, int W,
     if (tid < LEA_FS_MAXMID) { bn0[tid] = tid < c_mid ? sc0[tid] : 0.0f; bn0[LEA_FS_MAXMID + tid] = tid < c_mid ? sh0[tid] : 0.0f; }
     if (tid < LEA_FS_MAXOUT) { bn1[tid] = tid < c_out ? sc1[tid] : 0.0f; bn1[LEA_FS_MAXOUT + tid] = tid < c_out ? sh1[tid] : 0.0f; }
     __syncthreads();
-    const int w3 = blockIdx.x * 128 + tid;
+    // Two horizontally adjacent stem1 pixels per thread: every weight vector fetched from shared memory (one LDS.128
+    // per 4 FMAs in the one-pixel version, which made the kernel shared-memory-issue bound at 12 TFLOP/s) feeds both.
+    // The image is walked one stem0 row (= 3 image rows x 8 columns x 3 channels in registers) at a time.
+    const int w3 = (blockIdx.x * 128 + tid) * 2;
     const int h3 = blockIdx.y, b = blockIdx.z;
     if (w3 >= dst.W) return;
-    // 5x5x3 image patch around (3*h3, 3*w3), zero outside the image
-    float patch[3][5][5];
+    const bool two = w3 + 1 < dst.W;
     const float* __restrict__ ib = img + (int64_t)b * 3 * H * W;
+    float acc[2][LEA_FS_MAXOUT];
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
+    for (int p = 0; p < 2; ++p)
 #pragma unroll
-        for (int a = 0; a < 5; ++a)
+        for (int o = 0; o < LEA_FS_MAXOUT; ++o) acc[p][o] = 0.0f;
+#pragma unroll 1
+    for (int ij = 0; ij < 9; ++ij) {             // one stem1 tap at a time (kept rolled: the unrolled body spilled)
+        const int i = ij / 3, j = ij - 3 * i;
+        const int py = 3 * h3 - 1 + i;                                   // stem0 row feeding taps (i, .) of stem1
+        if (py < 0 || py >= H) continue;                                 // stem1's zero padding (uniform per block)
+        {
+            float im[3][3][6];                   // [channel][image row py-1+a][column 3*w3-2+j+x]: both pixels' 3x3 windows
 #pragma unroll
-            for (int e = 0; e < 5; ++e) {
-                const int y = 3 * h3 - 2 + a, x = 3 * w3 - 2 + e;
-                patch[c][a][e] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(ib + ((int64_t)c * H + y) * W + x) : 0.0f;
-            }
-    float acc[LEA_FS_MAXOUT];
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-    for (int o = 0; o < LEA_FS_MAXOUT; ++o) acc[o] = 0.0f;
+                for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+                    for (int x = 0; x < 6; ++x) {
+                        const int y = py - 1 + a, xx = 3 * w3 - 2 + j + x;
+                        im[c][a][x] = (y >= 0 && y < H && xx >= 0 && xx < W) ? __ldg(ib + ((int64_t)c * H + y) * W + xx) : 0.0f;
+                    }
+            const int px0 = 3 * w3 - 1 + j, px1 = px0 + 3;               // stem0 columns of the two pixels
+            const bool ok0 = px0 >= 0 && px0 < W, ok1 = two && px1 < W;
+            float mid[2][LEA_FS_MAXMID];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int py = 3 * h3 - 1 + i, px = 3 * w3 - 1 + j;          // stem0 pixel feeding tap (i, j) of stem1
-            if (py < 0 || py >= H || px < 0 || px >= W) continue;        // stem1's zero padding
-            float mid[LEA_FS_MAXMID];
-#pragma unroll
-            for (int m = 0; m < LEA_FS_MAXMID; ++m) mid[m] = 0.0f;
+            for (int m = 0; m < LEA_FS_MAXMID; ++m) { mid[0][m] = 0.0f; mid[1][m] = 0.0f; }
 #pragma unroll
             for (int c = 0; c < 3; ++c)
 #pragma unroll
                 for (int a = 0; a < 3; ++a)
 #pragma unroll
                     for (int e = 0; e < 3; ++e) {
-                        const float v = patch[c][i + a][j + e];
+                        const float v0 = im[c][a][e], v1 = im[c][a][3 + e];
                         const float4* wr = reinterpret_cast<const float4*>(w0s + (c * 9 + a * 3 + e) * LEA_FS_MAXMID);
 #pragma unroll
                         for (int m4 = 0; m4 < LEA_FS_MAXMID / 4; ++m4) {
                             const float4 q = wr[m4];
-                            mid[m4 * 4 + 0] += v * q.x; mid[m4 * 4 + 1] += v * q.y;
-                            mid[m4 * 4 + 2] += v * q.z; mid[m4 * 4 + 3] += v * q.w;
+                            mid[0][m4 * 4 + 0] += v0 * q.x; mid[0][m4 * 4 + 1] += v0 * q.y;
+                            mid[0][m4 * 4 + 2] += v0 * q.z; mid[0][m4 * 4 + 3] += v0 * q.w;
+                            mid[1][m4 * 4 + 0] += v1 * q.x; mid[1][m4 * 4 + 1] += v1 * q.y;
+                            mid[1][m4 * 4 + 2] += v1 * q.z; mid[1][m4 * 4 + 3] += v1 * q.w;
                         }
                     }
 #pragma unroll
             for (int m = 0; m < LEA_FS_MAXMID; ++m) {
-                float t = mid[m] * bn0[m] + bn0[LEA_FS_MAXMID + m];
-                t = t > 0.0f ? t : 0.0f;
+                float t0 = mid[0][m] * bn0[m] + bn0[LEA_FS_MAXMID + m];
+                float t1 = mid[1][m] * bn0[m] + bn0[LEA_FS_MAXMID + m];
+                t0 = (ok0 && t0 > 0.0f) ? t0 : 0.0f;                     // outside the image: stem1's zero padding
+                t1 = (ok1 && t1 > 0.0f) ? t1 : 0.0f;
                 const float4* wr = reinterpret_cast<const float4*>(w1s + ((i * 3 + j) * LEA_FS_MAXMID + m) * LEA_FS_MAXOUT);
 #pragma unroll
                 for (int o4 = 0; o4 < LEA_FS_MAXOUT / 4; ++o4) {
                     const float4 q = wr[o4];
-                    acc[o4 * 4 + 0] += t * q.x; acc[o4 * 4 + 1] += t * q.y;
-                    acc[o4 * 4 + 2] += t * q.z; acc[o4 * 4 + 3] += t * q.w;
+                    acc[0][o4 * 4 + 0] += t0 * q.x; acc[0][o4 * 4 + 1] += t0 * q.y;
+                    acc[0][o4 * 4 + 2] += t0 * q.z; acc[0][o4 * 4 + 3] += t0 * q.w;
+                    acc[1][o4 * 4 + 0] += t1 * q.x; acc[1][o4 * 4 + 1] += t1 * q.y;
+                    acc[1][o4 * 4 + 2] += t1 * q.z; acc[1][o4 * 4 + 3] += t1 * q.w;
                 }
             }
         }
     }
 #pragma unroll
-    for (int o = 0; o < LEA_FS_MAXOUT; ++o) {
-        const float t = acc[o] * bn1[o] + bn1[LEA_FS_MAXOUT + o];
-        acc[o] = t > 0.0f ? t : 0.0f;
-    }
+    for (int p = 0; p < 2; ++p) {
+        if (p == 0 || two) {
 #pragma unroll
-    for (int cb = 0; cb < LEA_FS_MAXOUT / 8; ++cb)
-        if (cb * 8 < c_out) lea_vol_store8(dst, b, (dst_c0 >> 3) + cb, 0, h3, w3, acc + cb * 8);
+            for (int cb = 0; cb < LEA_FS_MAXOUT / 8; ++cb) {
+                float out[8];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) {
+                    const float t = acc[p][cb * 8 + o] * bn1[cb * 8 + o] + bn1[LEA_FS_MAXOUT + cb * 8 + o];
+                    out[o] = t > 0.0f ? t : 0.0f;
+                }
+                if (cb * 8 < c_out) lea_vol_store8(dst, b, (dst_c0 >> 3) + cb, 0, h3, w3 + p, out);
+            }
+        }
+    }
 }
