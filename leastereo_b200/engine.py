@@ -965,9 +965,35 @@ def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[O
         return None
     fplan.img[:B].copy_(left.detach().float())
     fplan.img[B:].copy_(right.detach().float())
-    fplan.run(check_params=not opt["assume_frozen"])
-    mat = plan.run(check_params=not opt["assume_frozen"])
-    return ops.disp_head(mat, model.maxdisp)
+    if not (opt.get("cuda_graph", True) and left.is_cuda) or torch.cuda.is_current_stream_capturing():
+        fplan.run(check_params=not opt["assume_frozen"])
+        mat = plan.run(check_params=not opt["assume_frozen"])
+        return ops.disp_head(mat, model.maxdisp)
+    # The module replays its own CUDA graph of the ~160 launches (predict.py-style callers get the graph's rate without
+    # writing capture code: the eager launch list is host-bound at small batches - 164 against 209 pairs/s at batch 1).
+    # Parameters are checked on the host before every replay; the packed weight images and BN vectors are rewritten in
+    # place, and a change of the parameter key (values or storage) drops the graph so that raw weight pointers recorded
+    # in it can never go stale.  Two eager calls first (allocations, lazily built tensor maps).
+    st = fplan.__dict__.setdefault("_graph", {"calls": 0, "graph": None, "out": None, "keys": None})
+    if not opt["assume_frozen"] or plan._param_key is None or fplan._param_key is None:
+        fplan.refresh_params()
+        plan.refresh_params()
+    keys = (fplan._param_key, plan._param_key)
+    if st["graph"] is not None and st["keys"] != keys:
+        st["graph"], st["out"] = None, None
+    if st["graph"] is None:
+        st["calls"] += 1
+        if st["calls"] <= 2:
+            fplan.run(check_params=False)
+            return ops.disp_head(plan.run(check_params=False), model.maxdisp)
+        torch.cuda.synchronize(left.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            fplan.run(check_params=False)
+            st["out"] = ops.disp_head(plan.run(check_params=False), model.maxdisp)
+        st["graph"], st["keys"] = g, keys
+    st["graph"].replay()
+    return st["out"].clone()
 
 
 def matching_forward(matching: newMatching, x: torch.Tensor, ops: Optional[Ops] = None,

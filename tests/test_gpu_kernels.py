@@ -295,6 +295,34 @@ def test_full_forward_native_vs_golden(ops, name):
     assert rep["ok"], rep
 
 
+def test_module_owned_cuda_graph(ops):
+    """LEAStereo.forward replays its own CUDA graph from the third call on (engine option cuda_graph, default on): same
+    bits as the eager launch list, fresh inputs honoured, in-place parameter changes picked up, no aliasing of results."""
+    g = load_golden("cal_48x96_d48")
+    model = K.seeded_model(int(g["maxdisp"]))
+    model.load_state_dict(K.golden_state_dict(g, model))
+    model = model.to(DEV).eval()
+    left, right = torch.from_numpy(g["left"]).to(DEV), torch.from_numpy(g["right"]).to(DEV)
+    from leastereo_b200 import engine
+    with torch.no_grad():
+        model.engine_options = {"cuda_graph": False}
+        eager = model(left, right).clone()
+        eager_swapped = model(right, left).clone()
+        model.engine_options = {}
+        outs = [model(left, right) for _ in range(5)]
+        fplan = [p for p in engine._plans(model.feature).values() if isinstance(p, engine.FeaturePlan)][-1]
+        assert fplan.__dict__["_graph"]["graph"] is not None, "the module did not capture its graph"
+        for o in outs:
+            assert torch.equal(o, eager)
+        swapped = model(right, left)                       # new input values through the static buffers
+        assert torch.equal(swapped, eager_swapped) and torch.equal(outs[-1], eager)     # earlier results are not aliased
+        model.matching.stem1.conv.weight.mul_(1.25)         # parameters changed in place: re-packed, graph re-captured
+        changed = model(left, right)
+        model.engine_options = {"cuda_graph": False}
+        want = model(left, right)
+    assert not torch.equal(changed, eager) and torch.equal(changed, want)
+
+
 # ---- callers on either side of the path (SURVEY 8f rows 2-4) ------------------------------------------------
 def test_normalize_pad(ops):
     K.check_normalize_pad(ops, DEV)

@@ -1,4 +1,4 @@
-"""Throughput of the other BASELINE.json inference configs (device-resident, CUDA events, eager launches):
+"""Throughput of the other BASELINE.json inference configs (device-resident, CUDA events, through LEAStereo.forward = the module-owned CUDA graph):
    configs[1] SceneFlow 576x960 D=192 batch 8, configs[2] KITTI 384x1248 batch sweep, configs[3] Middlebury half-res
    1008x1512 D=408.  Prints one JSON line per case; bench.py remains the contract benchmark (KITTI, 4 pairs/step)."""
 import contextlib, io, json, os, sys
@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 from leastereo_b200 import LEAStereo, default_args  # noqa: E402
 
 
-def run(name, H, W, maxdisp, B, steps=5, warmup=2):
+def run(name, H, W, maxdisp, B, steps=5, warmup=4):     # the module captures its CUDA graph on the third call
     dev = torch.device("cuda:0")
     torch.cuda.empty_cache(); torch.cuda.reset_peak_memory_stats()
     torch.manual_seed(0)
