@@ -45,10 +45,11 @@ namespace {
 __host__ __device__ constexpr int epi_warps(int planes) { return planes == 3 ? 4 : 4; }
 __host__ __device__ constexpr int tc_threads(int planes) { return 64 + 32 * epi_warps(planes); }
 constexpr int kMaxTerms = 6;
+constexpr int kMaxSets = 8;      // TMEM accumulator sets (work items in flight between the issuer and the epilogue)
 constexpr int kMaxStages = 24;   // deep enough that 8 KB 1x1x1 stages keep ~1.5 us of HBM latency covered
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kHeaderBytes = 2048;
-static_assert(8 * (2 * kMaxStages + 8) <= 1024, "barriers must fit below the BN vectors at byte 1024");
+static_assert(8 * (2 * kMaxStages + 4 + 2 * kMaxSets) <= 1024, "barriers must fit below the BN vectors at byte 1024");
 #ifdef LEA_TC_SOFT_TIMEOUT
 constexpr unsigned long long kWaitTimeoutCycles = 100000000ull;
 #else
@@ -71,6 +72,7 @@ struct TcParams {
     int ncg, blocks_per_cg;
     int ks, taps;
     int tiles_w, tiles_h, dchunks, Dc, total_items;
+    int step_tw, step_th, step_dc, step_b;   // mixed-radix digits of the grid stride (ItemCursor)
     int NP, c_out, ngroups;   // padded N, real c_out, TMEM regions (weight planes) summed by the epilogue
     int nterm;
     int term_aoff[kMaxTerms], term_lbo_blocks[kMaxTerms], term_btile[kMaxTerms], term_region[kMaxTerms];
@@ -129,9 +131,15 @@ __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
     return ok;
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int code) {
+#ifdef LEA_TC_SPIN
+    if (mbar_test(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_test(bar, parity)) {
+#else
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#endif
         if (clock64() - t0 > kWaitTimeoutCycles) {
 #ifdef LEA_TC_SOFT_TIMEOUT
             atomicCAS(&g_lea_tc_status, 0, code * 1000 + (int)(threadIdx.x));   // debug build: record the first stuck wait, go on
@@ -173,13 +181,36 @@ __device__ __host__ __forceinline__ uint32_t make_idesc(int n) {
 }
 
 struct ItemGeom { int b, d0, d_hi, h0, w0, dlo, dhi; };
-__device__ __forceinline__ ItemGeom decode_item(const TcParams& p, int item) {
+// Work items are numbered (b, depth chunk, h tile, w tile) and a CTA takes every gridDim.x-th one.  The mixed-radix
+// digits of the current item are carried along and advanced by the digits of the stride (computed by the host) instead
+// of being re-derived with three integer divisions per item and role: with depth-1 volumes (the 2-D feature net) an item
+// is a single slab and those dependent divisions were a large part of the ~1400 cycles every item cost each role.
+struct ItemCursor {
+    int tw, th, dc, b;
+    __device__ __forceinline__ void init(const TcParams& p, int item) {
+        int r = item;
+        tw = r % p.tiles_w; r /= p.tiles_w;
+        th = r % p.tiles_h; r /= p.tiles_h;
+        dc = r % p.dchunks; r /= p.dchunks;
+        b = r;
+    }
+    __device__ __forceinline__ void next(const TcParams& p) {
+        tw += p.step_tw;
+        int carry = tw >= p.tiles_w ? 1 : 0;
+        tw -= carry ? p.tiles_w : 0;
+        th += p.step_th + carry;
+        carry = th >= p.tiles_h ? 1 : 0;
+        th -= carry ? p.tiles_h : 0;
+        dc += p.step_dc + carry;
+        carry = dc >= p.dchunks ? 1 : 0;
+        dc -= carry ? p.dchunks : 0;
+        b += p.step_b + carry;
+    }
+};
+__device__ __forceinline__ ItemGeom decode_item(const TcParams& p, const ItemCursor& c) {
     ItemGeom g;
-    int r = item;
-    const int tw = r % p.tiles_w; r /= p.tiles_w;
-    const int th = r % p.tiles_h; r /= p.tiles_h;
-    const int dc = r % p.dchunks; r /= p.dchunks;
-    g.b = r;
+    const int tw = c.tw, th = c.th, dc = c.dc;
+    g.b = c.b;
     g.d0 = dc * p.Dc;
     g.d_hi = min(g.d0 + p.Dc, p.D);
     g.h0 = th * (128 >> p.tw_log2); g.w0 = tw << p.tw_log2;
@@ -374,8 +405,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint64_t* empty = bars + kMaxStages;            // [kMaxStages]
     uint64_t* wfull = bars + 2 * kMaxStages;        // [2]
     uint64_t* wempty = wfull + 2;                   // [2]
-    uint64_t* accfull = wempty + 2;                 // [2]
-    uint64_t* accempty = accfull + 2;               // [2]
+    uint64_t* accfull = wempty + 2;                 // [kMaxSets]
+    uint64_t* accempty = accfull + kMaxSets;        // [kMaxSets]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1536);
     float* s_scale = reinterpret_cast<float*>(smem + 1024);     // [64]  (barriers occupy the first KB)
     float* s_shift = s_scale + 64;                              // [64]
@@ -392,8 +423,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1); }
+        for (int i = 0; i < kMaxSets; ++i) {
             mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 32 * epi_warps(PL));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -426,8 +457,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     bulk_load(smem_u32(wbuf + (size_t)cg * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
                               (uint32_t)p.wpart_bytes, smem_u32(wfull));
             }
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const ItemGeom g = decode_item(p, item);
+            ItemCursor cur;
+            cur.init(p, blockIdx.x);
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, cur.next(p)) {
+                const ItemGeom g = decode_item(p, cur);
                 if (item_skipped(p, g)) continue;
                 const int gbase = g.b * p.g0_stride_b + p.g0_first;
                 for (int cg = 0; cg < p.ncg; ++cg) {
@@ -482,8 +515,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
                                  // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
         if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const ItemGeom g = decode_item(p, item);
+        ItemCursor cur;
+        cur.init(p, blockIdx.x);
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, cur.next(p)) {
+            const ItemGeom g = decode_item(p, cur);
             if (item_skipped(p, g)) continue;
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
             ++it;
@@ -575,8 +610,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int lh = m >> p.tw_log2, lw = m & ((1 << p.tw_log2) - 1);
         const int64_t sp = (int64_t)p.D * p.H * p.W;
         int it = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const ItemGeom g = decode_item(p, item);
+        ItemCursor cur;
+        cur.init(p, blockIdx.x);
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, cur.next(p)) {
+            const ItemGeom g = decode_item(p, cur);
             if (item_skipped(p, g)) continue;
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
             ++it;
@@ -996,6 +1033,15 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     }
     if (opts && opts->depth_chunk > 0) Dc = opts->depth_chunk < dc_max ? opts->depth_chunk : dc_max;
     p.Dc = Dc;
+    // Short items (depth-1 volumes of the 2-D feature net, thin depth chunks): the accumulator hand-over between issuer
+    // and epilogue (tcgen05.commit -> epilogue -> arrive -> issuer) is a ~2600-cycle round trip that bounds the item rate
+    // at nsets items per round trip, whatever the work (measured: 1.07 us per item with neither MMAs nor epilogue work at
+    // two sets).  TMEM columns the depth chunk leaves unused therefore become further accumulator sets.
+    if (!(opts && (opts->acc_sets == 1 || opts->acc_sets == 2))) {
+        int more = 512 / (accw * Dc);
+        if (more > kMaxSets) more = kMaxSets;
+        if (more > p.nsets) p.nsets = more;
+    }
     p.dchunks = (p.D + Dc - 1) / Dc;
     const int64_t total = (int64_t)p.B * p.dchunks * p.tiles_h * p.tiles_w;
     LEA_CHECK(total < (1ll << 31), "conv3d_tc: too many work items");
@@ -1042,6 +1088,13 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
+    {
+        int r = grid;
+        p.step_tw = r % p.tiles_w; r /= p.tiles_w;
+        p.step_th = r % p.tiles_h; r /= p.tiles_h;
+        p.step_dc = r % p.dchunks; r /= p.dchunks;
+        p.step_b = r;
+    }
     // always request the full budget so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
     // programmatic stream serialization (see the kernel's prologue): opt-in with LEA_TC_PDL=1.  Measured inside the CUDA
     // graph of the KITTI step: 196.0 pairs/s with, 196.1 without - launch gaps are not what the step loses.
