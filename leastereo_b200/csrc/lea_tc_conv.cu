@@ -96,6 +96,20 @@ struct TcParams {
 };
 
 __device__ int g_lea_tc_status;
+#ifdef LEA_TC_ABLATION
+// development profile of CTA 0 (ablation builds only): per role [loop cycles, cycles inside barrier waits, items]
+__device__ long long g_lea_tc_prof[12];
+#define TC_PROF_DECL long long prof_t0 = clock64(), prof_wait = 0, prof_items = 0
+#define TC_PROF_WAIT(stmt) { const long long w0_ = clock64(); stmt; prof_wait += clock64() - w0_; }
+#define TC_PROF_ITEM ++prof_items
+#define TC_PROF_END(role) if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { g_lea_tc_prof[(role) * 3] = clock64() - prof_t0; \
+        g_lea_tc_prof[(role) * 3 + 1] = prof_wait; g_lea_tc_prof[(role) * 3 + 2] = prof_items; }
+#else
+#define TC_PROF_DECL
+#define TC_PROF_WAIT(stmt) stmt
+#define TC_PROF_ITEM
+#define TC_PROF_END(role)
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -451,6 +465,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         // ================= TMA producer =================
         if (lane == 0) {
             int stage = 0, sphase = 0, wb = 0, wphase = 0;
+            TC_PROF_DECL;
             if (p.wres) {                         // all weight parts fit: load them once, they stay for every item
                 mbar_arrive_expect_tx(smem_u32(wfull), (uint32_t)(p.ncg * p.wpart_bytes));
                 for (int cg = 0; cg < p.ncg; ++cg)
@@ -465,14 +480,14 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 const int gbase = g.b * p.g0_stride_b + p.g0_first;
                 for (int cg = 0; cg < p.ncg; ++cg) {
                     if (!p.wres) {
-                        mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101);
+                        TC_PROF_WAIT(mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101));
                         mbar_arrive_expect_tx(smem_u32(wfull + wb), (uint32_t)p.wpart_bytes);
                         bulk_load(smem_u32(wbuf + (size_t)wb * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
                                   (uint32_t)p.wpart_bytes, smem_u32(wfull + wb));
                         if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
                     }
                     for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
-                        mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102);
+                        TC_PROF_WAIT(mbar_wait(smem_u32(empty + stage), sphase ^ 1, 102));
                         mbar_arrive_expect_tx(smem_u32(full + stage), (uint32_t)p.stage_bytes);
                         if (p.fused_cv) {
                             // cost volume built by the loader: disparity d_in selects the tensor map; the map's
@@ -489,7 +504,9 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                     }
                 }
+                TC_PROF_ITEM;
             }
+            TC_PROF_END(0);
         }
     } else if (warp == 1) {
         // ================= MMA issuer: the whole warp walks the loop (warp-uniform descriptor arithmetic),
@@ -514,6 +531,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
         uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
                                  // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
+        TC_PROF_DECL;
         if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
         ItemCursor cur;
         cur.init(p, blockIdx.x);
@@ -522,14 +540,14 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             if (item_skipped(p, g)) continue;
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
             ++it;
-            mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201);
+            TC_PROF_WAIT(mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201));
             tc_fence_after();
             const uint32_t set_base = tmem_base + (uint32_t)set * set_cols;
             for (int cg = 0; cg < p.ncg; ++cg) {
-                if (!p.wres) mbar_wait(smem_u32(wfull + wb), wphase, 202);
+                if (!p.wres) TC_PROF_WAIT(mbar_wait(smem_u32(wfull + wb), wphase, 202));
                 const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
-                    if (!probed) mbar_wait(smem_u32(full + stage), sphase, 203);
+                    if (!probed) TC_PROF_WAIT(mbar_wait(smem_u32(full + stage), sphase, 203));
                     tc_fence_after();
                     const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
                     // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi)
@@ -595,7 +613,9 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 }
             }
             tc_commit_if(elected, smem_u32(accfull + set));
+            TC_PROF_ITEM;
         }
+        TC_PROF_END(1);
     } else {
         // ================= epilogue warps 2..5 =================
         // Thread m owns output voxel m of the tile (TMEM lane m).  Depth slices are processed kJB at a time so that
@@ -610,6 +630,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int lh = m >> p.tw_log2, lw = m & ((1 << p.tw_log2) - 1);
         const int64_t sp = (int64_t)p.D * p.H * p.W;
         int it = 0;
+        TC_PROF_DECL;
         ItemCursor cur;
         cur.init(p, blockIdx.x);
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, cur.next(p)) {
@@ -617,6 +638,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             if (item_skipped(p, g)) continue;
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
             ++it;
+            TC_PROF_ITEM;
             const int h = g.h0 + lh, w = g.w0 + lw;
             const bool valid = (h < p.H) && (w < p.W);
             const int nd = g.d_hi - g.d0;
@@ -637,7 +659,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         }
                     }
                     if (!waited) {                    // residual loads of the first batch are issued before the wait
-                        mbar_wait(smem_u32(accfull + set), aphase, 301);
+                        TC_PROF_WAIT(mbar_wait(smem_u32(accfull + set), aphase, 301));
                         tc_fence_after();
                         waited = true;
                     }
@@ -715,12 +737,13 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 }
             }
             if (!waited) {        // a warp group without a depth batch in this item still paces itself on the item
-                mbar_wait(smem_u32(accfull + set), aphase, 302);
+                TC_PROF_WAIT(mbar_wait(smem_u32(accfull + set), aphase, 302));
                 tc_fence_after();
             }
             tc_fence_before();
             mbar_arrive(smem_u32(accempty + set));
         }
+        if (warp == 2) { TC_PROF_END(2); }
     }
     tc_fence_before();
     __syncthreads();
@@ -773,7 +796,7 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P, 
     s.c8 = (c_in == 8);
     if (s.c8 ? (P < 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
     s.NP = (c_out + 15) & ~15;                                 // UMMA N granularity at M = 128
-    s.fold = allow_fold && ks == 3 && P == 2 && s.NP == 16;
+    s.fold = allow_fold && P == 2 && s.NP == 16;              // k = 1 too: the 1x1x1 convs are issue-bound at 3 tiny MMAs per slab
     if (s.fold) s.NP = 32;                                     // [main 16 | correction 16] virtual channels
     s.taps2d = ks * ks;
     s.nb_rows = ks * s.NP;
@@ -1156,6 +1179,12 @@ extern "C" int lea_conv3d_tc_debug(const lea_conv* c, const void* wimg, const le
                                    int swap_lbo_sbo) {
     return tc_launch(c, wimg, opts, stream, swap_lbo_sbo);
 }
+
+#ifdef LEA_TC_ABLATION
+extern "C" int lea_tc_prof(long long* out12) {
+    return cudaMemcpyFromSymbol(out12, g_lea_tc_prof, sizeof(long long) * 12) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int lea_tc_status(void) {
     int v = 0;
