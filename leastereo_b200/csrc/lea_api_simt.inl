@@ -78,8 +78,13 @@ extern "C" int lea_trilinear_ac(const lea_vol* src, int32_t src_c0, const lea_vo
     const int nchunk = (dst->D + LEA_UP_DCH - 1) / LEA_UP_DCH;
     if (dst->D > src->D && dst->D >= 4 && (int64_t)nchunk * dst->H <= 65535) {
         // depth is up-sampled: depth-marching kernel (fewer loads per output)
-        LEA_LAUNCH(lea_trilinear_ac_up_kernel, dim3((dst->W + 127) / 128, nchunk * dst->H, dst->B * (c >> 3)), dim3(128),
-                   0, stream, *src, src_c0, *dst, dst_c0, c, bn_scale, bn_shift, relu);
+        const dim3 grid((dst->W + 127) / 128, nchunk * dst->H, dst->B * (c >> 3));
+        if (src->P == 2 && dst->P == 2)
+            LEA_LAUNCH(lea_trilinear_ac_up_kernel<2>, grid, dim3(128), 0, stream, *src, src_c0, *dst, dst_c0, c, bn_scale, bn_shift, relu);
+        else if (src->P == 3 && dst->P == 3)
+            LEA_LAUNCH(lea_trilinear_ac_up_kernel<3>, grid, dim3(128), 0, stream, *src, src_c0, *dst, dst_c0, c, bn_scale, bn_shift, relu);
+        else
+            LEA_LAUNCH(lea_trilinear_ac_up_kernel<0>, grid, dim3(128), 0, stream, *src, src_c0, *dst, dst_c0, c, bn_scale, bn_shift, relu);
     } else {
         LEA_LAUNCH(lea_trilinear_ac_kernel, dim3((dst->W + 127) / 128, dst->D * dst->H, dst->B * (c >> 3)), dim3(128),
                    0, stream, *src, src_c0, *dst, dst_c0, c, bn_scale, bn_shift, relu);

@@ -279,7 +279,7 @@ lea_resample_conv1_kernel(lea_vol src, int src_c0, int c_in, lea_rc_out o0, lea_
 // The (h, w)-interpolated values of the two low-res depth slices in use stay in registers; a new slice costs 4 corner
 // loads, and with out/in ~ 2 along d only every second output needs one -> ~5 loads per output instead of 16.
 // Same blend order (w, then h, then d) as the kernel above.
-#define LEA_UP_DCH 8
+#define LEA_UP_DCH 16
 struct lea_up_ctx {
     const lea_u4* sbase;          // (b, channel block, plane 0, depth 0) of the source
     int64_t sHW, sPS;             // source slice / plane strides in 16-byte groups
@@ -287,13 +287,17 @@ struct lea_up_ctx {
     float wh0, wh1, ww0, ww1;
     int P;
 };
+// PP = plane count known at compile time (0: taken from the volume at run time).  The run-time form predicates every
+// plane access (a third of the kernel's instructions, which is what bounds it); the launcher picks PP = 2 / 3 instances.
+template <int PP>
 LEA_D void lea_up_slice(const lea_up_ctx& c, int id, float* o /*[8]*/) {
     const lea_u4* sp = c.sbase + (int64_t)id * c.sHW;
+    const int P = PP ? PP : c.P;
     float a[8], bb[8], e[8], g[8];
-    lea_load8_at(sp + c.o00, c.sPS, c.P, a);
-    lea_load8_at(sp + c.o01, c.sPS, c.P, bb);
-    lea_load8_at(sp + c.o10, c.sPS, c.P, e);
-    lea_load8_at(sp + c.o11, c.sPS, c.P, g);
+    lea_load8_at(sp + c.o00, c.sPS, P, a);
+    lea_load8_at(sp + c.o01, c.sPS, P, bb);
+    lea_load8_at(sp + c.o10, c.sPS, P, e);
+    lea_load8_at(sp + c.o11, c.sPS, P, g);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float v = 0.0f;
@@ -303,6 +307,7 @@ LEA_D void lea_up_slice(const lea_up_ctx& c, int id, float* o /*[8]*/) {
     }
 }
 
+template <int PP>
 __global__ void __launch_bounds__(128)
 lea_trilinear_ac_up_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int c,
                            const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, int relu) {
@@ -347,7 +352,7 @@ lea_trilinear_ac_up_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int
 #pragma unroll
                 for (int j = 0; j < 8; ++j) A[j] = Bv[j];
             } else {
-                lea_up_slice(cx, i0, A);
+                lea_up_slice<PP>(cx, i0, A);
             }
             cur0 = i0;
         }
@@ -356,7 +361,7 @@ lea_trilinear_ac_up_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int
 #pragma unroll
                 for (int j = 0; j < 8; ++j) Bv[j] = A[j];
             } else {
-                lea_up_slice(cx, i1, Bv);
+                lea_up_slice<PP>(cx, i1, Bv);
             }
             cur1 = i1;
         }
@@ -370,7 +375,7 @@ lea_trilinear_ac_up_kernel(lea_vol src, int src_c0, lea_vol dst, int dst_c0, int
             if (relu) v = v > 0.0f ? v : 0.0f;
             out[j] = v;
         }
-        lea_store8_at(dbase + (int64_t)d * dHW, dPS, dst.P, out);
+        lea_store8_at(dbase + (int64_t)d * dHW, dPS, PP ? PP : dst.P, out);
     }
 }
 
