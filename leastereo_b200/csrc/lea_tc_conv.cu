@@ -762,6 +762,7 @@ static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
         return lea_conv_tc_kernel<KS, 3, 2, E8>;                   // bf16x3
     }
     if (nterm == 1) return lea_conv_tc_kernel<KS, 1, 3, E8>;
+    if (nterm == 2) return lea_conv_tc_kernel<KS, 2, 3, E8>;      // 8-channel layout, 3 planes, folded
     if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3, E8>;      // 8-channel layout, 3 planes
     return lea_conv_tc_kernel<KS, 6, 3, E8>;                       // bf16x6
 }
@@ -796,11 +797,13 @@ __host__ __device__ inline TcShape tc_shape(int c_in, int c_out, int ks, int P, 
     s.c8 = (c_in == 8);
     if (s.c8 ? (P < 2) : (c_in % 16 != 0 || c_in < 16 || c_in > 1024)) return s;
     s.NP = (c_out + 15) & ~15;                                 // UMMA N granularity at M = 128
-    s.fold = allow_fold && P == 2 && s.NP == 16;              // k = 1 too: the 1x1x1 convs are issue-bound at 3 tiny MMAs per slab
+    // (k = 1 too: the 1x1x1 convs were issue-bound at 3 tiny MMAs per slab; 8 input channels on 3 planes - the convs of
+    //  the 2-D feature net, issue-bound at 27 MMAs per depth-1 item - fold their three tiles into two)
+    s.fold = allow_fold && s.NP == 16 && (P == 2 || (P == 3 && s.c8));
     if (s.fold) s.NP = 32;                                     // [main 16 | correction 16] virtual channels
     s.taps2d = ks * ks;
     s.nb_rows = ks * s.NP;
-    if (s.c8) { s.nbt = s.fold ? 1 : P; s.ncg = 1; s.ngroups = 1; }
+    if (s.c8) { s.nbt = s.fold ? (P == 3 ? 2 : 1) : P; s.ncg = 1; s.ngroups = 1; }
     else      { s.nbt = P; s.ncg = c_in / 16; s.ngroups = P; }
     s.btile_bytes = 2 * s.nb_rows * 16;
     s.wpart_bytes = s.taps2d * s.nbt * s.btile_bytes;
@@ -829,7 +832,12 @@ __global__ void lea_pack_weights_tc_kernel(const float* __restrict__ w, lea_u4* 
     int plane, ci0;
     bool zero = false;
     if (s.fold) {
-        if (s.c8) { ci0 = 0; plane = region; zero = (region == 1 && khalf == 1); }
+        if (s.c8 && P == 3) {
+            // tile 0 (A = [a0|a1]) = [[w0;w0] | [w1;w1]],  tile 1 (A = [a0|a2]) = [[w2;w0] | 0]       3 MMAs -> 2 per tap
+            ci0 = 0;
+            if (bt == 0) plane = region;
+            else { plane = (khalf == 0) ? 2 : 0; zero = (region == 1); }
+        } else if (s.c8) { ci0 = 0; plane = region; zero = (region == 1 && khalf == 1); }
         else {
             ci0 = cg * 16 + khalf * 8;
             if (bt == 0) plane = region;                       // A = a_hi:  [Whi | Wlo]
@@ -949,7 +957,8 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
         p.ngroups = 1;
         if (s.c8) {
             p.blocks_per_cg = P;
-            add_term(0, 1, 0, 0, 1);                           // [a0|a1] x [[w0;w0] | [w1;0]]
+            add_term(0, 1, 0, 0, 1);                           // [a0|a1] x [[w0;w0] | [w1;0]]     (P = 3: [[w0;w0] | [w1;w1]])
+            if (P == 3 && !single) add_term(0, 2, 1, 0, 0);    // [a0|a2] x [[w2;w0] | 0]
         } else {
             p.blocks_per_cg = 2 * P;
             add_term(0, P, 0, 0, 1);                           // a0 x [w0 | w1]
