@@ -130,3 +130,42 @@ def check_backward_kernels(ops, DEV):
         d.backward(go)
         dm = ops.disp_head_bwd(mat.detach().to(DEV), go.to(DEV), maxdisp)
         assert _rel(dm.cpu(), mat.grad[:, 0]) <= 2e-4, maxdisp
+
+
+def test_gradient_coverage_analysis():
+    """training._Coverage: the first writer of a gradient slice overwrites, a later writer of covered channels
+    accumulates, partial overlaps and reads of incompletely written slices fall back to a zero-filled volume."""
+    from leastereo_b200.training import _Coverage
+    from leastereo_b200.engine import Slice
+
+    class Vol:
+        def __init__(self, c):
+            self.C = c
+
+    v, w = Vol(48), Vol(32)
+    cov = _Coverage(set())
+    assert cov.write(Slice(v, 0, 16)) is False            # first writer of [0, 16)
+    assert cov.write(Slice(v, 16, 16)) is False           # disjoint range: also a first writer
+    assert cov.write(Slice(v, 0, 32)) is True             # fully covered by the two ranges: accumulates
+    assert not cov.retry
+    cov.read(Slice(v, 0, 32))                             # completely written: fine
+    assert not cov.retry
+    cov.read(Slice(v, 0, 48))                             # [32, 48) never written: the volume must be zero-filled
+    assert cov.retry and id(v) in cov.zero_vols
+    cov2 = _Coverage(cov.zero_vols)
+    assert cov2.write(Slice(v, 0, 16)) is True            # zero-filled volumes: every writer accumulates
+    assert cov2.write(Slice(w, 0, 16)) is False
+    assert cov2.write(Slice(w, 8, 16)) is True            # partial overlap [8, 24) over [0, 16): fall back, retry
+    assert cov2.retry and id(w) in cov2.zero_vols
+
+
+def test_train_plan_zero_fills_one_volume_for_the_shipped_genotype(emu_ops):
+    """With the reference's architecture every gradient volume but one has first writers covering it.  The exception is
+    the shared [C1 | C4 | C8] skip buffer: conv2's data gradient writes [C4 | C8] first and conv1's then writes
+    [C1 | C4], a partial overlap, so that one volume is zero-filled and its writers accumulate."""
+    from leastereo_b200.training import TrainPlan
+    model = seeded_model(24)
+    plan = TrainPlan(model.matching, emu_ops, 1, (8, 8, 16), 3, DEV, "simt", 24)
+    assert len(plan.zero_grads) == 1 and plan.zero_grads[0].C == 3 * 64
+    assert len(plan.values) > 150
+    assert sum(1 for n in plan.nodes if getattr(n, "up", False)) >= 6      # the up-sampling cells take conv-before-upsample
