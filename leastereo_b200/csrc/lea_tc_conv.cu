@@ -522,7 +522,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             reg_col[t] = (uint32_t)(p.term_region[t] * p.Dc * p.NP);
             t_first[t] = p.term_first[t] != 0;
         }
-        const uint32_t idesc1 = make_idesc(p.NP), idesc2 = make_idesc(2 * p.NP), idesc3 = make_idesc(3 * p.NP);
+        const int NPv = p.NP;
+        const uint32_t idesc0 = make_idesc(0), idesc_step = make_idesc(NPv) - idesc0;
         const uint32_t a_hi = (uint32_t)kPitch | (1u << 14);                      // SBO = kPitch*16 B, version 1
         const uint32_t b_hi = 8u | (1u << 14);                                    // SBO = 128 B
         const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;                   // LBO = nb_rows*16 B
@@ -550,30 +551,33 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     if (!probed) TC_PROF_WAIT(mbar_wait(smem_u32(full + stage), sphase, 203));
                     tc_fence_after();
                     const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
-                    // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi)
-                    int kd_a, kd_b;
+                    // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi):
+                    //   kd_a = 0 / 1 / 2 for d_in <= d_hi-2 / = d_hi-1 / = d_hi;   kd_b = 2 / 1 / 0 for d_in >= d0+1 / = d0 / = d0-1.
+                    // Branch-free on purpose: this bookkeeping sits between the last MMA of a slab and the first of the next
+                    // (the MMA queue is one deep), and as ternaries it compiled to a chain of ~10 uniform branches.
+                    int kd_a = 0, kd_b = 0;
                     if (KS == 3) {
-                        kd_a = (d_in + 1 <= g.d_hi - 1) ? 0 : ((d_in <= g.d_hi - 1) ? 1 : 2);
-                        kd_b = (d_in - 1 >= g.d0) ? 2 : ((d_in >= g.d0) ? 1 : 0);
-                    } else { kd_a = 0; kd_b = 0; }
+                        kd_a = min(max(d_in - (g.d_hi - 2), 0), 2);
+                        kd_b = min(max(d_in - g.d0 + 1, 0), 2);
+                    }
                     const int nkd = kd_b - kd_a + 1;
                     // accumulators are stored in descending depth order: depth d sits at column (d_hi-1-d)*NP
                     const int d_top = (KS == 3) ? d_in + 1 - kd_a : d_in;
-                    const uint32_t col0 = (uint32_t)((g.d_hi - 1 - d_top) * p.NP);
+                    const uint32_t col0 = (uint32_t)((g.d_hi - 1 - d_top) * NPv);
                     // depths touched for the first time by this slab (only while the first channel group runs):
                     // kd = 0 always opens depth d_in+1; at d_in == 0 depth 0 (kd = 1) opens too
-                    int nfresh = 0;
-                    if (cg == 0) {
-                        if (KS == 3) {
-                            if (kd_a == 0) nfresh = 1 + ((d_in == 0 && kd_b >= 1) ? 1 : 0);
-                            else if (kd_a == 1 && d_in == 0) nfresh = 1;
-                        } else nfresh = 1;
+                    int nfresh = 1;
+                    if (KS == 3) {
+                        const int z = (d_in == 0) ? 1 : 0;
+                        nfresh = ((kd_a == 0) ? 1 : 0) + (z & ((((kd_a == 0) ? 1 : 0) & ((kd_b >= 1) ? 1 : 0)) | ((kd_a == 1) ? 1 : 0)));
                     }
-                    const uint32_t brow16 = (uint32_t)(kd_a * p.NP);              // first weight row used, x16 B
-                    const uint32_t idesc_all = nkd == 3 ? idesc3 : (nkd == 2 ? idesc2 : idesc1);
-                    const uint32_t idesc_fresh = nfresh == 2 ? idesc2 : idesc1;
+                    nfresh = (cg == 0) ? nfresh : 0;
+                    const uint32_t brow16 = (uint32_t)(kd_a * NPv);               // first weight row used, x16 B
+                    // the instruction descriptor is linear in N: idesc(k * NP) = idesc0 + k * idesc_step
+                    const uint32_t idesc_all = idesc0 + (uint32_t)nkd * idesc_step;
+                    const uint32_t idesc_fresh = idesc0 + (uint32_t)nfresh * idesc_step;
                     const int nrest = nkd - nfresh;
-                    const uint32_t idesc_rest = nrest == 2 ? idesc2 : idesc1;
+                    const uint32_t idesc_rest = idesc0 + (uint32_t)nrest * idesc_step;
                     if (TC_DBG(p, 8)) {                // development: no MMAs - what the TMA ring and the epilogue cost alone
                         const bool wrap = (stage + 1 == p.nstages);
                         probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
@@ -592,8 +596,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 if (kh == 0 && kw == 0 && t_first[t] && nfresh > 0) {
                                     tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
                                     if (nrest > 0)
-                                        tc_mma_issue(elected, dcol + (uint32_t)(nfresh * p.NP), a_lo, a_hi,
-                                                     b_lo + (uint32_t)(nfresh * p.NP), b_hi, idesc_rest, 1u);
+                                        tc_mma_issue(elected, dcol + (uint32_t)(nfresh * NPv), a_lo, a_hi,
+                                                     b_lo + (uint32_t)(nfresh * NPv), b_hi, idesc_rest, 1u);
                                 } else {
                                     tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_all, 1u);
                                 }
