@@ -505,7 +505,8 @@ def main():
     ops = get_ops()
 
     H, W, maxdisp, B = WORKLOAD["H"], WORKLOAD["W"], WORKLOAD["maxdisp"], args.batch
-    options = {"planes": args.planes, "conv": args.conv, "mma_terms": args.mma_terms, "assume_frozen": True}
+    options = {"planes": args.planes, "conv": args.conv, "mma_terms": args.mma_terms, "assume_frozen": True,
+               "cuda_graph": not args.no_graph}
     for kv in args.knob:
         k, v = kv.split("=")
         options[k] = int(v)
@@ -526,29 +527,21 @@ def main():
         torch.cuda.synchronize()
         launches_per_step = ops.launches - n0
 
-        graph, static_out = None, None
+        # Both timed arms call the public API, ``LEAStereo.forward``: from its third call with one input shape the
+        # module replays its own CUDA graph of the launch list (engine option ``cuda_graph``; ``--no-graph`` turns it
+        # off for per-launch profiles).  The bench only checks that the graph exists and reproduces the eager result.
+        graph_on = False
         if not args.no_graph:
-            try:
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    model(left, right)
-                torch.cuda.current_stream().wait_stream(s)
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    static_out = model(left, right)
-                graph.replay()
-                torch.cuda.synchronize()
-                if not torch.allclose(static_out, disp, atol=1e-3, rtol=0):
-                    raise RuntimeError("graph replay differs from eager run")
-            except Exception as e:  # noqa: BLE001
-                print("[bench] CUDA graph capture unavailable (%s); running eagerly" % str(e)[:200], file=sys.stderr)
-                graph = None
+            out3 = model(left, right)
+            torch.cuda.synchronize()
+            fplans = [q for q in engine._plans(model.feature).values() if isinstance(q, engine.FeaturePlan)]
+            graph_on = bool(fplans) and fplans[-1].__dict__.get("_graph", {}).get("graph") is not None
+            if not graph_on:
+                print("[bench] the module did not capture its CUDA graph; running eagerly", file=sys.stderr)
+            elif not torch.equal(out3, disp):
+                raise RuntimeError("graph replay differs from the eager run")
 
         def step_device():
-            if graph is not None:
-                graph.replay()
-                return static_out
             return model(left, right)
 
         # ---- device-resident throughput ----
@@ -634,7 +627,6 @@ def main():
                       "arena_GB": round(getattr(plan, "arena_bytes", 0) / 2 ** 30, 2)}
 
     # ---- legs beside the headline ----
-    del graph, static_out
     engine.invalidate_cached_plans(model)
     del model, plan
     torch.cuda.empty_cache()
@@ -716,7 +708,7 @@ def main():
                 args.planes] if args.conv == "tc" else "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOAD["name"], "pairs_per_gpu_per_step": B, "conv": args.conv, "planes": args.planes,
-                       "mma_terms": args.mma_terms, "cuda_graph": not args.no_graph and launches_per_step > 0,
+                       "mma_terms": args.mma_terms, "cuda_graph": graph_on,
                        "parallelism": "pairs sharded, no collective",
                        "rewrites": {"collapse_stem0": plan_facts["collapse_stem0"], "fuse_cost_volume": plan_facts["fuse_cv"],
                                     "fuse_head": plan_facts["fuse_head"],
