@@ -36,8 +36,11 @@ def main():
             if op == c or op.startswith(c + ".") or (c == "MUFU.EX2" and op.startswith("MUFU.EX2")):
                 cur[c] += 1
     names = demangle([k["name"] for k in kernels])
-    print("SASS instruction counts per kernel of %s (cuobjdump -sass, sm_100a)." % os.path.relpath(LIB, ROOT))
-    print(__doc__.split("\n")[1].strip() + " " + __doc__.split("\n")[2].strip())
+    print("SASS instruction counts per kernel of %s (cuobjdump -sass, sm_100a; tools/sass_counts.py)." % os.path.relpath(LIB, ROOT))
+    print("UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG/UTMASTG = TMA tensor load/store, UBLKCP = cp.async.bulk, HMMA = mma.sync,")
+    print("LDSM = ldmatrix, SYNCS = mbarrier ops, MUFU.EX2 = ex2.  The ConvBR forward / data-gradient kernels are tcgen05-only; the only")
+    print("kernels with HMMA are the weight-gradient kernels (lea_wgrad_mma_kernel, see lea_wgrad_mma.cu for why).  UTMASTG = 0: the")
+    print("TMA-store epilogue was measured and rejected (profiles/r02_tma_store_epilogue_ab.txt).")
     print()
     print("%-110s %7s " % ("kernel", "instr") + " ".join("%8s" % c for c in COLS))
     for k, nm in sorted(zip(kernels, names), key=lambda t: t[1]):
