@@ -179,8 +179,17 @@ extern "C" int lea_disp_head(const float* mat, float* disp, int32_t B, int32_t D
     LEA_CHECK(mat && disp, "disp_head: null pointer");
     LEA_CHECK(B > 0 && D3 > 0 && H3 > 0 && W3 > 0 && maxdisp > 0 && B <= 65535, "disp_head: bad shape");
     LEA_CHECK(H3 <= 65535, "disp_head: grid too large");
+    // pass 1's blended logits stay in shared memory for pass 2 when a lane's quarter of the disparity range fits
+    const int kchunk = (D3 + LEA_DH_PARTS - 1) / LEA_DH_PARTS;
+    size_t smem = (size_t)kchunk * 9 * LEA_DH_CELLS * LEA_DH_PARTS * sizeof(float);
+    int cache = (smem <= 200 * 1024) ? 1 : 0;
+    if (!cache) smem = 0;
+#ifndef LEA_CPU_EMU
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(lea_disp_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
     LEA_LAUNCH(lea_disp_head_kernel, dim3((W3 + LEA_DH_CELLS - 1) / LEA_DH_CELLS, H3, B),
-               dim3(LEA_DH_CELLS * LEA_DH_PARTS), 0, stream, mat, disp, D3, H3, W3, maxdisp);
+               dim3(LEA_DH_CELLS * LEA_DH_PARTS), smem, stream, mat, disp, D3, H3, W3, maxdisp, cache);
     return LEA_POST_LAUNCH();
 }
 

@@ -598,9 +598,14 @@ LEA_HD bool lea_three_tap(int c, int r, int in_n, float* t /*[3]*/) {
 // 4x the threads of the one-thread-per-cell formulation: the kernel is latency-bound on its FMA/MUFU chains, so the
 // extra warps in flight are what buys time (measured 105 -> see DESIGN.md).  No early exit: every lane takes part in
 // the shuffles; lanes past the right edge work on the last column and do not store.
+// `cache` != 0: dynamic shared memory holds kchunk x 9 x blockDim floats and pass 1 keeps its blended logits there
+// ([k][pixel][thread]: conflict-free), so that pass 2 of the exact x3 path reads them back (9 LDS per sample) instead of
+// loading and blending the 3x3 neighbourhood a second time (9 loads + 54 FMAs per sample).
 __global__ void __launch_bounds__(LEA_DH_CELLS * LEA_DH_PARTS)
 lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
-                     int D3, int H3, int W3, int maxdisp) {
+                     int D3, int H3, int W3, int maxdisp, int cache) {
+    LEA_DYN_SMEM(float, ucache);
+    constexpr int kThreads = LEA_DH_CELLS * LEA_DH_PARTS;
     const int part = threadIdx.x & (LEA_DH_PARTS - 1);
     const int w3r = blockIdx.x * LEA_DH_CELLS + (threadIdx.x >> 2);
     const int h3 = blockIdx.y;
@@ -638,6 +643,7 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
                 m[q] = u[q] < m[q] ? u[q] : m[q];
                 amax = fmaxf(amax, fabsf(u[q]));
                 cur[q] = nxt[q];
+                if (cache) ucache[((k - ka) * 9 + q) * kThreads + threadIdx.x] = u[q];
             }
         }
 #pragma unroll
@@ -659,6 +665,7 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
     // (random-init weights with identity BN give |u| ~ 1e8; measured at 288x576: 0.2 % of pixels off by up to 0.4 px
     // against the reference, all of them ties that the reference's weight bits break).  So it is taken only where every
     // logit of the cell is below 64 (error <= 2.6e-4 in the exponent); other cells use the reference's own weights.
+    if (cache) __syncthreads();              // pass 2 also reads the first sample of the next lane's chunk
     if (maxdisp == 3 * D3 && amax <= 64.0f) {
         // pass 2, exact x3 scale (every BASELINE config): output 0 is sample 0, 3k+1 is sample k, 3k+2 and 3k+3 blend
         // samples k and k+1 with weights (2/3, 1/3) and (1/3, 2/3) (sample D3 := sample D3-1).  With
@@ -669,8 +676,13 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
         const float c3 = 1.4426950408889634f / 3.0f;                   // log2(e) / 3
         float T[9], raw[9], u[9];
         if (ka < kb) {
-            LEA_DH_LOAD(raw, ka);
-            LEA_DH_COMBINE(u, raw);
+            if (cache) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) u[q] = ucache[q * kThreads + threadIdx.x];
+            } else {
+                LEA_DH_LOAD(raw, ka);
+                LEA_DH_COMBINE(u, raw);
+            }
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
                 T[q] = exp2f((m[q] - u[q]) * c3);              // subtract first: logits can be ~1e8
@@ -680,8 +692,16 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
         for (int k = ka; k < kb; ++k) {
             float Tn[9];
             if (k + 1 < D3) {
-                LEA_DH_LOAD(raw, k + 1);
-                LEA_DH_COMBINE(u, raw);
+                if (cache) {
+                    // sample k+1: this lane's own chunk, or the first sample of the next lane (same cell, thread + 1)
+                    const int own = (k + 1 < kb) ? 1 : 0;
+                    const int base = own ? (k + 1 - ka) * 9 * kThreads + (int)threadIdx.x : (int)threadIdx.x + 1;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) u[q] = ucache[base + q * kThreads];
+                } else {
+                    LEA_DH_LOAD(raw, k + 1);
+                    LEA_DH_COMBINE(u, raw);
+                }
 #pragma unroll
                 for (int q = 0; q < 9; ++q) Tn[q] = exp2f((m[q] - u[q]) * c3);
             } else {
@@ -702,6 +722,7 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
     } else {
     // pass 2, general scale: this lane's quarter of the maxdisp output samples; (k0, k1) window along disparity
     int kc = -1, k1c = -1;
+    const int kchunk_all = (D3 + LEA_DH_PARTS - 1) / LEA_DH_PARTS;     // owner lane / slot of a cached sample
     const int ichunk = (maxdisp + LEA_DH_PARTS - 1) / LEA_DH_PARTS;
     const int ia = min(maxdisp, part * ichunk), ib = min(maxdisp, ia + ichunk);
     for (int i = ia; i < ib; ++i) {
@@ -710,6 +731,10 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
             if (ad.i0 == k1c) {
 #pragma unroll
                 for (int q = 0; q < 9; ++q) u0[q] = u1[q];
+            } else if (cache) {
+                const int pp = ad.i0 / kchunk_all, base = ((ad.i0 - pp * kchunk_all) * 9) * kThreads + (int)threadIdx.x - part + pp;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) u0[q] = ucache[base + q * kThreads];
             } else {
                 float raw[9];
                 LEA_DH_LOAD(raw, ad.i0);
@@ -721,6 +746,10 @@ lea_disp_head_kernel(const float* __restrict__ mat, float* __restrict__ disp,
             if (ad.i1 == kc) {
 #pragma unroll
                 for (int q = 0; q < 9; ++q) u1[q] = u0[q];
+            } else if (cache) {
+                const int pp = ad.i1 / kchunk_all, base = ((ad.i1 - pp * kchunk_all) * 9) * kThreads + (int)threadIdx.x - part + pp;
+#pragma unroll
+                for (int q = 0; q < 9; ++q) u1[q] = ucache[base + q * kThreads];
             } else {
                 float raw[9];
                 LEA_DH_LOAD(raw, ad.i1);
