@@ -715,6 +715,8 @@ def main():
                                     "note": "exact algebraic rewrites of the plan (DESIGN.md 3): stem0 separates into 2-D convs "
                                             "where the cost volume is un-masked; last_3's channel contraction runs before "
                                             "upsample_6"},
+                       "tc_fold": os.environ.get("LEA_TC_FOLD", "2") + " (2 = incl. the one-tile fold of the 32-output convs, which adds a "
+                                  "neighbour-tap a_lo*W_lo term <= 2^-18 relative, DESIGN.md 4.1; gated by the `parity` leg)",
                        "feature_planes": plan_facts["feature_planes"], "accum_split": plan_facts["accum_split"],
                        "activation_arena_GB": plan_facts["arena_GB"],
                        "l2": "per-step activation working set (>4 GB of planes volumes) exceeds the 126 MB L2; no flush needed",
