@@ -295,6 +295,22 @@ def test_full_forward_native_vs_golden(ops, name):
     assert rep["ok"], rep
 
 
+def test_pack_weights_dgrad_equals_explicit_transpose(ops):
+    """lea_pack_weights_tc_dgrad (the data-gradient conv's weight image, read in place from the forward weight) is
+    bit-identical to packing the explicitly flipped + transposed weight, for whole tensors and 64-channel slices."""
+    g = torch.Generator().manual_seed(5)
+    for (co, ci, k) in [(32, 64, 3), (64, 128, 3), (16, 16, 3), (8, 8, 3), (16, 64, 1), (32, 128, 1), (8, 64, 1)]:
+        w = torch.randn(co, ci, k, k, k, generator=g).to(DEV)
+        wt = w.flip(2, 3, 4).transpose(0, 1).contiguous()               # (ci, co, k, k, k): the data-gradient conv's weight
+        for o0 in range(0, ci, 64):
+            oc = min(64, ci - o0)
+            if ops.tc_weight_image_bytes(co, oc, k, 2) <= 0:
+                continue
+            want = ops.pack_weights_tc(wt[o0:o0 + oc].contiguous(), 2)
+            got = ops.pack_weights_tc_dgrad(w, 2, o0, oc)
+            assert torch.equal(got, want), (co, ci, k, o0)
+
+
 def test_module_owned_cuda_graph(ops):
     """LEAStereo.forward replays its own CUDA graph from the third call on (engine option cuda_graph, default on): same
     bits as the eager launch list, fresh inputs honoured, in-place parameter changes picked up, no aliasing of results."""
