@@ -457,7 +457,7 @@ def standalone_kernels(device, B, peaks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8,
                     help="stereo pairs per GPU per step (BASELINE configs[2] sweeps batch 1-64; throughput saturates from 4 on, "
