@@ -974,7 +974,7 @@ def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[O
     # Parameters are checked on the host before every replay; the packed weight images and BN vectors are rewritten in
     # place, and a change of the parameter key (values or storage) drops the graph so that raw weight pointers recorded
     # in it can never go stale.  Two eager calls first (allocations, lazily built tensor maps).
-    st = fplan.__dict__.setdefault("_graph", {"calls": 0, "graph": None, "out": None, "keys": None})
+    st = fplan.__dict__.setdefault("_graph", {"calls": 0, "graph": None, "out": None, "keys": None, "failed": None})
     if not opt["assume_frozen"] or plan._param_key is None or fplan._param_key is None:
         fplan.refresh_params()
         plan.refresh_params()
@@ -983,14 +983,22 @@ def full_forward(model, left: torch.Tensor, right: torch.Tensor, ops: Optional[O
         st["graph"], st["out"] = None, None
     if st["graph"] is None:
         st["calls"] += 1
-        if st["calls"] <= 2:
+        if st["calls"] <= 2 or st["failed"] is not None:
             fplan.run(check_params=False)
             return ops.disp_head(plan.run(check_params=False), model.maxdisp)
         torch.cuda.synchronize(left.device)
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                fplan.run(check_params=False)
+                st["out"] = ops.disp_head(plan.run(check_params=False), model.maxdisp)
+        except RuntimeError as e:      # capture refused by the runtime: stay on the (same) eager launch list, loudly
+            import warnings
+            st["failed"] = str(e)
+            warnings.warn("leastereo_b200: CUDA graph capture of the forward failed (%s); launching eagerly" % str(e)[:200])
+            torch.cuda.synchronize(left.device)
             fplan.run(check_params=False)
-            st["out"] = ops.disp_head(plan.run(check_params=False), model.maxdisp)
+            return ops.disp_head(plan.run(check_params=False), model.maxdisp)
         st["graph"], st["keys"] = g, keys
     st["graph"].replay()
     return st["out"].clone()

@@ -18,7 +18,8 @@ for name, N, ci, co, k, P, (D, H, W) in cases:
     src.t.copy_(torch.randn(src.t.shape, device=dev).bfloat16() * 0.1)
     dst = PlanesVol.empty(N, co, P, D, H, W, dev)
     dst.t.zero_()
-    p = ops.make_conv(src, 0, ci, co, k, sc, sh, True, dst=dst)
+    res = os.environ.get("RES", "0") == "1"
+    p = ops.make_conv(src, 0, ci, co, k, sc, sh, True, dst=dst, res=dst if res else None)
     for dbg in (0, 11):
         opts = lea_tc_opts(); opts.debug = dbg
         for _ in range(3):
