@@ -334,10 +334,13 @@ class TrainPlan:
                 return self.forward(fx, fy)
             self._fx_in, self._fy_in = fx.clone(), fy.clone()
             torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
             gen = self.generation
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._disp_out = self.forward(self._fx_in, self._fy_in)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._disp_out = self.forward(self._fx_in, self._fy_in)
+            except RuntimeError as e:            # capture refused: keep launching eagerly, loudly
+                return self._graph_failed(e, lambda: self.forward(fx, fy), gen)
             self.generation = gen
             self._graphs[0] = g
         self.generation += 1
@@ -345,6 +348,16 @@ class TrainPlan:
         self._fy_in.copy_(fy)
         self._graphs[0].replay()
         return self._disp_out.clone()
+
+    def _graph_failed(self, e, eager, generation):
+        import warnings
+        warnings.warn("leastereo_b200: CUDA graph capture of the training plan failed (%s); launching eagerly" % str(e)[:200])
+        self.use_graph = False
+        self._graphs = [None, None]
+        self._no_graph = True
+        torch.cuda.synchronize(self.device)
+        self.generation = generation
+        return eager()
 
     def run_backward(self, gdisp: torch.Tensor):
         if not self.use_graph or self._graphs[0] is None:
@@ -355,9 +368,12 @@ class TrainPlan:
                 return self.backward(gdisp)
             self._gdisp_in = gdisp.contiguous().float().clone()
             torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._bwd_out = self.backward(self._gdisp_in)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._bwd_out = self.backward(self._gdisp_in)
+            except RuntimeError as e:
+                return self._graph_failed(e, lambda: self.backward(gdisp), self.generation)
             self._graphs[1] = g
         self._gdisp_in.copy_(gdisp)
         self._graphs[1].replay()
@@ -599,7 +615,8 @@ def hot_path_train_forward(model, fx: torch.Tensor, fy: torch.Tensor, ops: Optio
         _TRAIN_PLANS.clear()                       # one live training plan: buffers are large
         plan = TrainPlan(model.matching, ops, B, (D3, H3, W3), planes, fx.device, conv, model.maxdisp)
         _TRAIN_PLANS[key] = plan
-    plan.use_graph = bool(opt.get("train_graph", True)) and ops.device_build and fx.is_cuda
+    plan.use_graph = (bool(opt.get("train_graph", True)) and ops.device_build and fx.is_cuda
+                      and not getattr(plan, "_no_graph", False))
     params = used_parameters(plan)
     # the BN kernels update running_mean / running_var / num_batches_tracked through raw pointers (no autograd version
     # bump): tell the eval-mode plans that parameters changed
