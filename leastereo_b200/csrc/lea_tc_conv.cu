@@ -42,8 +42,10 @@ namespace {
 // Epilogue warps: one per TMEM lane quarter.  Measured: two per quarter (alternate depth batches) speed up only the
 // 8-channel layers (155 -> 139 us) and lose overall (174 -> 170 pairs/s): 10 warps put three warps on one SM
 // sub-partition (16 K registers), capping the kernel at 168 registers per thread.
-__host__ __device__ constexpr int epi_warps(int planes) { return planes == 3 ? 4 : 4; }
-__host__ __device__ constexpr int tc_threads(int planes) { return 64 + 32 * epi_warps(planes); }
+// The 8-output-channel instances (E8 == 1, 2 planes: cell 10's single ops with residual, epilogue-bound) run two warps per
+// quarter; their epilogue fits the 168-register cap of 10 warps.
+__host__ __device__ constexpr int epi_warps(int planes, int e8) { return (planes == 2 && e8 == 1) ? 8 : 4; }
+__host__ __device__ constexpr int tc_threads(int planes, int e8) { return 64 + 32 * epi_warps(planes, e8); }
 constexpr int kMaxTerms = 6;
 constexpr int kMaxSets = 8;      // TMEM accumulator sets (work items in flight between the issuer and the epilogue)
 constexpr int kMaxStages = 24;   // deep enough that 8 KB 1x1x1 stages keep ~1.5 us of HBM latency covered
@@ -411,7 +413,7 @@ __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom
 }
 
 template <int KS, int NTERM, int PL, int E8>
-__global__ void __launch_bounds__(tc_threads(PL), 1)
+__global__ void __launch_bounds__(tc_threads(PL, E8), 1)
 lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     // header: barriers, TMEM base, BN scale/shift
@@ -440,7 +442,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1); }
         for (int i = 0; i < kMaxSets; ++i) {
-            mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 32 * epi_warps(PL));
+            mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 32 * epi_warps(PL, E8));
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -653,7 +655,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const bool valid = (h < p.H) && (w < p.W);
             const int nd = g.d_hi - g.d0;
             bool waited = false;
-            for (int j0 = ((warp - 2) >> 2) * kJB; j0 < nd; j0 += (epi_warps(PL) / 4) * kJB) {
+            for (int j0 = ((warp - 2) >> 2) * kJB; j0 < nd; j0 += (epi_warps(PL, E8) / 4) * kJB) {
                 for (int c16 = 0; c16 < p.c_out; c16 += 16) {
                     const bool two = (c16 + 8 < p.c_out);
                     uint4 rq[kJB][2][PL];
@@ -1138,7 +1140,8 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm, P, (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0);
+    const int e8 = (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0;
+    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm, P, e8);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
@@ -1154,7 +1157,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // graph of the KITTI step: 196.0 pairs/s with, 196.1 without - launch gaps are not what the step loses.
     static const int use_pdl = [] { const char* v = getenv("LEA_TC_PDL"); return (v && v[0] == '1') ? 1 : 0; }();
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)tc_threads(P));
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)tc_threads(P, e8));
     cfg.dynamicSmemBytes = kSmemBudget; cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
