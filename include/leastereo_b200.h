@@ -114,7 +114,7 @@ typedef struct lea_tc_opts {
     const void* cv_maps;   /* fused_cv: device array built by lea_build_fused_cv_maps for these fx/fy/d3 */
     int32_t resident_weights;  /* 0 = auto (all channel groups' weights stay in shared memory when they fit), 2 = never */
     int32_t cv_skip;           /* fused_cv only: 1 = leave the voxels lea_stem0_assemble writes (collapsed stem0) untouched */
-    int32_t debug;             /* timing-ablation switches, only in -DLEA_TC_ABLATION builds; 0 in production */
+    int32_t debug;             /* bits 0-3: timing-ablation switches (only in -DLEA_TC_ABLATION builds); bit 4: no flat mode for depth-1 volumes (A/B) */
     int32_t depth_chunk;       /* 0 = auto, n = depth slices per work item, clamped to what the schedule allows (test knob) */
     int32_t tile_w_log2;       /* 1x1x1 convs only: 0 = auto, 3..7 = tile of 2^n voxels along w by 128/2^n along h */
 } lea_tc_opts;

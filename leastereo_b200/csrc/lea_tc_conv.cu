@@ -74,6 +74,8 @@ struct TcParams {
     int ncg, blocks_per_cg;
     int ks, taps;
     int tiles_w, tiles_h, dchunks, Dc, total_items;
+    int flat, PD;             // flat = depth-1 volume (2-D conv): the 8-wide w tiles of a row of tiles take the place of the
+                              // depth slices of an item (PD of them), so that one accumulator hand-over serves Dc tiles
     int step_tw, step_th, step_dc, step_b;   // mixed-radix digits of the grid stride (ItemCursor)
     int NP, c_out, ngroups;   // padded N, real c_out, TMEM regions (weight planes) summed by the epilogue
     int nterm;
@@ -229,7 +231,7 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, const ItemCur
     const int tw = c.tw, th = c.th, dc = c.dc;
     g.b = c.b;
     g.d0 = dc * p.Dc;
-    g.d_hi = min(g.d0 + p.Dc, p.D);
+    g.d_hi = min(g.d0 + p.Dc, p.flat ? p.PD : p.D);
     g.h0 = th * (128 >> p.tw_log2); g.w0 = tw << p.tw_log2;
     if (p.cv_skip) {
         // collapsed stem0: keep only the depths of the chunk that lea_stem0_assemble does not write.  For one w tile
@@ -238,7 +240,7 @@ __device__ __forceinline__ ItemGeom decode_item(const TcParams& p, const ItemCur
         while (g.d0 < g.d_hi && lea_cv_collapsed(g.d0, tw, p.D, p.W)) ++g.d0;
         while (g.d_hi > g.d0 && lea_cv_collapsed(g.d_hi - 1, tw, p.D, p.W)) --g.d_hi;
     }
-    if (p.ks == 3) { g.dlo = max(g.d0 - 1, 0); g.dhi = min(g.d_hi, p.D - 1); }
+    if (p.ks == 3 && !p.flat) { g.dlo = max(g.d0 - 1, 0); g.dhi = min(g.d_hi, p.D - 1); }
     else           { g.dlo = g.d0;             g.dhi = g.d_hi - 1; }
     return g;
 }
@@ -356,10 +358,11 @@ __device__ __forceinline__ void tc_touch16(uint32_t* r) {
 
 // Epilogue of one depth batch [j0, j0 + JB) of an item for the channel group at c16: NV = 8 or 16 accumulator columns
 // per region, SB depths per tcgen05.wait::ld.  rq = residual groups loaded by the caller (valid when p.has_res).
-template <int PL, int NV, int SB, int JB>
+// FLAT: the "depth" index of the item is a w tile of a depth-1 volume: voxel (0, h, 8 * d + lw).
+template <int PL, int NV, int SB, int JB, bool FLAT>
 __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom& g, uint32_t tcol, uint32_t r1off,
-                                               bool two_regions, int j0, int nd, int c16, bool valid, int h, int w,
-                                               int64_t sp, const float* s_scale, const float* s_shift,
+                                               bool two_regions, int j0, int nd, int c16, bool valid, int h, int w_in,
+                                               int lw, int64_t sp, const float* s_scale, const float* s_shift,
                                                const uint4 (*rq)[2][PL]) {
 #pragma unroll
     for (int jb = 0; jb < JB; jb += SB) {
@@ -379,7 +382,9 @@ __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom
         for (int s = 0; s < SB; ++s) {
             const int jj = jb + s;
             if (j0 + jj >= nd) break;
-            const int d = g.d0 + j0 + jj;
+            const int dj = g.d0 + j0 + jj;
+            const int d = FLAT ? 0 : dj;
+            const int w = FLAT ? (dj << 3) + lw : w_in;
             float acc[NV];
             if (NV == 8) tc_touch8(ra[s]); else tc_touch16(ra[s]);
             if (two_regions) {
@@ -390,7 +395,7 @@ __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom
 #pragma unroll
                 for (int i = 0; i < NV; ++i) acc[i] = __uint_as_float(ra[s][i]);
             }
-            if (!valid || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
+            if (!valid || (FLAT && w >= p.W) || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
 #pragma unroll
             for (int i = 0; i < NV; ++i) {
                 float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
@@ -461,7 +466,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    constexpr int kHalo = (KS == 3) ? 1 : 0;
+    // KS: 1 = 1x1x1, 3 = 3x3x3, 2 = 3x3 in the plane of a depth-1 volume ("flat": w tiles as the depth slices of an item)
+    constexpr int KT = (KS == 1) ? 1 : 3;                      // taps per in-plane axis
+    constexpr bool FLAT = (KS == 2);
+    constexpr int kHalo = (KS != 1) ? 1 : 0;
     constexpr int kPitch = LEA_TC_TW + 2 * kHalo;              // voxels per staged row
 
     if (warp == 0) {
@@ -502,7 +510,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                         gbase + (left ? cg : cg - p.ncg_half) * p.blocks_per_cg);
                         } else {
                             tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_stride), &tmap, smem_u32(full + stage),
-                                        (g.w0 - kHalo) * 8, g.h0 - kHalo, d_in, gbase + cg * p.blocks_per_cg);
+                                        ((FLAT ? (d_in << 3) : g.w0) - kHalo) * 8, g.h0 - kHalo, FLAT ? 0 : d_in,
+                                        gbase + cg * p.blocks_per_cg);
                         }
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                     }
@@ -561,7 +570,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     //   kd_a = 0 / 1 / 2 for d_in <= d_hi-2 / = d_hi-1 / = d_hi;   kd_b = 2 / 1 / 0 for d_in >= d0+1 / = d0 / = d0-1.
                     // Branch-free on purpose: this bookkeeping sits between the last MMA of a slab and the first of the next
                     // (the MMA queue is one deep), and as ternaries it compiled to a chain of ~10 uniform branches.
-                    int kd_a = 0, kd_b = 0;
+                    int kd_a = FLAT ? 1 : 0, kd_b = FLAT ? 1 : 0;     // flat: the middle tap plane only, one "depth" per slab
                     if (KS == 3) {
                         // (measured: sums of compares instead of these clamps cost the issuer 4-7 % more cycles per item)
                         kd_a = min(max(d_in - (g.d_hi - 2), 0), 2);
@@ -590,11 +599,11 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
                     } else
 #pragma unroll
-                    for (int kh = 0; kh < KS; ++kh) {
+                    for (int kh = 0; kh < KT; ++kh) {
 #pragma unroll
-                        for (int kw = 0; kw < KS; ++kw) {
+                        for (int kw = 0; kw < KT; ++kw) {
                             const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
-                            const uint32_t b_tap = w16 + (uint32_t)(kh * KS + kw) * tap16 + brow16;
+                            const uint32_t b_tap = w16 + (uint32_t)(kh * KT + kw) * tap16 + brow16;
 #pragma unroll
                             for (int t = 0; t < NTERM; ++t) {
                                 const uint32_t a_lo = (a_tap + a_term16[t]) | a_lbo_field[t];
@@ -651,8 +660,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
             ++it;
             TC_PROF_ITEM;
-            const int h = g.h0 + lh, w = g.w0 + lw;
-            const bool valid = (h < p.H) && (w < p.W);
+            const int h = g.h0 + lh, w = g.w0 + lw, w_item = w;
+            const bool valid = (h < p.H) && (FLAT || w < p.W);
             const int nd = g.d_hi - g.d0;
             bool waited = false;
             for (int j0 = ((warp - 2) >> 2) * kJB; j0 < nd; j0 += (epi_warps(PL, E8) / 4) * kJB) {
@@ -662,11 +671,12 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     if (p.has_res && valid && !TC_DBG(p, 4)) {
 #pragma unroll
                         for (int jj = 0; jj < kJB; ++jj) {
-                            if (j0 + jj < nd) {
-                                ep_load_raw8<PL>(p.res, g.b, (p.res_c0 + c16) >> 3, g.d0 + j0 + jj, h, w, rq[jj][0]);
+                            const int dj = g.d0 + j0 + jj;
+                            const int rd = FLAT ? 0 : dj, rw = FLAT ? (dj << 3) + lw : w;
+                            if (j0 + jj < nd && (!FLAT || rw < p.W)) {
+                                ep_load_raw8<PL>(p.res, g.b, (p.res_c0 + c16) >> 3, rd, h, rw, rq[jj][0]);
                                 if (two)
-                                    ep_load_raw8<PL>(p.res, g.b, ((p.res_c0 + c16) >> 3) + 1, g.d0 + j0 + jj, h, w,
-                                                     rq[jj][1]);
+                                    ep_load_raw8<PL>(p.res, g.b, ((p.res_c0 + c16) >> 3) + 1, rd, h, rw, rq[jj][1]);
                             }
                         }
                     }
@@ -684,8 +694,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         const uint32_t r1off = (uint32_t)(p.fold ? (p.NP >> 1) : p.Dc * p.NP);
                         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + c16);
-                        ep_depth_batch<PL, 8, kJB, kJB>(p, g, tcol, r1off, two_regions, j0, nd, c16, valid, h, w, sp,
-                                                        s_scale, s_shift, rq);
+                        ep_depth_batch<PL, 8, kJB, kJB, FLAT>(p, g, tcol, r1off, two_regions, j0, nd, c16, valid, h, w, lw, sp,
+                                                              s_scale, s_shift, rq);
                         continue;
                     }
                     if (E8 != 1 && two) {
@@ -695,14 +705,16 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         const uint32_t r1off = (uint32_t)(p.fold ? (p.NP >> 1) : p.Dc * p.NP);
                         const uint32_t tcol = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + c16);
-                        ep_depth_batch<PL, 16, 2, kJB>(p, g, tcol, r1off, two_regions, j0, nd, c16, valid, h, w, sp,
-                                                       s_scale, s_shift, rq);
+                        ep_depth_batch<PL, 16, 2, kJB, FLAT>(p, g, tcol, r1off, two_regions, j0, nd, c16, valid, h, w, lw, sp,
+                                                             s_scale, s_shift, rq);
                         continue;
                     }
 #pragma unroll
                     for (int jj = 0; jj < kJB; ++jj) {
                         if (j0 + jj >= nd) break;
-                        const int d = g.d0 + j0 + jj;
+                        const int dj = g.d0 + j0 + jj;
+                        const int d = FLAT ? 0 : dj;
+                        const int w = FLAT ? (dj << 3) + lw : w_item;
                         // depth d of region r: column set*ngroups*Dc*NP + r*Dc*NP + (d_hi-1-d)*NP
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
@@ -727,7 +739,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 for (int i = 0; i < 16; ++i) acc[i] = __uint_as_float(ra[i]);
                             }
                         }
-                        if (!valid || TC_DBG(p, 1) || (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
+                        if (!valid || (FLAT && w >= p.W) || TC_DBG(p, 1) ||
+                            (p.cv_skip && lea_cv_collapsed(d, g.w0 >> 3, p.D, p.W))) continue;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             float v = acc[i] * s_scale[c16 + i] + s_shift[c16 + i];
@@ -778,10 +791,13 @@ static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
     if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3, E8>;      // 8-channel layout, 3 planes
     return lea_conv_tc_kernel<KS, 6, 3, E8>;                       // bf16x6
 }
-static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, int e8) {
-    if (e8 == 1) return ks == 3 ? tc_kernel_for_ks<3, 1>(nterm, planes) : tc_kernel_for_ks<1, 1>(nterm, planes);
-    if (e8 == 2) return ks == 3 ? tc_kernel_for_ks<3, 2>(nterm, planes) : tc_kernel_for_ks<1, 2>(nterm, planes);
-    return ks == 3 ? tc_kernel_for_ks<3, 0>(nterm, planes) : tc_kernel_for_ks<1, 0>(nterm, planes);
+static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, int e8) {      // ks: 1, 3, or 2 = flat 3x3 (depth-1 volumes)
+    if (e8 == 1) return ks == 3 ? tc_kernel_for_ks<3, 1>(nterm, planes) : ks == 2 ? tc_kernel_for_ks<2, 1>(nterm, planes)
+                                                                                  : tc_kernel_for_ks<1, 1>(nterm, planes);
+    if (e8 == 2) return ks == 3 ? tc_kernel_for_ks<3, 2>(nterm, planes) : ks == 2 ? tc_kernel_for_ks<2, 2>(nterm, planes)
+                                                                                  : tc_kernel_for_ks<1, 2>(nterm, planes);
+    return ks == 3 ? tc_kernel_for_ks<3, 0>(nterm, planes) : ks == 2 ? tc_kernel_for_ks<2, 0>(nterm, planes)
+                                                                      : tc_kernel_for_ks<1, 0>(nterm, planes);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1038,10 +1054,18 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // Round 2 measured a shared-memory-staged TMA-store epilogue - cp.async.bulk.tensor stores of each warp's 32-voxel box
     // per depth and 8-channel block, then one proxy fence per 4 boxes: the epilogue-bound convs lose 12-20 % against the
     // per-thread 16-byte stores below (8 -> 8 at 64x128x416, 4 pairs: 450 us -> 565 / 517 us); not kept.)
+    // Flat mode: a 3x3(x3) conv on a depth-1 volume (the 2-D feature net, the 2-D maps of the collapsed stem0) takes the
+    // 8-wide w tiles of a row of tiles as the "depth slices" of an item - no halo slabs, only the middle tap plane - so
+    // that one accumulator hand-over and one item set-up serve up to 16 tiles instead of one (they cost each role
+    // ~600 cycles per item, a third of a depth-1 item's time).
+    p.flat = (!fused && p.D == 1 && p.ks == 3 && !(opts && opts->debug & 16)) ? 1 : 0;
+    p.PD = (p.W + 7) / 8;
+    const int depth_n = p.flat ? p.PD : p.D;                   // slices an item chunks over
+    const bool dhalo = (p.ks == 3 && !p.flat);                 // halo slabs along the chunked axis
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
     if (p.nsets == 1 && 512 / (2 * accw) >= 2) {
-        const int halo = (p.ks == 3) ? 2 : 0;
-        const int nmax = (p.ks == 3 ? 3 : 1) * s.NP;
+        const int halo = dhalo ? 2 : 0;
+        const int nmax = (dhalo ? 3 : 1) * s.NP;
         const double M = (double)s.ncg * s.taps2d * p.nterm * (nmax / 2 > 64 ? nmax / 2 : 64);
         const double E = 650.0 * ((c->c_out + 15) / 16);
         const int d1 = 512 / accw, d2 = 512 / (2 * accw);
@@ -1070,35 +1094,36 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.blk_bytes = p.slab_vox * 16;
     p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
     p.stage_stride = (p.stage_bytes + 127) & ~127;
-    p.tiles_w = (p.W + tile_w - 1) / tile_w;
+    p.tiles_w = p.flat ? 1 : (p.W + tile_w - 1) / tile_w;
     p.tiles_h = (p.H + tile_h - 1) / tile_h;
     p.dbg = opts ? opts->debug : 0;
     p.cv_skip = (fused && opts->cv_skip == 1) ? 1 : 0;
     int dc_max = 512 / (p.nsets * accw);
     if (dc_max > 16) dc_max = 16;
-    if (dc_max > p.D) dc_max = p.D;
+    if (dc_max > depth_n) dc_max = depth_n;
     const int num_sms = (opts && opts->num_sms > 0) ? opts->num_sms : device_sm_count();
     // Depth slices per work item: an item of Dc slices streams Dc + 2*halo slabs at a fixed MMA cost per slab, and the
     // persistent grid runs ceil(items / SMs) items per CTA - pick the Dc that minimises slabs on the busiest SM.
     int Dc = 1;
     int64_t best = -1;
     for (int cand = 1; cand <= dc_max; ++cand) {
-        const int64_t items = (int64_t)p.B * ((p.D + cand - 1) / cand) * p.tiles_h * p.tiles_w;
-        const int64_t cost = ((items + num_sms - 1) / num_sms) * (cand + (p.ks == 3 ? 2 : 0));
+        const int64_t items = (int64_t)p.B * ((depth_n + cand - 1) / cand) * p.tiles_h * p.tiles_w;
+        // (flat mode: an item's set-up costs each role about half a slab of a small 2-D conv - without that term one tile
+        //  per item always wins the count of slabs and nothing is amortised)
+        const int64_t cost = ((items + num_sms - 1) / num_sms) * (p.flat ? 2 * cand + 1 : 2 * (cand + (dhalo ? 2 : 0)));
         if (best < 0 || cost < best || (cost == best && cand > Dc)) { best = cost; Dc = cand; }
     }
     if (opts && opts->depth_chunk > 0) Dc = opts->depth_chunk < dc_max ? opts->depth_chunk : dc_max;
     p.Dc = Dc;
-    // Short items (depth-1 volumes of the 2-D feature net, thin depth chunks): the accumulator hand-over between issuer
-    // and epilogue (tcgen05.commit -> epilogue -> arrive -> issuer) is a ~2600-cycle round trip that bounds the item rate
-    // at nsets items per round trip, whatever the work (measured: 1.07 us per item with neither MMAs nor epilogue work at
-    // two sets).  TMEM columns the depth chunk leaves unused therefore become further accumulator sets.
+    // TMEM columns a thin depth chunk leaves unused become further accumulator sets (more items in flight between issuer
+    // and epilogue).  Measured: no effect on the depth-1 convs it was tried for - their per-item cost was the item set-up
+    // of each role, not the hand-over round trip - and none anywhere else; kept because it is free.
     if (!(opts && (opts->acc_sets == 1 || opts->acc_sets == 2))) {
         int more = 512 / (accw * Dc);
         if (more > kMaxSets) more = kMaxSets;
         if (more > p.nsets) p.nsets = more;
     }
-    p.dchunks = (p.D + Dc - 1) / Dc;
+    p.dchunks = (depth_n + Dc - 1) / Dc;
     const int64_t total = (int64_t)p.B * p.dchunks * p.tiles_h * p.tiles_w;
     LEA_CHECK(total < (1ll << 31), "conv3d_tc: too many work items");
     p.total_items = (int)total;
@@ -1141,7 +1166,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
     const int e8 = (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0;
-    TcKernelFn kernel = tc_kernel_for(p.ks, p.nterm, P, e8);
+    TcKernelFn kernel = tc_kernel_for(p.flat ? 2 : p.ks, p.nterm, P, e8);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
