@@ -358,7 +358,7 @@ __device__ __forceinline__ void tc_touch16(uint32_t* r) {
 
 // Epilogue of one depth batch [j0, j0 + JB) of an item for the channel group at c16: NV = 8 or 16 accumulator columns
 // per region, SB depths per tcgen05.wait::ld.  rq = residual groups loaded by the caller (valid when p.has_res).
-// FLAT: the "depth" index of the item is a w tile of a depth-1 volume: voxel (0, h, 8 * d + lw).
+// FLAT: the "depth" index of the item is a w tile of a depth-1 volume: voxel (0, h, tile_w * d + lw).
 template <int PL, int NV, int SB, int JB, bool FLAT>
 __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom& g, uint32_t tcol, uint32_t r1off,
                                                bool two_regions, int j0, int nd, int c16, bool valid, int h, int w_in,
@@ -384,7 +384,7 @@ __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom
             if (j0 + jj >= nd) break;
             const int dj = g.d0 + j0 + jj;
             const int d = FLAT ? 0 : dj;
-            const int w = FLAT ? (dj << 3) + lw : w_in;
+            const int w = FLAT ? (dj << p.tw_log2) + lw : w_in;
             float acc[NV];
             if (NV == 8) tc_touch8(ra[s]); else tc_touch16(ra[s]);
             if (two_regions) {
@@ -466,10 +466,10 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // KS: 1 = 1x1x1, 3 = 3x3x3, 2 = 3x3 in the plane of a depth-1 volume ("flat": w tiles as the depth slices of an item)
-    constexpr int KT = (KS == 1) ? 1 : 3;                      // taps per in-plane axis
-    constexpr bool FLAT = (KS == 2);
-    constexpr int kHalo = (KS != 1) ? 1 : 0;
+    // KS: 1 = 1x1x1, 3 = 3x3x3; on depth-1 volumes ("flat": w tiles as the depth slices of an item) 2 = 3x3, 4 = 1x1
+    constexpr int KT = (KS == 1 || KS == 4) ? 1 : 3;           // taps per in-plane axis
+    constexpr bool FLAT = (KS == 2 || KS == 4);
+    constexpr int kHalo = (KT == 3) ? 1 : 0;
     constexpr int kPitch = LEA_TC_TW + 2 * kHalo;              // voxels per staged row
 
     if (warp == 0) {
@@ -510,7 +510,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                         gbase + (left ? cg : cg - p.ncg_half) * p.blocks_per_cg);
                         } else {
                             tma_load_4d(smem_u32(stages + (size_t)stage * p.stage_stride), &tmap, smem_u32(full + stage),
-                                        ((FLAT ? (d_in << 3) : g.w0) - kHalo) * 8, g.h0 - kHalo, FLAT ? 0 : d_in,
+                                        ((FLAT ? (d_in << p.tw_log2) : g.w0) - kHalo) * 8, g.h0 - kHalo, FLAT ? 0 : d_in,
                                         gbase + cg * p.blocks_per_cg);
                         }
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
@@ -570,7 +570,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     //   kd_a = 0 / 1 / 2 for d_in <= d_hi-2 / = d_hi-1 / = d_hi;   kd_b = 2 / 1 / 0 for d_in >= d0+1 / = d0 / = d0-1.
                     // Branch-free on purpose: this bookkeeping sits between the last MMA of a slab and the first of the next
                     // (the MMA queue is one deep), and as ternaries it compiled to a chain of ~10 uniform branches.
-                    int kd_a = FLAT ? 1 : 0, kd_b = FLAT ? 1 : 0;     // flat: the middle tap plane only, one "depth" per slab
+                    int kd_a = (KS == 2) ? 1 : 0, kd_b = kd_a;        // flat 3x3: the middle tap plane only, one "depth" per slab
                     if (KS == 3) {
                         // (measured: sums of compares instead of these clamps cost the issuer 4-7 % more cycles per item)
                         kd_a = min(max(d_in - (g.d_hi - 2), 0), 2);
@@ -672,7 +672,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
 #pragma unroll
                         for (int jj = 0; jj < kJB; ++jj) {
                             const int dj = g.d0 + j0 + jj;
-                            const int rd = FLAT ? 0 : dj, rw = FLAT ? (dj << 3) + lw : w;
+                            const int rd = FLAT ? 0 : dj, rw = FLAT ? (dj << p.tw_log2) + lw : w;
                             if (j0 + jj < nd && (!FLAT || rw < p.W)) {
                                 ep_load_raw8<PL>(p.res, g.b, (p.res_c0 + c16) >> 3, rd, h, rw, rq[jj][0]);
                                 if (two)
@@ -714,7 +714,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                         if (j0 + jj >= nd) break;
                         const int dj = g.d0 + j0 + jj;
                         const int d = FLAT ? 0 : dj;
-                        const int w = FLAT ? (dj << 3) + lw : w_item;
+                        const int w = FLAT ? (dj << p.tw_log2) + lw : w_item;
                         // depth d of region r: column set*ngroups*Dc*NP + r*Dc*NP + (d_hi-1-d)*NP
                         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) +
                                               (uint32_t)(set * p.ngroups * p.Dc * p.NP + (nd - 1 - (j0 + jj)) * p.NP);
@@ -791,13 +791,19 @@ static TcKernelFn tc_kernel_for_ks(int nterm, int planes) {
     if (nterm == 3) return lea_conv_tc_kernel<KS, 3, 3, E8>;      // 8-channel layout, 3 planes
     return lea_conv_tc_kernel<KS, 6, 3, E8>;                       // bf16x6
 }
-static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, int e8) {      // ks: 1, 3, or 2 = flat 3x3 (depth-1 volumes)
-    if (e8 == 1) return ks == 3 ? tc_kernel_for_ks<3, 1>(nterm, planes) : ks == 2 ? tc_kernel_for_ks<2, 1>(nterm, planes)
-                                                                                  : tc_kernel_for_ks<1, 1>(nterm, planes);
-    if (e8 == 2) return ks == 3 ? tc_kernel_for_ks<3, 2>(nterm, planes) : ks == 2 ? tc_kernel_for_ks<2, 2>(nterm, planes)
-                                                                                  : tc_kernel_for_ks<1, 2>(nterm, planes);
-    return ks == 3 ? tc_kernel_for_ks<3, 0>(nterm, planes) : ks == 2 ? tc_kernel_for_ks<2, 0>(nterm, planes)
-                                                                      : tc_kernel_for_ks<1, 0>(nterm, planes);
+template <int E8>
+static TcKernelFn tc_kernel_for_e8(int ks, int nterm, int planes) {      // ks: 1, 3, or flat (depth-1 volumes): 2 = 3x3, 4 = 1x1
+    switch (ks) {
+        case 3: return tc_kernel_for_ks<3, E8>(nterm, planes);
+        case 2: return tc_kernel_for_ks<2, E8>(nterm, planes);
+        case 4: return tc_kernel_for_ks<4, E8>(nterm, planes);
+        default: return tc_kernel_for_ks<1, E8>(nterm, planes);
+    }
+}
+static TcKernelFn tc_kernel_for(int ks, int nterm, int planes, int e8) {
+    if (e8 == 1) return tc_kernel_for_e8<1>(ks, nterm, planes);
+    if (e8 == 2) return tc_kernel_for_e8<2>(ks, nterm, planes);
+    return tc_kernel_for_e8<0>(ks, nterm, planes);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1058,9 +1064,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     // 8-wide w tiles of a row of tiles as the "depth slices" of an item - no halo slabs, only the middle tap plane - so
     // that one accumulator hand-over and one item set-up serve up to 16 tiles instead of one (they cost each role
     // ~600 cycles per item, a third of a depth-1 item's time).
-    p.flat = (!fused && p.D == 1 && p.ks == 3 && !(opts && opts->debug & 16)) ? 1 : 0;
-    p.PD = (p.W + 7) / 8;
-    const int depth_n = p.flat ? p.PD : p.D;                   // slices an item chunks over
+    p.flat = (!fused && p.D == 1 && c->dst_f32 == nullptr && !(opts && opts->debug & 16)) ? 1 : 0;
     const bool dhalo = (p.ks == 3 && !p.flat);                 // halo slabs along the chunked axis
     p.nsets = (512 / (2 * accw) >= 4) ? 2 : 1;
     if (p.nsets == 1 && 512 / (2 * accw) >= 2) {
@@ -1094,6 +1098,8 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.blk_bytes = p.slab_vox * 16;
     p.stage_bytes = p.blocks_per_cg * p.blk_bytes;
     p.stage_stride = (p.stage_bytes + 127) & ~127;
+    p.PD = (p.W + tile_w - 1) / tile_w;
+    const int depth_n = p.flat ? p.PD : p.D;                   // slices an item chunks over
     p.tiles_w = p.flat ? 1 : (p.W + tile_w - 1) / tile_w;
     p.tiles_h = (p.H + tile_h - 1) / tile_h;
     p.dbg = opts ? opts->debug : 0;
@@ -1166,7 +1172,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
     const int e8 = (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0;
-    TcKernelFn kernel = tc_kernel_for(p.flat ? 2 : p.ks, p.nterm, P, e8);
+    TcKernelFn kernel = tc_kernel_for(p.flat ? (p.ks == 3 ? 2 : 4) : p.ks, p.nterm, P, e8);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;
