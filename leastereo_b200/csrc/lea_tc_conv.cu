@@ -51,7 +51,7 @@ constexpr int kMaxSets = 8;      // TMEM accumulator sets (work items in flight 
 constexpr int kMaxStages = 24;   // deep enough that 8 KB 1x1x1 stages keep ~1.5 us of HBM latency covered
 constexpr int kSmemBudget = 227 * 1024;
 constexpr int kHeaderBytes = 2048;
-static_assert(8 * (2 * kMaxStages + 4 + 2 * kMaxSets) <= 1024, "barriers must fit below the BN vectors at byte 1024");
+static_assert(8 * (2 * kMaxStages + 4 + 2 * kMaxSets + 6) <= 1024, "barriers must fit below the BN vectors at byte 1024");
 #ifdef LEA_TC_SOFT_TIMEOUT
 constexpr unsigned long long kWaitTimeoutCycles = 100000000ull;
 #else
@@ -85,6 +85,7 @@ struct TcParams {
     int nbt, nb_rows, btile_bytes, wpart_bytes;
     int slab_vox, pitch_vox, blk_bytes, stage_bytes, stage_stride;   // stride = bytes rounded up to 128 (TMA alignment)
     int nstages, nwbuf;
+    int wsplit;               // single streamed weight buffer handed over in three parts (one per kh), see the producer
     int tw_log2;              // tile = (1 << tw_log2) voxels along w x (128 >> tw_log2) along h  (3 for k = 3)
     int cv_skip;              // collapsed stem0: skip the voxels lea_stem0_assemble writes (lea_cv_interior)
     int dbg;                  // development switches (bit 0: epilogue skips its stores, bit 1: skips the TMEM loads, bit 2: skips the
@@ -429,6 +430,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     uint64_t* wempty = wfull + 2;                   // [2]
     uint64_t* accfull = wempty + 2;                 // [kMaxSets]
     uint64_t* accempty = accfull + kMaxSets;        // [kMaxSets]
+    uint64_t* w3full = accempty + kMaxSets;         // [3]  weight parts (kh = 0, 1, 2) of the single streamed buffer (p.wsplit)
+    uint64_t* w3empty = w3full + 3;                 // [3]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 1536);
     float* s_scale = reinterpret_cast<float*>(smem + 1024);     // [64]  (barriers occupy the first KB)
     float* s_shift = s_scale + 64;                              // [64]
@@ -446,6 +449,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (threadIdx.x == 0) {
         for (int i = 0; i < p.nstages; ++i) { mbar_init(smem_u32(full + i), 1); mbar_init(smem_u32(empty + i), 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(wfull + i), 1); mbar_init(smem_u32(wempty + i), 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(smem_u32(w3full + i), 1); mbar_init(smem_u32(w3empty + i), 1); }
         for (int i = 0; i < kMaxSets; ++i) {
             mbar_init(smem_u32(accfull + i), 1); mbar_init(smem_u32(accempty + i), 32 * epi_warps(PL, E8));
         }
@@ -475,7 +479,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            int stage = 0, sphase = 0, wb = 0, wphase = 0;
+            int stage = 0, sphase = 0, wb = 0, wphase = 0, wuse = 0;
             TC_PROF_DECL;
             if (p.wres) {                         // all weight parts fit: load them once, they stay for every item
                 mbar_arrive_expect_tx(smem_u32(wfull), (uint32_t)(p.ncg * p.wpart_bytes));
@@ -490,7 +494,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 if (item_skipped(p, g)) continue;
                 const int gbase = g.b * p.g0_stride_b + p.g0_first;
                 for (int cg = 0; cg < p.ncg; ++cg) {
-                    if (!p.wres) {
+                    if (!p.wres && !p.wsplit) {
                         TC_PROF_WAIT(mbar_wait(smem_u32(wempty + wb), wphase ^ 1, 101));
                         mbar_arrive_expect_tx(smem_u32(wfull + wb), (uint32_t)p.wpart_bytes);
                         bulk_load(smem_u32(wbuf + (size_t)wb * wbuf_stride), p.wimg + (size_t)cg * p.wpart_bytes,
@@ -514,6 +518,23 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                         gbase + cg * p.blocks_per_cg);
                         }
                         if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                    }
+                    if (p.wsplit) {
+                        // conv1 / conv2: the 111 KB weight part of a channel group leaves room for ONE weight buffer, and
+                        // waiting for the issuer to finish a group before its successor's weights are even requested cost
+                        // ~1900 idle tensor-pipe cycles per group (measured: issuer 22 % in waits).  The buffer is handed
+                        // over in three parts, one per kh: a part is reloaded as soon as the issuer has run the last slab's
+                        // taps of that kh, while the taps of the later kh still execute.  The group's activation slabs are
+                        // requested BEFORE its weights so that they do not queue behind the hand-over.
+                        const uint32_t part = (uint32_t)p.wpart_bytes / 3u;
+#pragma unroll 1
+                        for (int kh = 0; kh < 3; ++kh) {
+                            TC_PROF_WAIT(mbar_wait(smem_u32(w3empty + kh), (uint32_t)((wuse & 1) ^ 1), 103));
+                            mbar_arrive_expect_tx(smem_u32(w3full + kh), part);
+                            bulk_load(smem_u32(wbuf) + (uint32_t)kh * part, p.wimg + (size_t)cg * p.wpart_bytes + (size_t)kh * part,
+                                      part, smem_u32(w3full + kh));
+                        }
+                        ++wuse;
                     }
                 }
                 TC_PROF_ITEM;
@@ -544,7 +565,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;                   // LBO = nb_rows*16 B
         const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per (kh,kw) / 16
         const uint32_t set_cols = (uint32_t)(p.ngroups * p.Dc * p.NP);
-        int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0;
+        int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0, wuse = 0;
         uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
                                  // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
         TC_PROF_DECL;
@@ -560,7 +581,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             tc_fence_after();
             const uint32_t set_base = tmem_base + (uint32_t)set * set_cols;
             for (int cg = 0; cg < p.ncg; ++cg) {
-                if (!p.wres) TC_PROF_WAIT(mbar_wait(smem_u32(wfull + wb), wphase, 202));
+                if (!p.wres && !p.wsplit) TC_PROF_WAIT(mbar_wait(smem_u32(wfull + wb), wphase, 202));
                 const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                     if (!probed) TC_PROF_WAIT(mbar_wait(smem_u32(full + stage), sphase, 203));
@@ -597,9 +618,17 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     if (TC_DBG(p, 8)) {                // development: no MMAs - what the TMA ring and the epilogue cost alone
                         const bool wrap = (stage + 1 == p.nstages);
                         probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
+                        if (p.wsplit) {
+                            for (int kh = 0; kh < 3; ++kh) {
+                                if (d_in == g.dlo) mbar_wait(smem_u32(w3full + kh), (uint32_t)(wuse & 1), 204);
+                                if (d_in == g.dhi) tc_commit_if(elected, smem_u32(w3empty + kh));
+                            }
+                        }
                     } else
 #pragma unroll
                     for (int kh = 0; kh < KT; ++kh) {
+                        if (KS == 3 && p.wsplit && d_in == g.dlo)          // this group's weight part for kh has landed
+                            TC_PROF_WAIT(mbar_wait(smem_u32(w3full + kh), (uint32_t)(wuse & 1), 204));
 #pragma unroll
                         for (int kw = 0; kw < KT; ++kw) {
                             const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
@@ -624,11 +653,14 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
                             }
                         }
+                        if (KS == 3 && p.wsplit && d_in == g.dhi)          // last slab of the group: part kh may be reloaded
+                            tc_commit_if(elected, smem_u32(w3empty + kh));
                     }
                     tc_commit_if(elected, smem_u32(empty + stage));
                     if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
                 }
-                if (!p.wres) {
+                if (p.wsplit) ++wuse;
+                else if (!p.wres) {
                     tc_commit_if(elected, smem_u32(wempty + wb));
                     if (++wb == p.nwbuf) { wb = 0; wphase ^= 1; }
                 }
@@ -1140,10 +1172,15 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     p.wres = (kHeaderBytes + (int64_t)p.ncg * wstride + 6 * (int64_t)p.stage_stride <= kSmemBudget) ? 1 : 0;
     if (opts && opts->resident_weights == 2) p.wres = 0;
     if (p.wres) p.nwbuf = p.ncg;
+
     int nst = (kSmemBudget - kHeaderBytes - p.nwbuf * wstride) / p.stage_stride;
     if (nst > kMaxStages) nst = kMaxStages;
     LEA_CHECK(nst >= 2, "conv3d_tc: shared memory too small for this shape (weights part %d B)", p.wpart_bytes);
     p.nstages = nst;
+    // (the producer requests a group's slabs before its weight parts: the ring must hold all of them, or it would wait for
+    //  slots that the issuer - waiting for those weights - never frees)
+    p.wsplit = (!p.wres && p.nwbuf == 1 && p.ks == 3 && !p.flat && !fused && (p.wpart_bytes % 48) == 0 &&
+                p.nstages >= p.Dc + 3 && !(opts && opts->debug & 32)) ? 1 : 0;
     p.swap_lbo_sbo = swap_lbo_sbo;
     p.wimg = reinterpret_cast<const uint8_t*>(wimg);
     p.bn_scale = c->bn_scale; p.bn_shift = c->bn_shift; p.relu = c->relu;

@@ -9,7 +9,8 @@ ops = Ops(os.path.join(ROOT, "leastereo_b200", "_C", "libleastereo_b200_abl.so")
 dev = torch.device("cuda:0")
 cases = [("feat 8->8 3x3 P3", 16, 8, 8, 3, 3, (1, 128, 416)), ("feat 32->8 1x1 P3", 16, 32, 8, 1, 3, (1, 128, 416)),
          ("L1 16->16 P2", 4, 16, 16, 3, 2, (32, 64, 208)), ("L0 8->8 P2", 4, 8, 8, 3, 2, (64, 128, 416)),
-         ("L1 64->16 1x1 P2", 4, 64, 16, 1, 2, (32, 64, 208)), ("stem1 32->32 P2", 2, 32, 32, 3, 2, (64, 128, 416))]
+         ("L1 64->16 1x1 P2", 4, 64, 16, 1, 2, (32, 64, 208)), ("stem1 32->32 P2", 2, 32, 32, 3, 2, (64, 128, 416)), ("conv1 128->64 P2", 4, 128, 64, 3, 2, (32, 64, 208)),
+         ("stem0 64->32 P2", 1, 64, 32, 3, 2, (64, 128, 416))]
 for name, N, ci, co, k, P, (D, H, W) in cases:
     w = torch.randn(co, ci, k, k, k, device=dev) * 0.05
     sc = torch.ones(co, device=dev); sh = torch.zeros(co, device=dev)
