@@ -470,9 +470,13 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // KS: 1 = 1x1x1, 3 = 3x3x3; on depth-1 volumes ("flat": w tiles as the depth slices of an item) 2 = 3x3, 4 = 1x1
+    // KS: 1 = 1x1x1, 3 = 3x3x3, 5 = 3x3x3 with the single streamed weight buffer handed over in three parts (p.wsplit; a
+    // variant of its own because even never-taken hooks in the tap loops cost every 3x3x3 kernel 2-4 % of its issuer cycles);
+    // on depth-1 volumes ("flat": w tiles as the depth slices of an item) 2 = 3x3, 4 = 1x1
     constexpr int KT = (KS == 1 || KS == 4) ? 1 : 3;           // taps per in-plane axis
     constexpr bool FLAT = (KS == 2 || KS == 4);
+    constexpr bool K3 = (KS == 3 || KS == 5);                  // three tap planes along depth, halo slabs
+    constexpr bool WSPLIT = (KS == 5);
     constexpr int kHalo = (KT == 3) ? 1 : 0;
     constexpr int kPitch = LEA_TC_TW + 2 * kHalo;              // voxels per staged row
 
@@ -547,15 +551,14 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t elected = elect_one();
         uint32_t a_term16[NTERM], a_lbo_field[NTERM], b_term16[NTERM], reg_col[NTERM];
         bool t_first[NTERM];
-        uint32_t t_skip[NTERM], t_skip_idesc[NTERM];
+        uint32_t t_skip_idesc[NTERM];
 #pragma unroll
         for (int t = 0; t < NTERM; ++t) {
-            t_skip[t] = (uint32_t)p.term_skip[t];
             t_skip_idesc[t] = ((uint32_t)p.term_skip[t] >> 3) << 17;         // make_idesc is linear in N
             a_term16[t] = (uint32_t)(p.term_aoff[t] * p.blk_bytes) >> 4;
             a_lbo_field[t] = ((uint32_t)(p.term_lbo_blocks[t] * p.blk_bytes) >> 4) << 16;
             b_term16[t] = (uint32_t)(p.term_btile[t] * p.btile_bytes) >> 4;
-            reg_col[t] = (uint32_t)(p.term_region[t] * p.Dc * p.NP);
+            reg_col[t] = (uint32_t)(p.term_region[t] * p.Dc * p.NP) + (uint32_t)p.term_skip[t];    // (a term's skipped columns)
             t_first[t] = p.term_first[t] != 0;
         }
         const int NPv = p.NP;
@@ -592,19 +595,19 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     // Branch-free on purpose: this bookkeeping sits between the last MMA of a slab and the first of the next
                     // (the MMA queue is one deep), and as ternaries it compiled to a chain of ~10 uniform branches.
                     int kd_a = (KS == 2) ? 1 : 0, kd_b = kd_a;        // flat 3x3: the middle tap plane only, one "depth" per slab
-                    if (KS == 3) {
+                    if (K3) {
                         // (measured: sums of compares instead of these clamps cost the issuer 4-7 % more cycles per item)
                         kd_a = min(max(d_in - (g.d_hi - 2), 0), 2);
                         kd_b = min(max(d_in - g.d0 + 1, 0), 2);
                     }
                     const int nkd = kd_b - kd_a + 1;
                     // accumulators are stored in descending depth order: depth d sits at column (d_hi-1-d)*NP
-                    const int d_top = (KS == 3) ? d_in + 1 - kd_a : d_in;
+                    const int d_top = K3 ? d_in + 1 - kd_a : d_in;
                     const uint32_t col0 = (uint32_t)((g.d_hi - 1 - d_top) * NPv);
                     // depths touched for the first time by this slab (only while the first channel group runs):
                     // kd = 0 always opens depth d_in+1; at d_in == 0 depth 0 (kd = 1) opens too
                     int nfresh = 1;
-                    if (KS == 3) {
+                    if (K3) {
                         const int z = (d_in == 0) ? 1 : 0;
                         nfresh = ((kd_a == 0) ? 1 : 0) + (z & ((((kd_a == 0) ? 1 : 0) & ((kd_b >= 1) ? 1 : 0)) | ((kd_a == 1) ? 1 : 0)));
                     }
@@ -612,6 +615,9 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     const uint32_t brow16 = (uint32_t)(kd_a * NPv);               // first weight row used, x16 B
                     // the instruction descriptor is linear in N: idesc(k * NP) = idesc0 + k * idesc_step
                     const uint32_t idesc_all = idesc0 + (uint32_t)nkd * idesc_step;
+                    uint32_t idesc_t[NTERM];                            // per term: N less the columns the term skips
+#pragma unroll
+                    for (int t = 0; t < NTERM; ++t) idesc_t[t] = idesc_all - t_skip_idesc[t];
                     const uint32_t idesc_fresh = idesc0 + (uint32_t)nfresh * idesc_step;
                     const int nrest = nkd - nfresh;
                     const uint32_t idesc_rest = idesc0 + (uint32_t)nrest * idesc_step;
@@ -627,7 +633,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     } else
 #pragma unroll
                     for (int kh = 0; kh < KT; ++kh) {
-                        if (KS == 3 && p.wsplit && d_in == g.dlo)          // this group's weight part for kh has landed
+                        if (WSPLIT && d_in == g.dlo)                        // this group's weight part for kh has landed
                             TC_PROF_WAIT(mbar_wait(smem_u32(w3full + kh), (uint32_t)(wuse & 1), 204));
 #pragma unroll
                         for (int kw = 0; kw < KT; ++kw) {
@@ -644,8 +650,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                         tc_mma_issue(elected, dcol + (uint32_t)(nfresh * NPv), a_lo, a_hi,
                                                      b_lo + (uint32_t)(nfresh * NPv), b_hi, idesc_rest, 1u);
                                 } else {
-                                    tc_mma_issue(elected, dcol + t_skip[t], a_lo, a_hi, b_lo, b_hi,
-                                                 idesc_all - t_skip_idesc[t], 1u);
+                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_t[t], 1u);
                                 }
                             }
                             if (kh == 0 && kw == 0) {
@@ -653,7 +658,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                                 probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
                             }
                         }
-                        if (KS == 3 && p.wsplit && d_in == g.dhi)          // last slab of the group: part kh may be reloaded
+                        if (WSPLIT && d_in == g.dhi)                        // last slab of the group: part kh may be reloaded
                             tc_commit_if(elected, smem_u32(w3empty + kh));
                     }
                     tc_commit_if(elected, smem_u32(empty + stage));
@@ -829,6 +834,7 @@ static TcKernelFn tc_kernel_for_e8(int ks, int nterm, int planes) {      // ks: 
         case 3: return tc_kernel_for_ks<3, E8>(nterm, planes);
         case 2: return tc_kernel_for_ks<2, E8>(nterm, planes);
         case 4: return tc_kernel_for_ks<4, E8>(nterm, planes);
+        case 5: return tc_kernel_for_ks<5, E8>(nterm, planes);
         default: return tc_kernel_for_ks<1, E8>(nterm, planes);
     }
 }
@@ -1209,7 +1215,7 @@ int tc_launch(const lea_conv* c, const void* wimg, const lea_tc_opts* opts, void
     LEA_CHECK(cr == CUDA_SUCCESS, "conv3d_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
     const int e8 = (p.c_out & 15) == 8 ? (p.c_out == 8 ? 1 : 2) : 0;
-    TcKernelFn kernel = tc_kernel_for(p.flat ? (p.ks == 3 ? 2 : 4) : p.ks, p.nterm, P, e8);
+    TcKernelFn kernel = tc_kernel_for(p.flat ? (p.ks == 3 ? 2 : 4) : (p.wsplit ? 5 : p.ks), p.nterm, P, e8);
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
     LEA_CHECK(e == cudaSuccess, "conv3d_tc: cannot raise dynamic shared memory: %s", cudaGetErrorString(e));
     const int grid = p.total_items < num_sms ? p.total_items : num_sms;

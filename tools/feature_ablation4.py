@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tools"))
 from leastereo_b200.kernels import Ops, PlanesVol, lea_tc_opts  # noqa: E402
 
-ops = Ops(os.path.join(ROOT, "leastereo_b200", "_C", "libleastereo_b200_abl.so"))
+ops = Ops(os.path.join(ROOT, "leastereo_b200", "_C", os.environ.get("ABL_LIB", "libleastereo_b200_abl.so")))
 dev = torch.device("cuda:0")
 cases = [("feat 8->8 3x3 P3", 16, 8, 8, 3, 3, (1, 128, 416)), ("feat 32->8 1x1 P3", 16, 32, 8, 1, 3, (1, 128, 416)),
          ("L1 16->16 P2", 4, 16, 16, 3, 2, (32, 64, 208)), ("L0 8->8 P2", 4, 8, 8, 3, 2, (64, 128, 416)),
