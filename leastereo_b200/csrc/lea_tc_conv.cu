@@ -616,8 +616,14 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                     // the instruction descriptor is linear in N: idesc(k * NP) = idesc0 + k * idesc_step
                     const uint32_t idesc_all = idesc0 + (uint32_t)nkd * idesc_step;
                     uint32_t idesc_t[NTERM];                            // per term: N less the columns the term skips
+                    uint32_t a_base[NTERM], b_base[NTERM], d_base[NTERM];
 #pragma unroll
-                    for (int t = 0; t < NTERM; ++t) idesc_t[t] = idesc_all - t_skip_idesc[t];
+                    for (int t = 0; t < NTERM; ++t) {
+                        idesc_t[t] = idesc_all - t_skip_idesc[t];
+                        a_base[t] = (s16 + a_term16[t]) | a_lbo_field[t];   // (the tap offset added later cannot carry into the LBO field)
+                        b_base[t] = w16 + b_term16[t] + brow16;
+                        d_base[t] = set_base + reg_col[t] + col0;
+                    }
                     const uint32_t idesc_fresh = idesc0 + (uint32_t)nfresh * idesc_step;
                     const int nrest = nkd - nfresh;
                     const uint32_t idesc_rest = idesc0 + (uint32_t)nrest * idesc_step;
@@ -637,13 +643,13 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             TC_PROF_WAIT(mbar_wait(smem_u32(w3full + kh), (uint32_t)(wuse & 1), 204));
 #pragma unroll
                         for (int kw = 0; kw < KT; ++kw) {
-                            const uint32_t a_tap = s16 + (uint32_t)(kh * kPitch + kw);
-                            const uint32_t b_tap = w16 + (uint32_t)(kh * KT + kw) * tap16 + brow16;
 #pragma unroll
                             for (int t = 0; t < NTERM; ++t) {
-                                const uint32_t a_lo = (a_tap + a_term16[t]) | a_lbo_field[t];
-                                const uint32_t b_lo = b_tap + b_term16[t];
-                                const uint32_t dcol = set_base + reg_col[t] + col0;
+                                // per-slab, per-term bases (below) + one add each per MMA: the operands of an MMA must not sit
+                                // at the end of a chain of dependent uniform-datapath instructions (each ~10 cycles)
+                                const uint32_t a_lo = a_base[t] + (uint32_t)(kh * kPitch + kw);
+                                const uint32_t b_lo = b_base[t] + (uint32_t)(kh * KT + kw) * tap16;
+                                const uint32_t dcol = d_base[t];
                                 if (kh == 0 && kw == 0 && t_first[t] && nfresh > 0) {
                                     tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
                                     if (nrest > 0)
