@@ -568,6 +568,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t b_lbo_field = (uint32_t)p.nb_rows << 16;                   // LBO = nb_rows*16 B
         const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per (kh,kw) / 16
         const uint32_t set_cols = (uint32_t)(p.ngroups * p.Dc * p.NP);
+        const uint32_t stages16 = smem_u32(stages) >> 4, stride16 = (uint32_t)p.stage_stride >> 4;   // (128 B multiples)
         int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0, wuse = 0;
         uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
                                  // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
@@ -589,7 +590,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                     if (!probed) TC_PROF_WAIT(mbar_wait(smem_u32(full + stage), sphase, 203));
                     tc_fence_after();
-                    const uint32_t s16 = smem_u32(stages + (size_t)stage * p.stage_stride) >> 4;
+                    const uint32_t s16 = stages16 + (uint32_t)stage * stride16;
                     // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi):
                     //   kd_a = 0 / 1 / 2 for d_in <= d_hi-2 / = d_hi-1 / = d_hi;   kd_b = 2 / 1 / 0 for d_in >= d0+1 / = d0 / = d0-1.
                     // Branch-free on purpose: this bookkeeping sits between the last MMA of a slab and the first of the next
