@@ -418,6 +418,14 @@ __device__ __forceinline__ void ep_depth_batch(const TcParams& p, const ItemGeom
     }
 }
 
+// what the MMA issuer needs for one activation slab (computed one slab ahead)
+template <int NTERM>
+struct SlabPar {
+    uint32_t idesc_t[NTERM], a_base[NTERM], b_base[NTERM], d_base[NTERM];
+    uint32_t idesc_fresh, idesc_rest, fresh_cols;
+    int nfresh, nrest;
+};
+
 template <int KS, int NTERM, int PL, int E8>
 __global__ void __launch_bounds__(tc_threads(PL, E8), 1)
 lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TcParams p) {
@@ -573,6 +581,47 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
                                  // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
         TC_PROF_DECL;
+        auto slab_par = [&](int d_in, int cg, int stage_v, uint32_t w16, uint32_t set_base, const ItemGeom& g) {
+            SlabPar<NTERM> r;
+            const uint32_t s16 = stages16 + (uint32_t)stage_v * stride16;
+            // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi):
+            //   kd_a = 0 / 1 / 2 for d_in <= d_hi-2 / = d_hi-1 / = d_hi;   kd_b = 2 / 1 / 0 for d_in >= d0+1 / = d0 / = d0-1.
+            // Branch-free on purpose (as ternaries it compiled to a chain of ~10 uniform branches).
+            int kd_a = (KS == 2) ? 1 : 0, kd_b = kd_a;        // flat 3x3: the middle tap plane only, one "depth" per slab
+            if (K3) {
+                // (measured: sums of compares instead of these clamps cost the issuer 4-7 % more cycles per item)
+                kd_a = min(max(d_in - (g.d_hi - 2), 0), 2);
+                kd_b = min(max(d_in - g.d0 + 1, 0), 2);
+            }
+            const int nkd = kd_b - kd_a + 1;
+            // accumulators are stored in descending depth order: depth d sits at column (d_hi-1-d)*NP
+            const int d_top = K3 ? d_in + 1 - kd_a : d_in;
+            const uint32_t col0 = (uint32_t)((g.d_hi - 1 - d_top) * NPv);
+            // depths touched for the first time by this slab (only while the first channel group runs):
+            // kd = 0 always opens depth d_in+1; at d_in == 0 depth 0 (kd = 1) opens too
+            int nfresh = 1;
+            if (K3) {
+                const int z = (d_in == 0) ? 1 : 0;
+                nfresh = ((kd_a == 0) ? 1 : 0) + (z & ((((kd_a == 0) ? 1 : 0) & ((kd_b >= 1) ? 1 : 0)) | ((kd_a == 1) ? 1 : 0)));
+            }
+            nfresh = (cg == 0) ? nfresh : 0;
+            const uint32_t brow16 = (uint32_t)(kd_a * NPv);               // first weight row used, x16 B
+            // the instruction descriptor is linear in N: idesc(k * NP) = idesc0 + k * idesc_step
+            const uint32_t idesc_all = idesc0 + (uint32_t)nkd * idesc_step;
+#pragma unroll
+            for (int t = 0; t < NTERM; ++t) {
+                r.idesc_t[t] = idesc_all - t_skip_idesc[t];            // per term: N less the columns the term skips
+                r.a_base[t] = (s16 + a_term16[t]) | a_lbo_field[t];   // (the tap offset added later cannot carry into the LBO field)
+                r.b_base[t] = w16 + b_term16[t] + brow16;
+                r.d_base[t] = set_base + reg_col[t] + col0;
+            }
+            r.nfresh = nfresh;
+            r.nrest = nkd - nfresh;
+            r.fresh_cols = (uint32_t)(nfresh * NPv);
+            r.idesc_fresh = idesc0 + (uint32_t)nfresh * idesc_step;
+            r.idesc_rest = idesc0 + (uint32_t)r.nrest * idesc_step;
+            return r;
+        };
         if (p.wres) mbar_wait(smem_u32(wfull), 0, 202);
         ItemCursor cur;
         cur.init(p, blockIdx.x);
@@ -587,56 +636,24 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
             for (int cg = 0; cg < p.ncg; ++cg) {
                 if (!p.wres && !p.wsplit) TC_PROF_WAIT(mbar_wait(smem_u32(wfull + wb), wphase, 202));
                 const uint32_t w16 = (smem_u32(wbuf + (size_t)(p.wres ? cg : wb) * wbuf_stride) >> 4) | b_lbo_field;
+                // Slab parameters are computed one slab ahead (before the last tap of the previous slab is issued): the
+                // bookkeeping then runs while MMAs execute instead of between the last MMA of a slab and the first of the next.
+                SlabPar<NTERM> sp = slab_par(g.dlo, cg, stage, w16, set_base, g);
                 for (int d_in = g.dlo; d_in <= g.dhi; ++d_in) {
                     if (!probed) TC_PROF_WAIT(mbar_wait(smem_u32(full + stage), sphase, 203));
                     tc_fence_after();
-                    const uint32_t s16 = stages16 + (uint32_t)stage * stride16;
-                    // valid kd range of this slab: output depth d = d_in + 1 - kd must lie in [d0, d_hi):
-                    //   kd_a = 0 / 1 / 2 for d_in <= d_hi-2 / = d_hi-1 / = d_hi;   kd_b = 2 / 1 / 0 for d_in >= d0+1 / = d0 / = d0-1.
-                    // Branch-free on purpose: this bookkeeping sits between the last MMA of a slab and the first of the next
-                    // (the MMA queue is one deep), and as ternaries it compiled to a chain of ~10 uniform branches.
-                    int kd_a = (KS == 2) ? 1 : 0, kd_b = kd_a;        // flat 3x3: the middle tap plane only, one "depth" per slab
-                    if (K3) {
-                        // (measured: sums of compares instead of these clamps cost the issuer 4-7 % more cycles per item)
-                        kd_a = min(max(d_in - (g.d_hi - 2), 0), 2);
-                        kd_b = min(max(d_in - g.d0 + 1, 0), 2);
-                    }
-                    const int nkd = kd_b - kd_a + 1;
-                    // accumulators are stored in descending depth order: depth d sits at column (d_hi-1-d)*NP
-                    const int d_top = K3 ? d_in + 1 - kd_a : d_in;
-                    const uint32_t col0 = (uint32_t)((g.d_hi - 1 - d_top) * NPv);
-                    // depths touched for the first time by this slab (only while the first channel group runs):
-                    // kd = 0 always opens depth d_in+1; at d_in == 0 depth 0 (kd = 1) opens too
-                    int nfresh = 1;
-                    if (K3) {
-                        const int z = (d_in == 0) ? 1 : 0;
-                        nfresh = ((kd_a == 0) ? 1 : 0) + (z & ((((kd_a == 0) ? 1 : 0) & ((kd_b >= 1) ? 1 : 0)) | ((kd_a == 1) ? 1 : 0)));
-                    }
-                    nfresh = (cg == 0) ? nfresh : 0;
-                    const uint32_t brow16 = (uint32_t)(kd_a * NPv);               // first weight row used, x16 B
-                    // the instruction descriptor is linear in N: idesc(k * NP) = idesc0 + k * idesc_step
-                    const uint32_t idesc_all = idesc0 + (uint32_t)nkd * idesc_step;
-                    uint32_t idesc_t[NTERM];                            // per term: N less the columns the term skips
-                    uint32_t a_base[NTERM], b_base[NTERM], d_base[NTERM];
-#pragma unroll
-                    for (int t = 0; t < NTERM; ++t) {
-                        idesc_t[t] = idesc_all - t_skip_idesc[t];
-                        a_base[t] = (s16 + a_term16[t]) | a_lbo_field[t];   // (the tap offset added later cannot carry into the LBO field)
-                        b_base[t] = w16 + b_term16[t] + brow16;
-                        d_base[t] = set_base + reg_col[t] + col0;
-                    }
-                    const uint32_t idesc_fresh = idesc0 + (uint32_t)nfresh * idesc_step;
-                    const int nrest = nkd - nfresh;
-                    const uint32_t idesc_rest = idesc0 + (uint32_t)nrest * idesc_step;
+                    SlabPar<NTERM> nx = sp;
+                    const bool wrap = (stage + 1 == p.nstages);
+                    const int stage_n = wrap ? 0 : stage + 1;
                     if (TC_DBG(p, 8)) {                // development: no MMAs - what the TMA ring and the epilogue cost alone
-                        const bool wrap = (stage + 1 == p.nstages);
-                        probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
+                        probed = mbar_test(smem_u32(full + stage_n), (uint32_t)(wrap ? sphase ^ 1 : sphase));
                         if (p.wsplit) {
                             for (int kh = 0; kh < 3; ++kh) {
                                 if (d_in == g.dlo) mbar_wait(smem_u32(w3full + kh), (uint32_t)(wuse & 1), 204);
                                 if (d_in == g.dhi) tc_commit_if(elected, smem_u32(w3empty + kh));
                             }
                         }
+                        nx = slab_par(d_in + 1, cg, stage_n, w16, set_base, g);
                     } else
 #pragma unroll
                     for (int kh = 0; kh < KT; ++kh) {
@@ -644,32 +661,33 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
                             TC_PROF_WAIT(mbar_wait(smem_u32(w3full + kh), (uint32_t)(wuse & 1), 204));
 #pragma unroll
                         for (int kw = 0; kw < KT; ++kw) {
+                            if (KT > 1 && kh == KT - 1 && kw == KT - 1) nx = slab_par(d_in + 1, cg, stage_n, w16, set_base, g);
 #pragma unroll
                             for (int t = 0; t < NTERM; ++t) {
-                                // per-slab, per-term bases (below) + one add each per MMA: the operands of an MMA must not sit
+                                // per-slab, per-term bases + one add each per MMA: the operands of an MMA must not sit
                                 // at the end of a chain of dependent uniform-datapath instructions (each ~10 cycles)
-                                const uint32_t a_lo = a_base[t] + (uint32_t)(kh * kPitch + kw);
-                                const uint32_t b_lo = b_base[t] + (uint32_t)(kh * KT + kw) * tap16;
-                                const uint32_t dcol = d_base[t];
-                                if (kh == 0 && kw == 0 && t_first[t] && nfresh > 0) {
-                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_fresh, 0u);
-                                    if (nrest > 0)
-                                        tc_mma_issue(elected, dcol + (uint32_t)(nfresh * NPv), a_lo, a_hi,
-                                                     b_lo + (uint32_t)(nfresh * NPv), b_hi, idesc_rest, 1u);
+                                const uint32_t a_lo = sp.a_base[t] + (uint32_t)(kh * kPitch + kw);
+                                const uint32_t b_lo = sp.b_base[t] + (uint32_t)(kh * KT + kw) * tap16;
+                                const uint32_t dcol = sp.d_base[t];
+                                if (kh == 0 && kw == 0 && t_first[t] && sp.nfresh > 0) {
+                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, sp.idesc_fresh, 0u);
+                                    if (sp.nrest > 0)
+                                        tc_mma_issue(elected, dcol + sp.fresh_cols, a_lo, a_hi,
+                                                     b_lo + sp.fresh_cols, b_hi, sp.idesc_rest, 1u);
                                 } else {
-                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, idesc_t[t], 1u);
+                                    tc_mma_issue(elected, dcol, a_lo, a_hi, b_lo, b_hi, sp.idesc_t[t], 1u);
                                 }
                             }
-                            if (kh == 0 && kw == 0) {
-                                const bool wrap = (stage + 1 == p.nstages);
-                                probed = mbar_test(smem_u32(full + (wrap ? 0 : stage + 1)), (uint32_t)(wrap ? sphase ^ 1 : sphase));
-                            }
+                            if (kh == 0 && kw == 0)
+                                probed = mbar_test(smem_u32(full + stage_n), (uint32_t)(wrap ? sphase ^ 1 : sphase));
+                            if (KT == 1) nx = slab_par(d_in + 1, cg, stage_n, w16, set_base, g);
                         }
                         if (WSPLIT && d_in == g.dhi)                        // last slab of the group: part kh may be reloaded
                             tc_commit_if(elected, smem_u32(w3empty + kh));
                     }
                     tc_commit_if(elected, smem_u32(empty + stage));
                     if (++stage == p.nstages) { stage = 0; sphase ^= 1; }
+                    sp = nx;
                 }
                 if (p.wsplit) ++wuse;
                 else if (!p.wres) {
