@@ -577,7 +577,7 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const uint32_t tap16 = (uint32_t)(p.nbt * p.btile_bytes) >> 4;            // weight bytes per (kh,kw) / 16
         const uint32_t set_cols = (uint32_t)(p.ngroups * p.Dc * p.NP);
         const uint32_t stages16 = smem_u32(stages) >> 4, stride16 = (uint32_t)p.stage_stride >> 4;   // (128 B multiples)
-        int stage = 0, sphase = 0, wb = 0, wphase = 0, it = 0, wuse = 0;
+        int stage = 0, sphase = 0, wb = 0, wphase = 0, set_run = 0, aphase_run = 0, wuse = 0;
         uint32_t probed = 0;     // the NEXT stage's full barrier, tested while this stage's MMAs issue (tcgen05.mma issue
                                  // is synchronous with the pipe: a barrier round trip between slabs is a tensor-pipe bubble)
         TC_PROF_DECL;
@@ -628,8 +628,8 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, cur.next(p)) {
             const ItemGeom g = decode_item(p, cur);
             if (item_skipped(p, g)) continue;
-            const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
-            ++it;
+            const int set = set_run, aphase = aphase_run;      // (running counters: it % nsets was an integer division per item)
+            if (++set_run == p.nsets) { set_run = 0; aphase_run ^= 1; }
             TC_PROF_WAIT(mbar_wait(smem_u32(accempty + set), aphase ^ 1, 201));
             tc_fence_after();
             const uint32_t set_base = tmem_base + (uint32_t)set * set_cols;
@@ -712,15 +712,15 @@ lea_conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         const int m = q * 32 + lane;                 // tile row = TMEM lane
         const int lh = m >> p.tw_log2, lw = m & ((1 << p.tw_log2) - 1);
         const int64_t sp = (int64_t)p.D * p.H * p.W;
-        int it = 0;
+        int set_run = 0, aphase_run = 0;
         TC_PROF_DECL;
         ItemCursor cur;
         cur.init(p, blockIdx.x);
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, cur.next(p)) {
             const ItemGeom g = decode_item(p, cur);
             if (item_skipped(p, g)) continue;
-            const int set = it % p.nsets, aphase = (it / p.nsets) & 1;
-            ++it;
+            const int set = set_run, aphase = aphase_run;      // (running counters: it % nsets was an integer division per item)
+            if (++set_run == p.nsets) { set_run = 0; aphase_run ^= 1; }
             TC_PROF_ITEM;
             const int h = g.h0 + lh, w = g.w0 + lw, w_item = w;
             const bool valid = (h < p.H) && (FLAT || w < p.W);
